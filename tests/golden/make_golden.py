@@ -1,0 +1,283 @@
+#!/usr/bin/env python3
+"""Record golden vectors from the UNMODIFIED r2p2 reference.  Build-container only.
+
+    python tests/golden/make_golden.py            # rewrites tests/golden/*.npz
+
+The reference ships no tests or fixtures, so parity is pinned by running
+the reference itself (tests/golden/ref_harness.py, recipe of SURVEY.md section 8c) and committing
+what it returns.  The GPU box has no /root/reference; tests there read only these files.
+
+Three fixture files (float64 values are stored as-is, i.e. bit-exact):
+  rays.npz      raw `utils.search_edge_in_angle_with_limit` calls (reference utils.py:420-432):
+                integer and float origins, several limits, three stages; hit point, distance and
+                the number of pixels the loop tested (counted through an ndarray subclass).
+  ticks.npz     single `Robot.update` calls from random states with a scripted command (a
+                Controller subclass returning a fixed (speed, angular_velocity)): everything the
+                tick produces except the MLP -- sonar distances, raw ray hits, new pose, collide
+                calls, exceptions.
+  episodes.npz  free-running episodes with the reference's own Neuro_controller (sklearn MLP),
+                Inspyred_controller (linear) and a constant command (KAT2/KAT3/KAT4 of SURVEY 8c).
+ulp-level digits are specific to this image (glibc 2.39, numpy 2.3.5 / OpenBLAS 0.3.30, AVX-512
+Xeon); the environment is recorded in each file's `meta`.
+"""
+import contextlib
+import io
+import json
+import math
+import os
+import platform
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import ref_harness  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+STAGES = ["track_2.png", "stage.png", "track.png"]
+
+
+class CountingEnv(np.ndarray):
+    """env whose .item() calls are counted (= pixels tested by the ray loops)."""
+    count = 0
+
+    def item(self, *a):
+        CountingEnv.count += 1
+        return super().item(*a)
+
+
+def counting(env):
+    return np.ascontiguousarray(env).view(CountingEnv)
+
+
+def meta():
+    import sklearn
+    return json.dumps({"python": platform.python_version(), "numpy": np.__version__, "sklearn": sklearn.__version__,
+                       "libc": platform.libc_ver()[1], "machine": platform.machine(),
+                       "cpu_flags": [f for f in open("/proc/cpuinfo").read().split("flags")[1].split("\n")[0].split()
+                                     if f in ("fma", "avx2", "avx512f")]})
+
+
+def free_points(env, rng, n, clearance):
+    """Random float positions whose whole crash-radius disc is free (valid last_pos)."""
+    W, H = env.shape
+    wall = (np.asarray(env) == 0)
+    pts = []
+    while len(pts) < n:
+        x = rng.uniform(clearance + 1, W - clearance - 2)
+        y = rng.uniform(clearance + 1, H - clearance - 2)
+        x0, x1, y0, y1 = int(x - clearance - 1), int(x + clearance + 2), int(y - clearance - 1), int(y + clearance + 2)
+        if not wall[x0:x1, y0:y1].any():
+            pts.append((x, y))
+    return pts
+
+
+def near_wall_points(env, rng, n, radius):
+    """Free positions 5..9 px from some wall pixel (so that moves collide)."""
+    W, H = env.shape
+    wall = (np.asarray(env) == 0)
+    pts = []
+    while len(pts) < n:
+        x = rng.uniform(radius + 2, W - radius - 3)
+        y = rng.uniform(radius + 2, H - radius - 3)
+        r_in, r_out = int(radius + 1), int(radius + 5)
+        xi, yi = int(x), int(y)
+        if wall[xi - r_in:xi + r_in + 1, yi - r_in:yi + r_in + 1].any():
+            continue
+        if wall[max(0, xi - r_out):xi + r_out + 1, max(0, yi - r_out):yi + r_out + 1].any():
+            pts.append((x, y))
+    return pts
+
+
+def gen_rays(E):
+    u = E.u
+    rng = np.random.RandomState(20261019)
+    rec = {k: [] for k in ("stage", "ox", "oy", "angle", "limit", "hit", "hx", "hy", "dst", "nsamp")}
+    for si, stage in enumerate(STAGES):
+        env = counting(E.load_env(stage))
+        W, H = env.shape
+        cases = []
+        # KAT1 of SURVEY 8c first
+        if stage == "track_2.png":
+            cases += [((230, 250), math.radians(a), 30) for a in (0, 45, 70, 290, 315)]
+            cases += [((193, 249), math.radians(a), 55) for a in range(0, 360, 45)]
+        if stage == "stage.png":
+            cases += [((260, 200), math.radians(a), 30) for a in (0, 45, 70, 290, 315)]
+        for _ in range(1400):   # integer origins, integer limits (the sonar case, knife edge H5)
+            o = (int(rng.randint(1, W - 1)), int(rng.randint(1, H - 1)))
+            cases.append((o, math.radians(rng.uniform(-720, 720)), int(rng.choice([30, 45, 55]))))
+        for _ in range(300):    # exact multiples of 45 degrees plus heading offsets that are integers
+            o = (int(rng.randint(1, W - 1)), int(rng.randint(1, H - 1)))
+            cases.append((o, math.radians(float(rng.randint(-8, 16) * 45)), 30))
+        for _ in range(800):    # float origins, float limits (the collision ray)
+            o = (float(rng.uniform(1, W - 2)), float(rng.uniform(1, H - 2)))
+            cases.append((o, math.radians(rng.uniform(0, 360)), float(rng.uniform(5.0, 12.0))))
+        for _ in range(200):    # rays that leave the map / start near the border
+            o = (float(rng.uniform(-3, W + 3)), float(rng.uniform(-3, H + 3)))
+            cases.append((o, math.radians(rng.uniform(0, 360)), float(rng.uniform(3.0, 60.0))))
+        for (o, ang, lim) in cases:
+            CountingEnv.count = 0
+            try:
+                res = u.search_edge_in_angle_with_limit(o, ang, env, lim)
+                hit = int(res != (-1, -1))
+            except IndexError:
+                res, hit = (-1, -1), -1
+            ns = CountingEnv.count
+            d = float(np.linalg.norm((res[0] - o[0], res[1] - o[1]))) if hit == 1 else math.inf
+            for k, v in zip(rec, (si, o[0], o[1], ang, lim, hit, res[0], res[1], d, ns)):
+                rec[k].append(v)
+    np.savez_compressed(os.path.join(OUT, "rays.npz"), meta=meta(), stages=np.array(STAGES),
+                        **{k: np.asarray(v, dtype=(np.int32 if k in ("stage", "hit", "nsamp") else np.float64))
+                           for k, v in rec.items()})
+    print("rays:", len(rec["hit"]), "hits", sum(1 for h in rec["hit"] if h == 1), "faults", sum(1 for h in rec["hit"] if h < 0))
+
+
+def make_scripted(E):
+    class Scripted(E.ctrl.Controller):
+        """Harness controller: returns the command it was given; counts collide() calls."""
+        def __init__(self):
+            super().__init__("SCRIPTED", None)
+            self.cmd = (0.0, 0.0)
+            self.ncollide = 0
+
+        def control(self, dst):
+            return self.cmd
+
+        def on_collision(self, pos):
+            self.ncollide += 1
+    return Scripted
+
+
+def gen_ticks(E):
+    u = E.u
+    Scripted = make_scripted(E)
+    rng = np.random.RandomState(77)
+    raw = []
+    orig = u.search_edge_in_angle_with_limit
+
+    def spy(origin, angle, image, limit):
+        res = orig(origin, angle, image, limit)
+        raw.append(res)
+        return res
+    u.search_edge_in_angle_with_limit = spy
+    keys = ("stage", "robot", "delta", "x", "y", "theta", "v", "w", "nx", "ny", "ntheta", "nspeed", "ncollide", "exc",
+            "nlast_x", "nlast_y", "nsamp")
+    rec = {k: [] for k in keys}
+    dsts, rays_hit = [], []
+    robots = ["robot-neuro.json", "robot_omni.json", "robot-track.json"]
+    try:
+        for si, stage in enumerate(STAGES):
+            env = counting(E.load_env(stage))
+            for ri, rj in enumerate(robots):
+                ctrl = Scripted()
+                with contextlib.redirect_stdout(io.StringIO()):
+                    r = E.make_robot(rj, ctrl)
+                n = 700 if ri == 0 else 350
+                pts = free_points(env, rng, n // 2, r.radius + 1) + near_wall_points(env, rng, n - n // 2, r.radius)
+                for i, (x, y) in enumerate(pts):
+                    theta = float(rng.uniform(-400, 400)) if i % 5 else float(rng.randint(-4, 9) * 45)
+                    v = float(rng.uniform(-60, 60)) if i % 7 else 0.0
+                    w = float(rng.uniform(-90, 90))
+                    delta = 0.1 if i % 4 else float(rng.choice([0.033, 0.5, 1.0]))
+                    r.x, r.y, r.orientation, r.last_pos = x, y, theta, (x, y)
+                    ctrl.cmd, ctrl.ncollide = (v, w), 0
+                    raw.clear()
+                    CountingEnv.count = 0
+                    exc = 0
+                    try:
+                        r.update(env, delta, False)
+                    except IndexError:
+                        exc = 1
+                        import threading
+                        r.lock = threading.Lock()
+                    R = len(ctrl.dst)
+                    d = np.full(8, np.nan)
+                    d[:R] = ctrl.dst
+                    dsts.append(d)
+                    h = np.full((9, 2), np.nan)
+                    for j, p in enumerate(raw[:9]):
+                        h[j] = p
+                    rays_hit.append(h)
+                    for k, val in zip(keys, (si, ri, delta, x, y, theta, v, w, r.x, r.y, r.orientation, r.speed,
+                                             ctrl.ncollide, exc, r.last_pos[0], r.last_pos[1], CountingEnv.count)):
+                        rec[k].append(val)
+    finally:
+        u.search_edge_in_angle_with_limit = orig
+    np.savez_compressed(os.path.join(OUT, "ticks.npz"), meta=meta(), stages=np.array(STAGES), robots=np.array(robots),
+                        dst=np.asarray(dsts), raw_hits=np.asarray(rays_hit),
+                        **{k: np.asarray(v, dtype=(np.int32 if k in ("stage", "robot", "ncollide", "exc", "nsamp") else np.float64))
+                           for k, v in rec.items()})
+    print("ticks:", len(rec["x"]), "with collide", sum(1 for c in rec["ncollide"] if c), "exceptions", sum(rec["exc"]))
+
+
+def gen_episodes(E):
+    Scripted = make_scripted(E)
+    out = {}
+    specs = []
+
+    def run(name, stage, robot_json, ctrl, T, genome, kind, layers=(), delta=0.1):
+        env = counting(E.load_env(stage))
+        with contextlib.redirect_stdout(io.StringIO()):
+            r = E.make_robot(robot_json, ctrl)
+        ncol = [0]
+        orig = ctrl.on_collision
+
+        def oc(pos):
+            ncol[0] += 1
+            orig(pos)
+        ctrl.on_collision = oc
+        R = len(r.sensors) if isinstance(r.sensors, list) else len(range(0, 360, math.floor(365 / r.sensors)))
+        pose = np.zeros((T, 5)); dst = np.zeros((T, R)); ncoll = np.zeros(T, dtype=np.int32); fit = np.zeros(T); nsamp = np.zeros(T, dtype=np.int32)
+        for t in range(T):
+            CountingEnv.count = 0
+            r.update(env, delta, False)
+            pose[t] = (r.x, r.y, r.orientation, r.speed, r.angular_velocity)
+            dst[t] = ctrl.dst
+            ncoll[t] = ncol[0]
+            nsamp[t] = CountingEnv.count
+            fit[t] = ctrl.fitness() if hasattr(ctrl, "fitness") else 0.0
+        out[name + "/pose"] = pose; out[name + "/dst"] = dst; out[name + "/ncoll"] = ncoll
+        out[name + "/fitness"] = fit; out[name + "/genome"] = np.asarray(genome, dtype=np.float64); out[name + "/nsamp"] = nsamp
+        specs.append({"name": name, "stage": stage, "robot": robot_json, "T": T, "kind": kind, "layers": list(layers), "delta": delta})
+        print("episode", name, "T", T, "collides", ncol[0], "fitness", repr(float(fit[-1])))
+
+    # KAT2: neuro 5-10-7-4-2 on track_2
+    w = np.random.RandomState(1).uniform(-1, 1, 156)
+    run("kat2_neuro", "track_2.png", "robot-neuro.json", E.neuro_controller(w, [10, 7, 4]), 1000, w, "neuro", (5, 10, 7, 4, 2))
+    for seed in (2, 3, 4):
+        w = np.random.RandomState(seed).uniform(-1, 1, 156)
+        run("neuro_stage_s%d" % seed, "stage.png", "robot-neuro.json", E.neuro_controller(w, [10, 7, 4]), 400, w, "neuro", (5, 10, 7, 4, 2))
+    w = np.random.RandomState(5).uniform(-1, 1, 7)
+    run("neuro_simple_track", "track.png", "robot-track.json", E.neuro_controller(w, [1]), 400, w, "neuro", (5, 1, 2))
+    # KAT3: linear controller, 8 int-form sonars
+    c = np.random.RandomState(7).uniform(-1, 1, 18) * 0.05
+    run("kat3_linear", "track_2.png", "robot_omni.json", E.linear_controller(c), 300, c, "linear")
+    for seed in (8, 9):
+        c = np.random.RandomState(seed).uniform(-1, 1, 18) * 0.03
+        run("linear_s%d" % seed, "track_2.png", "robot_omni.json", E.linear_controller(c), 300, c, "linear")
+    c = np.random.RandomState(10).uniform(-1, 1, 12) * 0.08     # BASELINE C2: robot-neuro ring + linear, G = 12
+    run("linear_neuro_ring", "track_2.png", "robot-neuro.json", E.linear_controller(c), 300, c, "linear")
+    # KAT4: constant command into a wall
+    sc = Scripted(); sc.cmd = (30.0, 2.0)
+    run("kat4_const", "track_2.png", "robot-neuro.json", sc, 100, [30.0, 2.0], "const")
+    sc = Scripted(); sc.cmd = (-12.5, -7.0)
+    run("const_stage", "stage.png", "robot.json", sc, 300, [-12.5, -7.0], "const")
+    np.savez_compressed(os.path.join(OUT, "episodes.npz"), meta=meta(), specs=json.dumps(specs), **out)
+
+
+def main():
+    E = ref_harness.RefEnv()
+    try:
+        gen_rays(E)
+        gen_ticks(E)
+        gen_episodes(E)
+        # stage bitmaps as the reference loads them (env[x, y], int32) -- fixtures for the GPU box
+        for stage in STAGES:
+            env = np.ascontiguousarray(E.load_env(stage)).astype(np.uint8)
+            np.savez_compressed(os.path.join(OUT, "stage_" + stage.replace(".png", "") + ".npz"), env=env)
+    finally:
+        E.close()
+
+
+if __name__ == "__main__":
+    main()
