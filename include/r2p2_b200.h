@@ -1,0 +1,155 @@
+/* r2p2_b200.h -- C ABI of the B200-native batched robot-step core for r2p2.
+ *
+ * This is the drop-in boundary for r2p2's one data-parallel hot path: a
+ * whole population of robots x ticks is evaluated per call instead of one Python `Robot.update`
+ * per robot per frame.  Plain C types only; caller owns host buffers, the library owns device
+ * memory behind the opaque handle.  Every call returns 0 on success or a negative R2P2_E_* code;
+ * the message is available from r2p2_last_error().  Nothing here ever falls back to the CPU: if
+ * there is no CUDA device, r2p2_create fails.
+ *
+ * Reference interfaces replaced (paths under the r2p2 repository):
+ *   r2p2_set_stage        <- utils.load_image + transpose          r2p2/utils.py:273-280, 302-303
+ *   r2p2_set_robot        <- utils.create_robot / Robot.__init__   r2p2/utils.py:133-163, r2p2/robot.py:50-96
+ *   r2p2_set_controller   <- controllers.load_controller + Neuro_controller.__build_network /
+ *                            Inspyred_controller.set_network_params
+ *                                                                  r2p2/controllers/controllers.py:20-39,
+ *                                                                  r2p2/controllers/neurocontroller.py:106-127,
+ *                                                                  r2p2/controllers/inspyred.py:132-144
+ *   r2p2_upload_genomes   <- evolution.write_params -> ../res/weights.json -> set_network_params
+ *                                                                  r2p2/evolution.py:24-27,
+ *                                                                  r2p2/controllers/neurocontroller.py:139-160,168-178
+ *   r2p2_reset            <- Controller.register_robot + episode reset
+ *                                                                  r2p2/controllers/neurocontroller.py:77-85,100-104
+ *   r2p2_run              <- the simulator loop `for r in robots: r.update(npdata, delta, True)`
+ *                                                                  r2p2/utils.py:226-227, 233-234; r2p2/robot.py:389-402
+ *   r2p2_read_fitness     <- Neuro_controller.fitness / __output_fitness -> ../res/fitness.txt -> evaluate_ann
+ *                                                                  r2p2/controllers/neurocontroller.py:62-65,129-131,
+ *                                                                  r2p2/evolution.py:29-52
+ *   r2p2_read_state       <- Robot attributes x, y, orientation, speed, angular_velocity  r2p2/robot.py:63-75
+ *   r2p2_read_trace       <- the per-tick sensor log (dst per ray)   r2p2/robot.py:337-352 and controller.dst
+ */
+#ifndef R2P2_B200_H
+#define R2P2_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct r2p2_sim* r2p2_handle;
+
+/* error codes */
+#define R2P2_OK 0
+#define R2P2_E_ARG (-1)      /* bad argument / call order      */
+#define R2P2_E_CUDA (-2)     /* CUDA runtime error             */
+#define R2P2_E_NODEV (-3)    /* no usable CUDA device          */
+#define R2P2_E_LIMIT (-4)    /* exceeds a compiled-in limit    */
+
+/* controller kinds (r2p2_set_controller) */
+#define R2P2_CTRL_CONST 0    /* genome = [speed, angular_velocity]: naive_controller.py generalised   */
+#define R2P2_CTRL_NEURO 1    /* neurocontroller.Neuro_controller: MLP, genome = flat C-order weights  */
+#define R2P2_CTRL_LINEAR 2   /* inspyred.Inspyred_controller: [l_1..l_n, a_1..a_n, vmaxlin, vmaxang]  */
+
+/* activations (sklearn names) */
+#define R2P2_ACT_IDENTITY 0
+#define R2P2_ACT_TANH 1
+#define R2P2_ACT_RELU 2
+#define R2P2_ACT_LOGISTIC 3
+
+/* per-robot flag bits (r2p2_read_state) */
+#define R2P2_F_COLLIDED 1u   /* Robot.collide() was called at least once                               */
+#define R2P2_F_FAULT 2u      /* the reference would have raised (IndexError off-map, ValueError on NaN) */
+#define R2P2_F_DONE 4u       /* evolve mode: the episode ended (timer ran out or collision)             */
+#define R2P2_F_TRIGRANGE 8u  /* heading beyond the supported sin/cos range (|radians| >= 105414350)     */
+
+/* limits */
+#define R2P2_MAX_RAYS 64
+#define R2P2_MAX_LAYERS 8
+#define R2P2_MAX_WIDTH 64
+
+/* lanes-per-robot choices for r2p2_set_mapping (0 = let the library choose from P) */
+#define R2P2_LPR_AUTO 0
+
+/* ---- lifetime ---------------------------------------------------------------------------- */
+int r2p2_create(int device, r2p2_handle* out);
+int r2p2_destroy(r2p2_handle h);
+const char* r2p2_last_error(r2p2_handle h);            /* h may be NULL: error of the last failed create */
+int r2p2_version(void);
+
+/* ---- configuration ------------------------------------------------------------------------- */
+/* Stage as the reference holds it after the transpose: levels[x*H + y], grey level 0..255
+ * (0 = wall; 50 = the "crash" level tested at robot.py:249).  Packed on the device into
+ * 1-bit planes (level==0, level==50). */
+int r2p2_set_stage(r2p2_handle h, const uint8_t* levels_xy, int32_t W, int32_t H);
+/* Same from the reference's own int32 array (npdata after flipud(rot90)). */
+int r2p2_set_stage_i32(r2p2_handle h, const int32_t* levels_xy, int32_t W, int32_t H);
+
+/* Robot json: sonar_range = [vr0, vr1], radius, max_speed, ray angles in degrees (list form, or the
+ * int form already expanded by the host as range(0, 360, floor(365/n))). */
+int r2p2_set_robot(r2p2_handle h, double vr0, double vr1, double radius, double max_speed,
+                   const double* ray_deg, int32_t n_rays);
+
+/* kind = R2P2_CTRL_*; NEURO: layers = [n_rays, hidden..., 2] (n_layers entries), activation = R2P2_ACT_*.
+ * For CONST / LINEAR pass layers = NULL, n_layers = 0. */
+int r2p2_set_controller(r2p2_handle h, int32_t kind, const int32_t* layers, int32_t n_layers, int32_t activation);
+
+/* Thread mapping: lanes per robot (1, 2, 4, 8, 16, 32) or R2P2_LPR_AUTO; stage_in_smem: 1 force the
+ * shared-memory copy of the bit planes, 0 read them through L1/L2, -1 choose. */
+int r2p2_set_mapping(r2p2_handle h, int32_t lanes_per_robot, int32_t stage_in_smem);
+
+/* ---- population ---------------------------------------------------------------------------- */
+/* genomes: [P][G] row-major doubles in HOST memory; copied to the device (async on the handle's stream,
+ * the buffer may be reused when the call returns only if it is pageable; pinned buffers must stay
+ * valid until the next synchronising call). */
+int r2p2_upload_genomes(r2p2_handle h, const double* genomes, int32_t P, int32_t G);
+/* Same, from a DEVICE pointer (e.g. a torch tensor's data_ptr on the same device). */
+int r2p2_set_genomes_device(r2p2_handle h, const double* d_genomes, int32_t P, int32_t G);
+
+/* (Re)start every robot: pose from x0/y0/theta0 (n = 1: broadcast one pose, n = P: per robot),
+ * speed = 0, odometry/origin = pose, distance = 0, flags = 0, controller timer = time_budget. */
+int r2p2_reset(r2p2_handle h, const double* x0, const double* y0, const double* theta0, int32_t n, double time_budget);
+
+/* ---- execution ----------------------------------------------------------------------------- */
+/* Advance every robot by up to T ticks of Robot.update(env, delta) in ONE kernel launch (state stays in
+ * registers across ticks).  delta_ctrl is what the controller subtracts from its timer per control()
+ * call (utils.delta, in the controller's own unit).  evolve != 0: neurocontroller.py:72-85 episode
+ * semantics -- a robot stops at the control() call where its timer is <= 0 (a collision zeroes the
+ * timer) and its fitness is frozen there.  evolve == 0: free run for T ticks.  Asynchronous. */
+int r2p2_run(r2p2_handle h, int32_t T, double delta, double delta_ctrl, int32_t evolve);
+int r2p2_sync(r2p2_handle h);
+/* Device time of the most recent r2p2_run kernel in milliseconds (CUDA events on the handle's stream). */
+int r2p2_last_run_ms(r2p2_handle h, float* ms);
+
+/* ---- results (each synchronises) ------------------------------------------------------------ */
+int r2p2_read_fitness(r2p2_handle h, double* fitness /*[P]*/);
+/* Any pointer may be NULL. Arrays of P elements. */
+int r2p2_read_state(r2p2_handle h, double* x, double* y, double* theta, double* speed, double* omega,
+                    uint32_t* flags, uint32_t* ncollide, uint32_t* ticks);
+/* Totals over the population since the last reset: sonar-ray samples, collision-ray samples (pixels the
+ * reference semantics test), executed robot-steps. */
+int r2p2_read_counters(r2p2_handle h, uint64_t* sonar_samples, uint64_t* collision_samples, uint64_t* robot_steps);
+/* Device pointer of the fitness vector [P] (for a collective issued by the caller, e.g. NCCL all-gather). */
+int r2p2_fitness_device(r2p2_handle h, double** d_fitness);
+/* Kernels launched by this handle since creation (every one is ours; no library kernels are used). */
+int r2p2_launch_count(r2p2_handle h, uint64_t* n);
+
+/* ---- per-tick trace (parity tests, Robot.update facade) -------------------------------------- */
+/* Enable recording for the next runs: up to T_max ticks per run, layouts [T][P][...]. */
+int r2p2_set_trace(r2p2_handle h, int32_t enable, int32_t T_max);
+/* pose [T][P][5] = x, y, theta, speed, omega after the tick; dst [T][P][R] distances handed to the
+ * controller; hitk [T][P][R] hit step or -1; hitpx [T][P][R][2] hit pixel or -1; nsamp [T][P][R] pixels
+ * tested per ray; ncoll [T][P] collide() calls in the tick.  Any pointer may be NULL. */
+int r2p2_read_trace(r2p2_handle h, int32_t T, double* pose, double* dst, int32_t* hitk, int32_t* hitpx,
+                    uint32_t* nsamp, uint32_t* ncoll);
+
+/* ---- raw ray-caster (utils.search_edge_in_angle_with_limit, r2p2/utils.py:420-432) --------------- */
+/* n independent rays against the current stage; host arrays in, host arrays out.
+ * status: 1 hit, 0 miss, -1 fault (IndexError in the reference). */
+int r2p2_cast_rays(r2p2_handle h, int32_t n, const double* ox, const double* oy, const double* angle_rad,
+                   const double* limit, int32_t* status, double* hx, double* hy, int32_t* k, uint32_t* nsamp);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* R2P2_B200_H */

@@ -1,0 +1,615 @@
+// r2p2_capi.cu -- C ABI (include/r2p2_b200.h) over the sm_100a kernels in r2p2_kernels.cuh.
+//
+// Host side of the drop-in boundary: owns the device buffers (bit-packed stage, SoA robot state,
+// genomes), picks the lane mapping and launches exactly one episode kernel per r2p2_run.  CUDA runtime
+// only -- no torch types, no library kernels, no CPU fallback.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "r2p2_kernels.cuh"
+
+using namespace r2p2;
+
+namespace {
+std::string g_create_error;
+
+struct StateArrays {
+    double *x = nullptr, *y = nullptr, *theta = nullptr, *speed = nullptr, *omega = nullptr, *last_x = nullptr, *last_y = nullptr,
+           *dist = nullptr, *odom_x = nullptr, *odom_y = nullptr, *origin_x = nullptr, *origin_y = nullptr, *time = nullptr,
+           *fitness = nullptr;
+    uint32_t *flags = nullptr, *ncollide = nullptr, *ticks = nullptr;
+    unsigned long long *nsamp_sonar = nullptr, *nsamp_coll = nullptr;
+};
+}  // namespace
+
+struct r2p2_sim {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool ev_valid = false;
+    std::string err;
+    int sm_count = 0;
+    size_t smem_optin = 0;
+    // stage
+    int W = 0, H = 0, wpr = 0, has50 = 0;
+    uint32_t plane_bytes = 0;
+    uint32_t *d_wall = nullptr, *d_l50 = nullptr;
+    // robot
+    bool have_robot = false;
+    int R = 0;
+    double ray_deg[R2P2_MAX_RAYS];
+    double vr0 = 0, vr1 = 0, radius = 0, max_speed = 0;
+    double* d_crxy = nullptr;
+    double* d_sincostab = nullptr;
+    // controller
+    bool have_ctrl = false;
+    int kind = 0, n_layers = 0, activation = 0, maxw = 1;
+    int layers[R2P2_MAX_LAYERS];
+    // population
+    int P = 0, G = 0;
+    double* d_genomes = nullptr;     // [P][G]
+    double* d_genomes_t = nullptr;   // [G][P], built lazily for the 1-lane mapping
+    size_t genomes_cap = 0;
+    bool genomes_t_valid = false;
+    bool have_genomes = false, have_reset = false;
+    StateArrays st;
+    int state_cap = 0;
+    double *d_x0 = nullptr, *d_y0 = nullptr, *d_t0 = nullptr;
+    // mapping
+    int lpr_req = 0, smem_req = -1;
+    // trace
+    bool trace = false;
+    int trace_T = 0, trace_P = 0, trace_R = 0;
+    double *tr_pose = nullptr, *tr_dst = nullptr;
+    int32_t *tr_hitk = nullptr, *tr_hitpx = nullptr;
+    uint32_t *tr_nsamp = nullptr, *tr_ncoll = nullptr;
+    // scheduling / counters
+    unsigned int* d_work = nullptr;
+    unsigned long long* d_cnt3 = nullptr;
+    uint64_t launches = 0;
+};
+
+namespace {
+
+int fail(r2p2_handle h, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) return fail(h, R2P2_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+template <typename T>
+cudaError_t dalloc(T** p, size_t n) {
+    if (*p) { cudaFree(*p); *p = nullptr; }
+    return cudaMalloc(reinterpret_cast<void**>(p), std::max<size_t>(n, 1) * sizeof(T));
+}
+
+int ensure_state(r2p2_handle h, int P) {
+    if (P <= h->state_cap) return R2P2_OK;
+    StateArrays& s = h->st;
+    double** dbl[] = {&s.x, &s.y, &s.theta, &s.speed, &s.omega, &s.last_x, &s.last_y, &s.dist, &s.odom_x, &s.odom_y,
+                      &s.origin_x, &s.origin_y, &s.time, &s.fitness, &h->d_x0, &h->d_y0, &h->d_t0};
+    for (double** p : dbl) CK(dalloc(p, (size_t)P));
+    CK(dalloc(&s.flags, (size_t)P)); CK(dalloc(&s.ncollide, (size_t)P)); CK(dalloc(&s.ticks, (size_t)P));
+    CK(dalloc(&s.nsamp_sonar, (size_t)P)); CK(dalloc(&s.nsamp_coll, (size_t)P));
+    h->state_cap = P;
+    h->have_reset = false;
+    return R2P2_OK;
+}
+
+int ensure_genomes(r2p2_handle h, int P, int G) {
+    const size_t need = (size_t)P * (size_t)G;
+    if (need > h->genomes_cap) {
+        CK(dalloc(&h->d_genomes, need));
+        CK(dalloc(&h->d_genomes_t, need));
+        h->genomes_cap = need;
+    }
+    if (P != h->P) h->have_reset = false;
+    h->P = P; h->G = G;
+    h->genomes_t_valid = false;
+    return ensure_state(h, P);
+}
+
+void free_trace(r2p2_handle h) {
+    cudaFree(h->tr_pose); cudaFree(h->tr_dst); cudaFree(h->tr_hitk); cudaFree(h->tr_hitpx); cudaFree(h->tr_nsamp); cudaFree(h->tr_ncoll);
+    h->tr_pose = h->tr_dst = nullptr; h->tr_hitk = h->tr_hitpx = nullptr; h->tr_nsamp = h->tr_ncoll = nullptr;
+    h->trace_T = h->trace_P = h->trace_R = 0;
+}
+
+int pack_stage(r2p2_handle h, const uint8_t* d_levels, int W, int H) {
+    const int wpr = (W + 31) / 32;
+    size_t bytes = (size_t)wpr * 4 * (size_t)H;
+    bytes = (bytes + 15) & ~(size_t)15;
+    CK(dalloc(&h->d_wall, bytes / 4));
+    CK(dalloc(&h->d_l50, bytes / 4));
+    CK(cudaMemsetAsync(h->d_wall, 0, bytes, h->stream));
+    CK(cudaMemsetAsync(h->d_l50, 0, bytes, h->stream));
+    int* d_has = nullptr;
+    CK(cudaMalloc(&d_has, sizeof(int)));
+    CK(cudaMemsetAsync(d_has, 0, sizeof(int), h->stream));
+    dim3 grid((H + 127) / 128, wpr);
+    pack_stage_kernel<<<grid, 128, 0, h->stream>>>(d_levels, W, H, wpr, h->d_wall, h->d_l50, d_has);
+    h->launches++;
+    CK(cudaGetLastError());
+    int has = 0;
+    CK(cudaMemcpyAsync(&has, d_has, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    cudaFree(d_has);
+    h->W = W; h->H = H; h->wpr = wpr; h->has50 = has; h->plane_bytes = (uint32_t)bytes;
+    return R2P2_OK;
+}
+
+int upload_crxy(r2p2_handle h) {
+    // robot.py:183 `math.cos(math.radians(i)) * self.radius`: per-config constants.  Evaluated on the host with the
+    // same glibc-exact sin/cos restatement the device uses, so the numbers do not depend on the host's libm build.
+    std::vector<double> t(720);
+    for (int i = 0; i < 360; ++i) {
+        const double a = (double)i * kRad;
+        t[i] = r2p2_cos(a, r2p2_h_sincostab, nullptr) * h->radius;
+        t[360 + i] = r2p2_sin(a, r2p2_h_sincostab, nullptr) * h->radius;
+    }
+    if (!h->d_crxy) CK(dalloc(&h->d_crxy, (size_t)720));
+    CK(cudaMemcpyAsync(h->d_crxy, t.data(), 720 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return R2P2_OK;
+}
+
+template <int LPR, bool SMEM>
+int launch_episode(r2p2_handle h, const KParams& kp, size_t smem) {
+    auto kern = episode_kernel<LPR, SMEM>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kBlock, smem));
+    if (occ < 1) return fail(h, R2P2_E_LIMIT, "episode kernel does not fit on an SM (smem %zu bytes)", smem);
+    const int robots_per_cta = kBlock / LPR;
+    long long ctas = ((long long)kp.P + robots_per_cta - 1) / robots_per_cta;
+    ctas = std::min<long long>(ctas, (long long)occ * h->sm_count);   // persistent: the work counter feeds the rest
+    CK(cudaMemsetAsync(h->d_work, 0, sizeof(unsigned int), h->stream));
+    CK(cudaEventRecord(h->ev0, h->stream));
+    kern<<<(unsigned)ctas, kBlock, smem, h->stream>>>(kp);
+    CK(cudaEventRecord(h->ev1, h->stream));
+    h->ev_valid = true;
+    h->launches++;
+    CK(cudaGetLastError());
+    return R2P2_OK;
+}
+
+template <int LPR>
+int launch_episode_s(r2p2_handle h, const KParams& kp, bool smem_stage) {
+    const size_t smem = episode_smem_bytes(LPR, smem_stage, kp.plane_bytes, kp.has50, kp.maxw);
+    return smem_stage ? launch_episode<LPR, true>(h, kp, smem) : launch_episode<LPR, false>(h, kp, smem);
+}
+
+int choose_lpr(const r2p2_handle h) {
+    if (h->lpr_req) return h->lpr_req;
+    const long long lanes_wanted = (long long)h->sm_count * 1024;   // ~half of the resident-thread capacity
+    if ((long long)h->P >= lanes_wanted) return 1;
+    if ((long long)h->P * 8 >= lanes_wanted) return 8;
+    return 32;
+}
+
+}  // namespace
+
+extern "C" {
+
+int r2p2_version(void) { return 100; }
+
+const char* r2p2_last_error(r2p2_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int r2p2_create(int device, r2p2_handle* out) {
+    r2p2_handle h = nullptr;
+    if (!out) return fail(nullptr, R2P2_E_ARG, "out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(nullptr, R2P2_E_NODEV, "no CUDA device: %s (this library has no CPU fallback)", cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail(nullptr, R2P2_E_ARG, "device %d out of range (have %d)", device, n);
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return fail(nullptr, R2P2_E_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major != 10)
+        return fail(nullptr, R2P2_E_NODEV, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+    r2p2_sim* s = new r2p2_sim();
+    h = s;
+    s->device = device;
+    s->sm_count = prop.multiProcessorCount;
+    s->smem_optin = prop.sharedMemPerBlockOptin;
+    e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&s->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&s->ev1);
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_work, sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_cnt3, 3 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_sincostab, R2P2_SINCOSTAB_LEN * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemcpy(s->d_sincostab, r2p2_h_sincostab, R2P2_SINCOSTAB_LEN * sizeof(double), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        fail(nullptr, R2P2_E_CUDA, "r2p2_create: %s", cudaGetErrorString(e));
+        delete s;
+        return R2P2_E_CUDA;
+    }
+    *out = s;
+    return R2P2_OK;
+}
+
+int r2p2_destroy(r2p2_handle h) {
+    if (!h) return R2P2_OK;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    StateArrays& s = h->st;
+    void* ptrs[] = {s.x, s.y, s.theta, s.speed, s.omega, s.last_x, s.last_y, s.dist, s.odom_x, s.odom_y, s.origin_x, s.origin_y,
+                    s.time, s.fitness, s.flags, s.ncollide, s.ticks, s.nsamp_sonar, s.nsamp_coll, h->d_x0, h->d_y0, h->d_t0,
+                    h->d_wall, h->d_l50, h->d_crxy, h->d_sincostab, h->d_genomes, h->d_genomes_t, h->d_work, h->d_cnt3};
+    for (void* p : ptrs) cudaFree(p);
+    free_trace(h);
+    cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
+    cudaStreamDestroy(h->stream);
+    delete h;
+    return R2P2_OK;
+}
+
+int r2p2_set_stage(r2p2_handle h, const uint8_t* levels_xy, int32_t W, int32_t H) {
+    if (!h) return R2P2_E_ARG;
+    if (!levels_xy || W < 3 || H < 3) return fail(h, R2P2_E_ARG, "stage must be at least 3x3");
+    if (W > 32768 || H > 32768) return fail(h, R2P2_E_LIMIT, "stage larger than 32768 px per side");
+    CK(cudaSetDevice(h->device));
+    uint8_t* d = nullptr;
+    CK(cudaMalloc(&d, (size_t)W * H));
+    CK(cudaMemcpyAsync(d, levels_xy, (size_t)W * H, cudaMemcpyHostToDevice, h->stream));
+    const int rc = pack_stage(h, d, W, H);
+    cudaFree(d);
+    return rc;
+}
+
+int r2p2_set_stage_i32(r2p2_handle h, const int32_t* levels_xy, int32_t W, int32_t H) {
+    if (!h) return R2P2_E_ARG;
+    if (!levels_xy || W < 3 || H < 3) return fail(h, R2P2_E_ARG, "stage must be at least 3x3");
+    if (W > 32768 || H > 32768) return fail(h, R2P2_E_LIMIT, "stage larger than 32768 px per side");
+    CK(cudaSetDevice(h->device));
+    const size_t n = (size_t)W * H;
+    int32_t* d32 = nullptr; uint8_t* d8 = nullptr; int* d_bad = nullptr;
+    CK(cudaMalloc(&d32, n * 4)); CK(cudaMalloc(&d8, n)); CK(cudaMalloc(&d_bad, 4));
+    CK(cudaMemsetAsync(d_bad, 0, 4, h->stream));
+    CK(cudaMemcpyAsync(d32, levels_xy, n * 4, cudaMemcpyHostToDevice, h->stream));
+    i32_to_u8_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(d32, d8, n, d_bad);
+    h->launches++;
+    int bad = 0;
+    CK(cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    int rc = bad ? fail(h, R2P2_E_ARG, "stage levels must be grey values 0..255") : pack_stage(h, d8, W, H);
+    cudaFree(d32); cudaFree(d8); cudaFree(d_bad);
+    return rc;
+}
+
+int r2p2_set_robot(r2p2_handle h, double vr0, double vr1, double radius, double max_speed, const double* ray_deg, int32_t n_rays) {
+    if (!h) return R2P2_E_ARG;
+    if (!ray_deg || n_rays < 1) return fail(h, R2P2_E_ARG, "need at least one sonar ray");
+    if (n_rays > R2P2_MAX_RAYS) return fail(h, R2P2_E_LIMIT, "at most %d sonar rays", R2P2_MAX_RAYS);
+    CK(cudaSetDevice(h->device));
+    h->vr0 = vr0; h->vr1 = vr1; h->radius = radius; h->max_speed = max_speed; h->R = n_rays;
+    memcpy(h->ray_deg, ray_deg, sizeof(double) * (size_t)n_rays);
+    h->have_robot = true;
+    return upload_crxy(h);
+}
+
+int r2p2_set_controller(r2p2_handle h, int32_t kind, const int32_t* layers, int32_t n_layers, int32_t activation) {
+    if (!h) return R2P2_E_ARG;
+    if (kind < R2P2_CTRL_CONST || kind > R2P2_CTRL_LINEAR) return fail(h, R2P2_E_ARG, "unknown controller kind %d", kind);
+    if (activation < 0 || activation > R2P2_ACT_LOGISTIC) return fail(h, R2P2_E_ARG, "unknown activation %d", activation);
+    h->maxw = 1;
+    if (kind == R2P2_CTRL_NEURO) {
+        if (!layers || n_layers < 2 || n_layers > R2P2_MAX_LAYERS) return fail(h, R2P2_E_LIMIT, "MLP needs 2..%d layer sizes", R2P2_MAX_LAYERS);
+        for (int i = 0; i < n_layers; ++i) {
+            if (layers[i] < 1 || layers[i] > R2P2_MAX_WIDTH) return fail(h, R2P2_E_LIMIT, "layer width must be 1..%d", R2P2_MAX_WIDTH);
+            h->layers[i] = layers[i];
+            h->maxw = std::max(h->maxw, layers[i]);
+        }
+        if (layers[n_layers - 1] != 2) return fail(h, R2P2_E_ARG, "the MLP must end in 2 outputs (speed, angular velocity)");
+        h->n_layers = n_layers;
+    } else {
+        h->n_layers = 0;
+    }
+    h->kind = kind; h->activation = activation; h->have_ctrl = true;
+    return R2P2_OK;
+}
+
+int r2p2_set_mapping(r2p2_handle h, int32_t lanes_per_robot, int32_t stage_in_smem) {
+    if (!h) return R2P2_E_ARG;
+    const int l = lanes_per_robot;
+    if (!(l == 0 || l == 1 || l == 2 || l == 4 || l == 8 || l == 16 || l == 32)) return fail(h, R2P2_E_ARG, "lanes_per_robot must be 0,1,2,4,8,16,32");
+    if (stage_in_smem < -1 || stage_in_smem > 1) return fail(h, R2P2_E_ARG, "stage_in_smem must be -1, 0 or 1");
+    h->lpr_req = l; h->smem_req = stage_in_smem;
+    return R2P2_OK;
+}
+
+int r2p2_upload_genomes(r2p2_handle h, const double* genomes, int32_t P, int32_t G) {
+    if (!h) return R2P2_E_ARG;
+    if (!genomes || P < 1 || G < 1) return fail(h, R2P2_E_ARG, "genomes: need P >= 1, G >= 1");
+    CK(cudaSetDevice(h->device));
+    int rc = ensure_genomes(h, P, G);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(h->d_genomes, genomes, (size_t)P * G * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    h->have_genomes = true;
+    return R2P2_OK;
+}
+
+int r2p2_set_genomes_device(r2p2_handle h, const double* d_genomes, int32_t P, int32_t G) {
+    if (!h) return R2P2_E_ARG;
+    if (!d_genomes || P < 1 || G < 1) return fail(h, R2P2_E_ARG, "genomes: need P >= 1, G >= 1");
+    CK(cudaSetDevice(h->device));
+    int rc = ensure_genomes(h, P, G);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(h->d_genomes, d_genomes, (size_t)P * G * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    h->have_genomes = true;
+    return R2P2_OK;
+}
+
+int r2p2_reset(r2p2_handle h, const double* x0, const double* y0, const double* theta0, int32_t n, double time_budget) {
+    if (!h) return R2P2_E_ARG;
+    if (h->P < 1) return fail(h, R2P2_E_ARG, "upload genomes (population size) before r2p2_reset");
+    if (!x0 || !y0 || !theta0 || !(n == 1 || n == h->P)) return fail(h, R2P2_E_ARG, "reset: n must be 1 or P");
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync(h->d_x0, x0, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_y0, y0, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_t0, theta0, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+    ResetParams r;
+    StateArrays& s = h->st;
+    r.P = h->P; r.n = n; r.x0 = h->d_x0; r.y0 = h->d_y0; r.theta0 = h->d_t0; r.time_budget = time_budget;
+    r.x = s.x; r.y = s.y; r.theta = s.theta; r.speed = s.speed; r.omega = s.omega; r.last_x = s.last_x; r.last_y = s.last_y;
+    r.dist = s.dist; r.odom_x = s.odom_x; r.odom_y = s.odom_y; r.origin_x = s.origin_x; r.origin_y = s.origin_y;
+    r.time = s.time; r.fitness = s.fitness; r.flags = s.flags; r.ncollide = s.ncollide; r.ticks = s.ticks;
+    r.nsamp_sonar = s.nsamp_sonar; r.nsamp_coll = s.nsamp_coll;
+    reset_kernel<<<(h->P + 255) / 256, 256, 0, h->stream>>>(r);
+    h->launches++;
+    CK(cudaGetLastError());
+    if (n > 1) CK(cudaStreamSynchronize(h->stream));   // host arrays may be pageable and reused by the caller
+    h->have_reset = true;
+    return R2P2_OK;
+}
+
+int r2p2_run(r2p2_handle h, int32_t T, double delta, double delta_ctrl, int32_t evolve) {
+    if (!h) return R2P2_E_ARG;
+    if (!h->d_wall) return fail(h, R2P2_E_ARG, "r2p2_run: no stage (call r2p2_set_stage)");
+    if (!h->have_robot) return fail(h, R2P2_E_ARG, "r2p2_run: no robot (call r2p2_set_robot)");
+    if (!h->have_ctrl) return fail(h, R2P2_E_ARG, "r2p2_run: no controller (call r2p2_set_controller)");
+    if (!h->have_genomes) return fail(h, R2P2_E_ARG, "r2p2_run: no genomes (call r2p2_upload_genomes)");
+    if (!h->have_reset) return fail(h, R2P2_E_ARG, "r2p2_run: population not initialised (call r2p2_reset)");
+    if (T < 0) return fail(h, R2P2_E_ARG, "T must be >= 0");
+    if (h->kind == R2P2_CTRL_NEURO) {
+        if (h->layers[0] != h->R) return fail(h, R2P2_E_ARG, "MLP input width %d != number of sonar rays %d", h->layers[0], h->R);
+        int g = 0;
+        for (int l = 0; l + 1 < h->n_layers; ++l) g += h->layers[l] * h->layers[l + 1];
+        if (g != h->G) return fail(h, R2P2_E_ARG, "genome length %d != MLP weight count %d", h->G, g);
+    } else if (h->kind == R2P2_CTRL_LINEAR) {
+        if (h->G < 4 || (h->G & 1)) return fail(h, R2P2_E_ARG, "linear chromosome length must be even and >= 4 (got %d)", h->G);
+    } else if (h->G != 2) {
+        return fail(h, R2P2_E_ARG, "constant-command genome must be [speed, angular_velocity]");
+    }
+    if (h->trace && (T > h->trace_T)) return fail(h, R2P2_E_ARG, "trace enabled for at most %d ticks per run", h->trace_T);
+    CK(cudaSetDevice(h->device));
+
+    const int lpr = choose_lpr(h);
+    KParams kp;
+    memset(&kp, 0, sizeof kp);
+    kp.W = h->W; kp.H = h->H; kp.wpr = h->wpr; kp.has50 = h->has50;
+    kp.g_wall = h->d_wall; kp.g_lvl50 = h->d_l50; kp.plane_bytes = h->plane_bytes;
+    kp.R = h->R;
+    memcpy(kp.ray_deg, h->ray_deg, sizeof(double) * (size_t)h->R);
+    kp.vr1 = h->vr1; kp.radius = h->radius; kp.max_speed = h->max_speed;
+    kp.L = h->vr1 + h->radius;
+    {
+        const volatile double m = h->vr0 * 0.125;   // two roundings, as Python evaluates vr0*0.125 + radius
+        kp.db_lo = m + h->radius;
+    }
+    kp.db_hi = h->vr0 + h->radius;
+    kp.rad_p1 = h->radius + 1.0;
+    kp.ctrl_kind = h->kind; kp.n_layers = h->n_layers; kp.activation = h->activation; kp.G = h->G;
+    kp.maxw = std::max(h->maxw, h->R);
+    memcpy(kp.layers, h->layers, sizeof(int) * R2P2_MAX_LAYERS);
+    kp.P = h->P; kp.T = T; kp.evolve = evolve ? 1 : 0;
+    kp.delta = delta; kp.delta_ctrl = delta_ctrl;
+    kp.g_sincostab = h->d_sincostab; kp.g_crxy = h->d_crxy;
+    StateArrays& s = h->st;
+    kp.x = s.x; kp.y = s.y; kp.theta = s.theta; kp.speed = s.speed; kp.omega = s.omega; kp.last_x = s.last_x; kp.last_y = s.last_y;
+    kp.dist = s.dist; kp.odom_x = s.odom_x; kp.odom_y = s.odom_y; kp.origin_x = s.origin_x; kp.origin_y = s.origin_y;
+    kp.time = s.time; kp.fitness = s.fitness; kp.flags = s.flags; kp.ncollide = s.ncollide; kp.ticks = s.ticks;
+    kp.nsamp_sonar = s.nsamp_sonar; kp.nsamp_coll = s.nsamp_coll;
+    kp.work_counter = h->d_work;
+
+    if (lpr == 1) {
+        if (!h->genomes_t_valid) {
+            dim3 grid((h->P + 31) / 32, (h->G + 31) / 32), block(32, 8);
+            transpose_genomes_kernel<<<grid, block, 0, h->stream>>>(h->d_genomes, h->d_genomes_t, h->P, h->G);
+            h->launches++;
+            CK(cudaGetLastError());
+            h->genomes_t_valid = true;
+        }
+        kp.genomes = h->d_genomes_t;
+    } else {
+        kp.genomes = h->d_genomes;
+    }
+
+    if (h->trace) {
+        if (h->trace_P != h->P || h->trace_R != h->R) return fail(h, R2P2_E_ARG, "trace buffers were sized for another population; call r2p2_set_trace again");
+        const size_t rows = (size_t)T * h->P;
+        CK(cudaMemsetAsync(h->tr_pose, 0, rows * 5 * sizeof(double), h->stream));
+        CK(cudaMemsetAsync(h->tr_dst, 0, rows * h->R * sizeof(double), h->stream));
+        CK(cudaMemsetAsync(h->tr_hitk, 0xff, rows * h->R * sizeof(int32_t), h->stream));
+        CK(cudaMemsetAsync(h->tr_hitpx, 0xff, rows * h->R * 2 * sizeof(int32_t), h->stream));
+        CK(cudaMemsetAsync(h->tr_nsamp, 0, rows * h->R * sizeof(uint32_t), h->stream));
+        CK(cudaMemsetAsync(h->tr_ncoll, 0, rows * sizeof(uint32_t), h->stream));
+        kp.tr_pose = h->tr_pose; kp.tr_dst = h->tr_dst; kp.tr_hitk = h->tr_hitk; kp.tr_hitpx = h->tr_hitpx;
+        kp.tr_nsamp = h->tr_nsamp; kp.tr_ncoll = h->tr_ncoll;
+    }
+
+    bool smem_stage;
+    const size_t with_stage = episode_smem_bytes(lpr, true, kp.plane_bytes, kp.has50, kp.maxw);
+    if (h->smem_req == 1) smem_stage = true;
+    else if (h->smem_req == 0) smem_stage = false;
+    else smem_stage = with_stage <= 100 * 1024;           // keep >= 2 CTAs per SM
+    if (smem_stage && with_stage > h->smem_optin) {
+        if (h->smem_req == 1) return fail(h, R2P2_E_LIMIT, "stage planes (%zu bytes with tables) exceed shared memory", with_stage);
+        smem_stage = false;
+    }
+    switch (lpr) {
+        case 1: return launch_episode_s<1>(h, kp, smem_stage);
+        case 2: return launch_episode_s<2>(h, kp, smem_stage);
+        case 4: return launch_episode_s<4>(h, kp, smem_stage);
+        case 8: return launch_episode_s<8>(h, kp, smem_stage);
+        case 16: return launch_episode_s<16>(h, kp, smem_stage);
+        default: return launch_episode_s<32>(h, kp, smem_stage);
+    }
+}
+
+int r2p2_sync(r2p2_handle h) {
+    if (!h) return R2P2_E_ARG;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    return R2P2_OK;
+}
+
+int r2p2_last_run_ms(r2p2_handle h, float* ms) {
+    if (!h || !ms) return R2P2_E_ARG;
+    if (!h->ev_valid) return fail(h, R2P2_E_ARG, "no run yet");
+    CK(cudaSetDevice(h->device));
+    CK(cudaEventSynchronize(h->ev1));
+    CK(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+    return R2P2_OK;
+}
+
+int r2p2_read_fitness(r2p2_handle h, double* fitness) {
+    if (!h || !fitness) return R2P2_E_ARG;
+    if (h->P < 1) return fail(h, R2P2_E_ARG, "no population");
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync(fitness, h->st.fitness, sizeof(double) * h->P, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return R2P2_OK;
+}
+
+int r2p2_read_state(r2p2_handle h, double* x, double* y, double* theta, double* speed, double* omega, uint32_t* flags,
+                    uint32_t* ncollide, uint32_t* ticks) {
+    if (!h) return R2P2_E_ARG;
+    if (h->P < 1) return fail(h, R2P2_E_ARG, "no population");
+    CK(cudaSetDevice(h->device));
+    const StateArrays& s = h->st;
+    const size_t nb = sizeof(double) * h->P, nu = sizeof(uint32_t) * h->P;
+    if (x) CK(cudaMemcpyAsync(x, s.x, nb, cudaMemcpyDeviceToHost, h->stream));
+    if (y) CK(cudaMemcpyAsync(y, s.y, nb, cudaMemcpyDeviceToHost, h->stream));
+    if (theta) CK(cudaMemcpyAsync(theta, s.theta, nb, cudaMemcpyDeviceToHost, h->stream));
+    if (speed) CK(cudaMemcpyAsync(speed, s.speed, nb, cudaMemcpyDeviceToHost, h->stream));
+    if (omega) CK(cudaMemcpyAsync(omega, s.omega, nb, cudaMemcpyDeviceToHost, h->stream));
+    if (flags) CK(cudaMemcpyAsync(flags, s.flags, nu, cudaMemcpyDeviceToHost, h->stream));
+    if (ncollide) CK(cudaMemcpyAsync(ncollide, s.ncollide, nu, cudaMemcpyDeviceToHost, h->stream));
+    if (ticks) CK(cudaMemcpyAsync(ticks, s.ticks, nu, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return R2P2_OK;
+}
+
+int r2p2_read_counters(r2p2_handle h, uint64_t* sonar_samples, uint64_t* collision_samples, uint64_t* robot_steps) {
+    if (!h) return R2P2_E_ARG;
+    if (h->P < 1) return fail(h, R2P2_E_ARG, "no population");
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemsetAsync(h->d_cnt3, 0, 3 * sizeof(unsigned long long), h->stream));
+    const int blocks = std::min((h->P + 255) / 256, 4 * h->sm_count);
+    sum_counters_kernel<<<blocks, 256, 0, h->stream>>>(h->st.nsamp_sonar, h->st.nsamp_coll, h->st.ticks, h->P, h->d_cnt3);
+    h->launches++;
+    CK(cudaGetLastError());
+    unsigned long long c[3];
+    CK(cudaMemcpyAsync(c, h->d_cnt3, sizeof c, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (sonar_samples) *sonar_samples = c[0];
+    if (collision_samples) *collision_samples = c[1];
+    if (robot_steps) *robot_steps = c[2];
+    return R2P2_OK;
+}
+
+int r2p2_fitness_device(r2p2_handle h, double** d_fitness) {
+    if (!h || !d_fitness) return R2P2_E_ARG;
+    if (h->P < 1) return fail(h, R2P2_E_ARG, "no population");
+    *d_fitness = h->st.fitness;
+    return R2P2_OK;
+}
+
+int r2p2_launch_count(r2p2_handle h, uint64_t* n) {
+    if (!h || !n) return R2P2_E_ARG;
+    *n = h->launches;
+    return R2P2_OK;
+}
+
+int r2p2_set_trace(r2p2_handle h, int32_t enable, int32_t T_max) {
+    if (!h) return R2P2_E_ARG;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    free_trace(h);
+    h->trace = false;
+    if (!enable) return R2P2_OK;
+    if (h->P < 1 || !h->have_robot) return fail(h, R2P2_E_ARG, "set the robot and the population before enabling the trace");
+    if (T_max < 1) return fail(h, R2P2_E_ARG, "T_max must be >= 1");
+    const size_t rows = (size_t)T_max * h->P;
+    CK(dalloc(&h->tr_pose, rows * 5)); CK(dalloc(&h->tr_dst, rows * h->R));
+    CK(dalloc(&h->tr_hitk, rows * h->R)); CK(dalloc(&h->tr_hitpx, rows * h->R * 2));
+    CK(dalloc(&h->tr_nsamp, rows * h->R)); CK(dalloc(&h->tr_ncoll, rows));
+    h->trace = true; h->trace_T = T_max; h->trace_P = h->P; h->trace_R = h->R;
+    return R2P2_OK;
+}
+
+int r2p2_read_trace(r2p2_handle h, int32_t T, double* pose, double* dst, int32_t* hitk, int32_t* hitpx, uint32_t* nsamp, uint32_t* ncoll) {
+    if (!h) return R2P2_E_ARG;
+    if (!h->trace) return fail(h, R2P2_E_ARG, "trace not enabled");
+    if (T < 0 || T > h->trace_T) return fail(h, R2P2_E_ARG, "T out of range");
+    CK(cudaSetDevice(h->device));
+    const size_t rows = (size_t)T * h->trace_P, R = (size_t)h->trace_R;
+    if (pose) CK(cudaMemcpyAsync(pose, h->tr_pose, rows * 5 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (dst) CK(cudaMemcpyAsync(dst, h->tr_dst, rows * R * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (hitk) CK(cudaMemcpyAsync(hitk, h->tr_hitk, rows * R * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    if (hitpx) CK(cudaMemcpyAsync(hitpx, h->tr_hitpx, rows * R * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    if (nsamp) CK(cudaMemcpyAsync(nsamp, h->tr_nsamp, rows * R * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    if (ncoll) CK(cudaMemcpyAsync(ncoll, h->tr_ncoll, rows * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return R2P2_OK;
+}
+
+int r2p2_cast_rays(r2p2_handle h, int32_t n, const double* ox, const double* oy, const double* angle_rad, const double* limit,
+                   int32_t* status, double* hx, double* hy, int32_t* k, uint32_t* nsamp) {
+    if (!h) return R2P2_E_ARG;
+    if (!h->d_wall) return fail(h, R2P2_E_ARG, "no stage");
+    if (n < 1 || !ox || !oy || !angle_rad || !limit || !status || !hx || !hy || !k || !nsamp) return fail(h, R2P2_E_ARG, "cast_rays: bad arguments");
+    CK(cudaSetDevice(h->device));
+    double* d_in = nullptr; double* d_out = nullptr; int32_t* d_i = nullptr;
+    CK(cudaMalloc(&d_in, sizeof(double) * 4 * n)); CK(cudaMalloc(&d_out, sizeof(double) * 2 * n)); CK(cudaMalloc(&d_i, sizeof(int32_t) * 3 * n));
+    const size_t nb = sizeof(double) * n;
+    CK(cudaMemcpyAsync(d_in, ox, nb, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d_in + n, oy, nb, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d_in + 2 * n, angle_rad, nb, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d_in + 3 * n, limit, nb, cudaMemcpyHostToDevice, h->stream));
+    StageView sv; sv.wall = h->d_wall; sv.lvl50 = h->d_l50; sv.W = h->W; sv.H = h->H; sv.wpr = h->wpr;
+    cast_rays_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(sv, h->d_sincostab, n, d_in, d_in + n, d_in + 2 * n, d_in + 3 * n,
+                                                             d_i, d_out, d_out + n, d_i + n, reinterpret_cast<uint32_t*>(d_i + 2 * n));
+    h->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(status, d_i, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(k, d_i + n, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(nsamp, d_i + 2 * n, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(hx, d_out, nb, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(hy, d_out + n, nb, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    cudaFree(d_in); cudaFree(d_out); cudaFree(d_i);
+    return R2P2_OK;
+}
+
+}  // extern "C"

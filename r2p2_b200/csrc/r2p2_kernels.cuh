@@ -1,0 +1,602 @@
+// r2p2_kernels.cuh -- hand-written sm_100a kernels for the r2p2 robot step.
+//
+// One launch of episode_kernel advances a whole population by up to T ticks of the reference's
+// Robot.update (r2p2/robot.py:389-402): sonar ray-march (r2p2/utils.py:420-432 through
+// robot.py:287-318), controller forward (neurocontroller.py:67-95 / inspyred.py:60-100), unicycle
+// integration with wall / border / crash-radius handling (robot.py:181-260) and the fitness
+// bookkeeping (neurocontroller.py:69-85,129-131).  State lives in registers across ticks; HBM is
+// touched at robot start (genome, pose) and robot end only.
+//
+// Mapping: LPR lanes cooperate on one robot (LPR = 1, 8 or 32; a "group" is an aligned slice of a
+// warp synchronised with its own member mask).  Sonar rays, MLP neurons and the 360 crash-radius
+// probes are spread over the group's lanes; the strictly sequential per-robot scalar work is done
+// redundantly by every lane of the group (free under SIMT, keeps values uniform without broadcasts).
+// Robots are handed out through a global work counter, so a group that finishes an episode early
+// (collision) immediately starts the next robot.
+//
+// Exactness: every FP64 operation that can reach an integer decision is issued with explicit
+// rounding (r2p2_math.h); this translation unit is compiled with -fmad=false.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/r2p2_b200.h"
+#include "r2p2_math.h"
+
+namespace r2p2 {
+
+constexpr int kBlock = 128;                    // threads per CTA
+constexpr double kRad = 3.14159265358979323846 / 180.0;   // CPython math.radians multiplier
+constexpr double kDeg = 180.0 / 3.14159265358979323846;   // CPython math.degrees multiplier
+constexpr double kNormSlack = 1e-6;            // |norm(p_k - o) - k| bound used to skip the norm test (see march)
+
+struct KParams {
+    // stage
+    int32_t W, H, wpr;                 // wpr = 32-bit words per bit-plane row
+    int32_t has50;
+    const uint32_t* g_wall;            // [H][wpr] bit x of row y set <=> level(x, y) == 0
+    const uint32_t* g_lvl50;           //                         <=> level(x, y) == 50
+    uint32_t plane_bytes;              // bytes of one plane, multiple of 16
+    // robot
+    int32_t R;
+    double ray_deg[R2P2_MAX_RAYS];
+    double vr1, radius, max_speed;
+    double L, db_lo, db_hi;            // vr1 + radius, vr0*0.125 + radius, vr0 + radius
+    double rad_p1;                     // radius + 1
+    // controller
+    int32_t ctrl_kind, n_layers, activation, G, maxw;
+    int32_t layers[R2P2_MAX_LAYERS];
+    const double* genomes;             // [P][G] (LPR > 1) or [G][P] (LPR == 1)
+    // run
+    int32_t P, T, evolve;
+    double delta, delta_ctrl;
+    // tables
+    const double* g_sincostab;         // 440 doubles
+    const double* g_crxy;              // 360 x offsets then 360 y offsets (cos/sin(radians(i)) * radius)
+    // state (SoA, P each)
+    double *x, *y, *theta, *speed, *omega, *last_x, *last_y, *dist, *odom_x, *odom_y, *origin_x, *origin_y, *time, *fitness;
+    uint32_t *flags, *ncollide, *ticks;
+    unsigned long long *nsamp_sonar, *nsamp_coll;
+    // trace (optional)
+    double* tr_pose; double* tr_dst; int32_t* tr_hitk; int32_t* tr_hitpx; uint32_t* tr_nsamp; uint32_t* tr_ncoll;
+    // scheduling
+    unsigned int* work_counter;
+};
+
+struct StageView {
+    const uint32_t* wall;
+    const uint32_t* lvl50;
+    int W, H, wpr;
+};
+
+// ---------------------------------------------------------------------------------------------
+// TMA (1-D bulk copy) + mbarrier helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t mbar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(mbar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// global -> shared bulk copy executed by the TMA unit; completion is signalled on the mbarrier
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint32_t mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(mbar) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// pixel probes with the reference's (Python) index semantics
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int dtrunc(double v) { return __double2int_rz(v); }   // int(v); saturates, NaN -> 0
+
+__device__ __forceinline__ bool plane_bit(const uint32_t* __restrict__ plane, int wpr, int ix, int iy) {
+    return (plane[iy * wpr + (ix >> 5)] >> (ix & 31)) & 1u;
+}
+// env.item(ix, iy) == target-level?  Negative indices wrap, anything else out of range is an IndexError.
+__device__ __forceinline__ bool px_probe(const uint32_t* __restrict__ plane, const StageView& s, int ix, int iy, bool& fault) {
+    if (ix < 0) ix += s.W;
+    if (iy < 0) iy += s.H;
+    if ((unsigned)ix >= (unsigned)s.W || (unsigned)iy >= (unsigned)s.H) { fault = true; return false; }
+    return plane_bit(plane, s.wpr, ix, iy);
+}
+
+struct Hit {
+    double x, y;
+    int k;            // hit step, -1 on miss
+    unsigned nsamp;   // pixels tested (loop body executions)
+    bool fault;
+};
+
+// utils.search_edge_in_angle_with_limit (r2p2/utils.py:420-432) with (vx, vy) = (cos, sin) already taken.
+//
+// Two tests of the reference loop are decided without arithmetic whenever that is provably safe:
+//  * `norm(p - o) < limit`: p_k is o plus k accumulated unit steps, so |norm - k| < kNormSlack for every
+//    in-map coordinate (|coord| < 2^15, k < 3e4: <= k * (ulp(2^15)/2) * sqrt(2) + k * 3e-16 < 2e-7).  The
+//    test is therefore true for k < limit - slack and false for k >= limit + slack; only the (at most one)
+//    k in between -- the knife-edge sample of SURVEY.md H5 -- is evaluated exactly, with the reference's
+//    own arithmetic sqrt(fma(dy,dy, dx*dx)) < limit.
+//  * `round(p.x) in range(0, W)`: true whenever the truncated pixel index is in [1, W-2]; otherwise the
+//    half-to-even test is evaluated exactly.
+__device__ __forceinline__ Hit march(const StageView& s, double ox, double oy, double vx, double vy, double limit) {
+    Hit r;
+    r.x = -1.0; r.y = -1.0; r.k = -1; r.nsamp = 0u; r.fault = false;
+    int kA = 0, kB = 0x7fffffff;          // k < kA: norm test true; k >= kB: false; else exact
+    if (limit > -1.0 && limit < 30000.0) {
+        kA = (int)ceil(limit - kNormSlack);
+        kB = (int)ceil(limit + kNormSlack);
+        if (kA < 0) kA = 0;
+        if (kB < 0) kB = 0;
+    }
+    double x = ox, y = oy;
+    const double dW = (double)s.W, dH = (double)s.H;
+    for (int k = 0; k < kB; ++k) {
+        const int ix = dtrunc(x), iy = dtrunc(y);
+        const bool interior = ((unsigned)(ix - 1) < (unsigned)(s.W - 2)) & ((unsigned)(iy - 1) < (unsigned)(s.H - 2));
+        if (!interior) {
+            if (!isfinite(x) || !isfinite(y)) { r.fault = true; return r; }     // round(nan/inf) raises
+            const double rx = rint(x), ry = rint(y);
+            if (!(rx >= 0.0 && rx < dW && ry >= 0.0 && ry < dH)) return r;
+        }
+        if (k >= kA) {
+            if (!(r2p2_norm2(R2P2_SUB(x, ox), R2P2_SUB(y, oy)) < limit)) return r;
+        }
+        r.nsamp++;
+        bool w;
+        if (interior) {
+            w = plane_bit(s.wall, s.wpr, ix, iy);
+        } else {
+            bool f = false;
+            w = px_probe(s.wall, s, ix, iy, f);
+            if (f) { r.fault = true; return r; }
+        }
+        if (w) { r.x = x; r.y = y; r.k = k; return r; }
+        x = R2P2_ADD(x, vx);
+        y = R2P2_ADD(y, vy);
+    }
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// group (LPR lanes of one warp working on one robot)
+// ---------------------------------------------------------------------------------------------
+template <int LPR>
+struct Group {
+    unsigned mask;
+    int sub;
+    __device__ __forceinline__ Group() {
+        const int lane = threadIdx.x & 31;
+        sub = lane & (LPR - 1);
+        mask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (lane & ~(LPR - 1)));
+    }
+    __device__ __forceinline__ void sync() const { if (LPR > 1) __syncwarp(mask); }
+    __device__ __forceinline__ bool any(bool p) const { return (LPR == 1) ? p : (__ballot_sync(mask, p) != 0u); }
+    __device__ __forceinline__ int min_i(int v) const {
+#pragma unroll
+        for (int o = LPR / 2; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(mask, v, o, 32));
+        return v;
+    }
+    __device__ __forceinline__ unsigned sum_u(unsigned v) const {
+#pragma unroll
+        for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o, 32);
+        return v;
+    }
+    __device__ __forceinline__ unsigned bcast_u(unsigned v) const { return (LPR == 1) ? v : __shfl_sync(mask, v, 0, LPR); }
+};
+
+__device__ __forceinline__ double activate(int kind, double v) {
+    switch (kind) {
+        case R2P2_ACT_TANH: return r2p2_tanh(v);
+        case R2P2_ACT_RELU:
+            if (v != v) return v;
+            if (v > 1.7976931348623157e308) return 1.7976931348623157e308;
+            return v > 0.0 ? v : 0.0;
+        case R2P2_ACT_LOGISTIC: return r2p2_logistic(v);
+        default: return v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// the episode kernel
+// ---------------------------------------------------------------------------------------------
+// dynamic shared memory layout (bytes):
+//   [0,16)                         mbarrier
+//   [16, 16+3520)                  sin/cos table
+//   [.., +5760)                    crash-radius offsets (360 x, 360 y)
+//   [.., +plane_bytes)             wall plane      (SMEM_STAGE only)
+//   [.., +plane_bytes)             level-50 plane  (SMEM_STAGE and has50 only)
+//   [.., +2*maxw*NR*8)             MLP / sonar buffers A and B, element i of robot slot r at [i*NR + r]
+__host__ __device__ inline size_t episode_smem_bytes(int lpr, bool smem_stage, uint32_t plane_bytes, int has50, int maxw) {
+    size_t n = 16 + R2P2_SINCOSTAB_LEN * 8 + 720 * 8;
+    if (smem_stage) n += (size_t)plane_bytes * (has50 ? 2 : 1);
+    n += (size_t)2 * maxw * (kBlock / lpr) * 8;
+    return n;
+}
+
+template <int LPR, bool SMEM_STAGE>
+__global__ void __launch_bounds__(kBlock) episode_kernel(const __grid_constant__ KParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int NR = kBlock / LPR;                      // robots in flight per CTA
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw);
+    double* s_tab = reinterpret_cast<double*>(smem_raw + 16);
+    double* s_crx = s_tab + R2P2_SINCOSTAB_LEN;
+    double* s_cry = s_crx + 360;
+    unsigned char* cur = reinterpret_cast<unsigned char*>(s_cry + 360);
+    uint32_t* s_wall = nullptr;
+    uint32_t* s_l50 = nullptr;
+    if (SMEM_STAGE) {
+        s_wall = reinterpret_cast<uint32_t*>(cur); cur += p.plane_bytes;
+        if (p.has50) { s_l50 = reinterpret_cast<uint32_t*>(cur); cur += p.plane_bytes; }
+    }
+    double* s_bufA = reinterpret_cast<double*>(cur);
+    double* s_bufB = s_bufA + (size_t)p.maxw * NR;
+
+    // ---- stage the read-only tables (and the bit planes) into shared memory with the TMA unit ----
+    const uint32_t mb = smem_u32(mbar);
+    if (threadIdx.x == 0) {
+        mbar_init(mb, 1);
+        uint32_t total = R2P2_SINCOSTAB_LEN * 8 + 720 * 8;
+        if (SMEM_STAGE) total += p.plane_bytes * (p.has50 ? 2u : 1u);
+        mbar_expect_tx(mb, total);
+        tma_load_1d(s_tab, p.g_sincostab, R2P2_SINCOSTAB_LEN * 8, mb);
+        tma_load_1d(s_crx, p.g_crxy, 720 * 8, mb);
+        if (SMEM_STAGE) {
+            for (uint32_t off = 0; off < p.plane_bytes; off += 32768u) {
+                const uint32_t n = min(32768u, p.plane_bytes - off);
+                tma_load_1d(reinterpret_cast<unsigned char*>(s_wall) + off, reinterpret_cast<const unsigned char*>(p.g_wall) + off, n, mb);
+                if (p.has50)
+                    tma_load_1d(reinterpret_cast<unsigned char*>(s_l50) + off, reinterpret_cast<const unsigned char*>(p.g_lvl50) + off, n, mb);
+            }
+        }
+    }
+    __syncthreads();
+    while (!mbar_try_wait(mb, 0)) { }
+
+    StageView sv;
+    sv.wall = SMEM_STAGE ? s_wall : p.g_wall;
+    sv.lvl50 = SMEM_STAGE ? s_l50 : p.g_lvl50;
+    sv.W = p.W; sv.H = p.H; sv.wpr = p.wpr;
+
+    const Group<LPR> g;
+    const int slot = threadIdx.x / LPR;                   // robot slot inside the CTA
+    double* bufA = s_bufA + slot;
+    double* bufB = s_bufB + slot;
+    const int R = p.R;
+    const double delta = p.delta;
+    const bool tracing = p.tr_pose != nullptr;
+
+    for (;;) {
+        // ---- fetch the next robot --------------------------------------------------------------
+        unsigned rb = 0;
+        if (g.sub == 0) rb = atomicAdd(p.work_counter, 1u);
+        rb = g.bcast_u(rb);
+        if (rb >= (unsigned)p.P) break;
+
+        double x = p.x[rb], y = p.y[rb], theta = p.theta[rb], speed = p.speed[rb], omega = p.omega[rb];
+        double last_x = p.last_x[rb], last_y = p.last_y[rb];
+        double dist = p.dist[rb], odom_x = p.odom_x[rb], odom_y = p.odom_y[rb];
+        const double origin_x = p.origin_x[rb], origin_y = p.origin_y[rb];
+        double tmr = p.time[rb];
+        double fitness = p.fitness[rb];
+        unsigned flags = p.flags[rb], ncollide = p.ncollide[rb], ticks = p.ticks[rb];
+        unsigned my_ns_sonar = 0u, ns_coll = 0u;          // my_ns_sonar: this lane's rays only
+
+        int t = 0;
+        unsigned ncollide0 = ncollide;
+        for (; t < p.T; ++t) {
+            if (flags & (R2P2_F_FAULT | R2P2_F_DONE)) break;
+            ncollide0 = ncollide;
+            const size_t trow = (size_t)t * (size_t)p.P + rb;
+
+            // ---- sense: Robot.check_sensors (robot.py:287-318) --------------------------------
+            bool fault = !(isfinite(x) && isfinite(y));   // round(nan) / round(inf) raise
+            const double ox = rint(x), oy = rint(y);      // Python round(): half to even
+            if (!fault) {
+                for (int i = g.sub; i < R; i += LPR) {
+                    const double ang = R2P2_ADD(p.ray_deg[i], theta);
+                    int ok = 1;
+                    double vs, vc;
+                    r2p2_sincos(R2P2_MUL(ang, kRad), s_tab, &vs, &vc, &ok);
+                    if (!ok) { flags |= R2P2_F_TRIGRANGE; fault = true; break; }
+                    const Hit h = march(sv, ox, oy, vc, vs, p.L);
+                    my_ns_sonar += h.nsamp;
+                    if (h.fault) { fault = true; }
+                    double d = (h.k >= 0) ? r2p2_norm2(R2P2_SUB(h.x, ox), R2P2_SUB(h.y, oy)) : r2p2_from_bits(0x7ff0000000000000ULL);
+                    if ((d < p.db_hi && d > p.db_lo) || d > p.L) d = p.L;
+                    bufA[i * NR] = d;
+                    if (tracing) {
+                        p.tr_dst[trow * R + i] = d;
+                        p.tr_hitk[trow * R + i] = h.k;
+                        p.tr_hitpx[(trow * R + i) * 2] = (h.k >= 0) ? dtrunc(h.x) : -1;
+                        p.tr_hitpx[(trow * R + i) * 2 + 1] = (h.k >= 0) ? dtrunc(h.y) : -1;
+                        p.tr_nsamp[trow * R + i] = h.nsamp;
+                    }
+                    if (h.fault) break;
+                }
+            }
+            if (LPR > 1) {
+                const unsigned tr_bit = __ballot_sync(g.mask, (flags & R2P2_F_TRIGRANGE) != 0u);
+                if (tr_bit) flags |= R2P2_F_TRIGRANGE;
+            }
+            if (g.any(fault)) { flags |= R2P2_F_FAULT; break; }
+            g.sync();
+
+            // ---- control: Neuro_controller.control / Inspyred_controller.control -----------------
+            dist = R2P2_ADD(dist, r2p2_norm2(R2P2_SUB(x, odom_x), R2P2_SUB(y, odom_y)));
+            odom_x = x; odom_y = y;
+            if (p.ctrl_kind != R2P2_CTRL_CONST) {
+                if (p.evolve) tmr = R2P2_SUB(tmr, p.delta_ctrl);
+                if (tmr <= 0.0 && p.evolve) {             // episode over: fitness is frozen here
+                    fitness = R2P2_ADD(dist, r2p2_norm2(R2P2_SUB(odom_x, origin_x), R2P2_SUB(odom_y, origin_y)));
+                    flags |= R2P2_F_DONE;
+                    speed = 0.0; omega = 0.0;
+                    break;
+                }
+            }
+            double v, w;
+            if (p.ctrl_kind == R2P2_CTRL_NEURO) {
+                for (int i = g.sub; i < R; i += LPR) bufA[i * NR] = R2P2_DIV(p.vr1, bufA[i * NR]);   // 25/dst (inf when dst == 0)
+                g.sync();
+                double* hin = bufA;
+                double* hout = bufB;
+                int woff = 0;
+                for (int l = 0; l + 1 < p.n_layers; ++l) {
+                    const int nin = p.layers[l], nout = p.layers[l + 1];
+                    const bool last = (l + 2 == p.n_layers);
+                    for (int j = g.sub; j < nout; j += LPR) {
+                        double acc = 0.0;
+                        if (LPR == 1) {
+                            const double* wp = p.genomes + (size_t)(woff + j) * (size_t)p.P + rb;
+                            for (int i = 0; i < nin; ++i) acc = R2P2_FMA(hin[i * NR], __ldg(wp + (size_t)i * nout * (size_t)p.P), acc);
+                        } else {
+                            const double* wp = p.genomes + (size_t)rb * (size_t)p.G + woff + j;
+                            for (int i = 0; i < nin; ++i) acc = R2P2_FMA(hin[i * NR], __ldg(wp + i * nout), acc);
+                        }
+                        hout[j * NR] = last ? acc : activate(p.activation, acc);
+                    }
+                    g.sync();
+                    double* tsw = hin; hin = hout; hout = tsw;
+                    woff += nin * nout;
+                }
+                v = hin[0];
+                if (v > 180.0) v = R2P2_SUB(v, 360.0);
+                w = hin[NR];
+                g.sync();                                  // buffers are rewritten by the next tick's sense
+            } else if (p.ctrl_kind == R2P2_CTRL_LINEAR) {
+                const int n = p.G / 2 - 1;
+                const int m = n < R ? n : R;
+                double lin = 0.0, angv = 0.0;
+                if (LPR == 1) {
+                    for (int i = 0; i < m; ++i) lin = R2P2_ADD(lin, R2P2_MUL(__ldg(p.genomes + (size_t)i * p.P + rb), bufA[i * NR]));
+                    for (int i = 0; i < m; ++i) angv = R2P2_ADD(angv, R2P2_MUL(__ldg(p.genomes + (size_t)(n + i) * p.P + rb), bufA[i * NR]));
+                } else {
+                    const double* gp = p.genomes + (size_t)rb * (size_t)p.G;
+                    for (int i = 0; i < m; ++i) lin = R2P2_ADD(lin, R2P2_MUL(__ldg(gp + i), bufA[i * NR]));
+                    for (int i = 0; i < m; ++i) angv = R2P2_ADD(angv, R2P2_MUL(__ldg(gp + n + i), bufA[i * NR]));
+                }
+                v = lin; w = angv;
+                g.sync();
+            } else {
+                if (LPR == 1) { v = __ldg(p.genomes + rb); w = __ldg(p.genomes + (size_t)p.P + rb); }
+                else { v = __ldg(p.genomes + (size_t)rb * p.G); w = __ldg(p.genomes + (size_t)rb * p.G + 1); }
+            }
+            // Robot.control clamp (robot.py:386-387)
+            if (r2p2_fabs(v) > p.max_speed) v = R2P2_MUL(R2P2_DIV(v, r2p2_fabs(v)), p.max_speed);
+            speed = v; omega = w;
+
+            // ---- integrate: __update_angle, __update_position (robot.py:188-267) ------------------
+            theta = R2P2_ADD(theta, R2P2_MUL(omega, delta));
+            {
+                int ok = 1;
+                double hs, hc;
+                r2p2_sincos(R2P2_MUL(theta, kRad), s_tab, &hs, &hc, &ok);
+                if (!ok) { flags |= R2P2_F_TRIGRANGE | R2P2_F_FAULT; break; }
+                const double cx = R2P2_ADD(x, R2P2_MUL(R2P2_MUL(hc, speed), delta));
+                const double cy = R2P2_ADD(y, R2P2_MUL(R2P2_MUL(hs, speed), delta));
+                const double dx = R2P2_SUB(cx, x), dy = R2P2_SUB(cy, y);
+                double angle = R2P2_MUL(r2p2_atan2(dy, dx), kDeg);
+                // Python float % 360 for |angle| <= 180: fmod is the identity, then the sign fix-up
+                if (angle != 0.0) { if (angle < 0.0) angle = R2P2_ADD(angle, 360.0); } else angle = 0.0;
+                double cs_, cc_;
+                r2p2_sincos(R2P2_MUL(angle, kRad), s_tab, &cs_, &cc_, &ok);
+                if (!ok) { flags |= R2P2_F_TRIGRANGE | R2P2_F_FAULT; break; }   // NaN displacement: the reference faults two statements later
+                const Hit ms = march(sv, x, y, cc_, cs_, R2P2_ADD(r2p2_norm2(dx, dy), p.radius));
+                ns_coll += ms.nsamp;
+                if (ms.fault) { flags |= R2P2_F_FAULT; break; }
+                x = cx; y = cy;
+                if (ms.k >= 0) {
+                    if (!(isfinite(cx) && isfinite(cy))) { flags |= R2P2_F_FAULT; break; }   // int(inf) raises
+                    bool f = false;
+                    const bool inwall = px_probe(sv.wall, sv, dtrunc(cx), dtrunc(cy), f);
+                    if (f) { flags |= R2P2_F_FAULT; break; }
+                    if (inwall) {
+                        ncollide++; tmr = 0.0;
+                        const double ex = R2P2_SUB(ms.x, x), ey = R2P2_SUB(ms.y, y);
+                        if (ex > 0.0) x = R2P2_ADD(ms.x, p.rad_p1); else if (ex < 0.0) x = R2P2_SUB(ms.x, p.rad_p1);
+                        if (ey > 0.0) y = R2P2_ADD(ms.y, p.rad_p1); else if (ey < 0.0) y = R2P2_SUB(ms.y, p.rad_p1);
+                    }
+                }
+                const double dW = (double)p.W, dH = (double)p.H, rad = p.radius;
+                if (R2P2_ADD(x, rad) >= dW) {
+                    ncollide++; tmr = 0.0;
+                    if (R2P2_ADD(y, rad) < dH && R2P2_SUB(y, rad) >= 0.0) { }
+                    else if (R2P2_ADD(y, rad) >= dH) y = R2P2_SUB(R2P2_SUB(dH, 1.0), rad);
+                    else y = rad;
+                    x = R2P2_SUB(dW, 1.0);
+                } else if (R2P2_SUB(x, rad) < 0.0) {
+                    ncollide++; tmr = 0.0;
+                    if (R2P2_ADD(y, rad) < dH && R2P2_SUB(y, rad) >= 0.0) { }
+                    else if (R2P2_ADD(y, rad) >= dH) y = R2P2_SUB(R2P2_SUB(dH, 1.0), rad);
+                    else y = rad;
+                    x = 0.0;
+                } else if (R2P2_ADD(y, rad) > dH) {
+                    ncollide++; tmr = 0.0;
+                    y = R2P2_SUB(R2P2_SUB(dH, 1.0), rad);
+                } else if (R2P2_SUB(y, rad) < 0.0) {
+                    ncollide++; tmr = 0.0;
+                    y = rad;
+                }
+                // env[int(x), int(y)] is 50 or __crashing_radius (robot.py:249, 181-186)
+                if (!(isfinite(x) && isfinite(y))) { flags |= R2P2_F_FAULT; break; }
+                bool f = false;
+                bool crash = false;
+                if (p.has50) crash = px_probe(sv.lvl50, sv, dtrunc(x), dtrunc(y), f);
+                else { int ix = dtrunc(x), iy = dtrunc(y); if (ix < 0) ix += p.W; if (iy < 0) iy += p.H; f = ((unsigned)ix >= (unsigned)p.W) | ((unsigned)iy >= (unsigned)p.H); }
+                if (f) { flags |= R2P2_F_FAULT; break; }
+                if (!crash) {
+                    // 360 probes spread over the group; the reference stops at the first wall, so an
+                    // IndexError only counts if it comes before the first wall probe
+                    int first_wall = 360, first_fault = 360;
+                    for (int i = g.sub; i < 360; i += LPR) {
+                        bool pf = false;
+                        const bool wl = px_probe(sv.wall, sv, dtrunc(R2P2_ADD(x, s_crx[i])), dtrunc(R2P2_ADD(y, s_cry[i])), pf);
+                        if (pf) first_fault = min(first_fault, i);
+                        if (wl) first_wall = min(first_wall, i);
+                    }
+                    if (LPR > 1) { first_wall = g.min_i(first_wall); first_fault = g.min_i(first_fault); }
+                    if (first_fault < first_wall) { flags |= R2P2_F_FAULT; break; }
+                    crash = first_wall < 360;
+                }
+                if (crash) { x = last_x; y = last_y; ncollide++; tmr = 0.0; }
+                else { last_x = x; last_y = y; }
+            }
+            ticks++;
+            if (ncollide != ncollide0) flags |= R2P2_F_COLLIDED;
+            if (tracing && g.sub == 0) {
+                double* q = p.tr_pose + trow * 5;
+                q[0] = x; q[1] = y; q[2] = theta; q[3] = speed; q[4] = omega;
+                p.tr_ncoll[trow] = ncollide - ncollide0;
+            }
+        }
+        if (ncollide != p.ncollide[rb]) flags |= R2P2_F_COLLIDED;
+        if (tracing && g.sub == 0) {     // rows of ticks that did not complete: frozen pose (as the oracle records them)
+            for (int t2 = t; t2 < p.T; ++t2) {
+                const size_t trow = (size_t)t2 * (size_t)p.P + rb;
+                double* q = p.tr_pose + trow * 5;
+                q[0] = x; q[1] = y; q[2] = theta; q[3] = speed; q[4] = omega;
+                p.tr_ncoll[trow] = (t2 == t) ? (ncollide - ncollide0) : 0u;
+            }
+        }
+        if (!(flags & R2P2_F_DONE))      // controller.fitness() after the last update
+            fitness = R2P2_ADD(dist, r2p2_norm2(R2P2_SUB(odom_x, origin_x), R2P2_SUB(odom_y, origin_y)));
+        const unsigned ns_sonar = (LPR == 1) ? my_ns_sonar : g.sum_u(my_ns_sonar);
+        if (g.sub == 0) {
+            p.x[rb] = x; p.y[rb] = y; p.theta[rb] = theta; p.speed[rb] = speed; p.omega[rb] = omega;
+            p.last_x[rb] = last_x; p.last_y[rb] = last_y;
+            p.dist[rb] = dist; p.odom_x[rb] = odom_x; p.odom_y[rb] = odom_y;
+            p.time[rb] = tmr; p.fitness[rb] = fitness;
+            p.flags[rb] = flags; p.ncollide[rb] = ncollide; p.ticks[rb] = ticks;
+            p.nsamp_sonar[rb] += ns_sonar; p.nsamp_coll[rb] += ns_coll;
+        }
+        g.sync();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// small service kernels
+// ---------------------------------------------------------------------------------------------
+// levels[x*H + y] (uint8) -> bit planes [H][wpr]; one thread per output word
+__global__ void pack_stage_kernel(const uint8_t* __restrict__ levels, int W, int H, int wpr,
+                                  uint32_t* __restrict__ wall, uint32_t* __restrict__ lvl50, int* __restrict__ has50) {
+    const int iy = blockIdx.x * blockDim.x + threadIdx.x;
+    const int wx = blockIdx.y;
+    if (iy >= H) return;
+    uint32_t bw = 0u, b5 = 0u;
+    for (int b = 0; b < 32; ++b) {
+        const int ix = wx * 32 + b;
+        if (ix < W) {
+            const uint8_t v = levels[(size_t)ix * H + iy];
+            bw |= (uint32_t)(v == 0) << b;
+            b5 |= (uint32_t)(v == 50) << b;
+        }
+    }
+    wall[(size_t)iy * wpr + wx] = bw;
+    lvl50[(size_t)iy * wpr + wx] = b5;
+    if (b5) atomicOr(has50, 1);
+}
+
+__global__ void i32_to_u8_kernel(const int32_t* __restrict__ in, uint8_t* __restrict__ out, size_t n, int* __restrict__ bad) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int32_t v = in[i];
+    if (v < 0 || v > 255) atomicOr(bad, 1);
+    out[i] = (uint8_t)v;
+}
+
+// [P][G] -> [G][P]
+__global__ void transpose_genomes_kernel(const double* __restrict__ in, double* __restrict__ out, int P, int G) {
+    __shared__ double tile[32][33];
+    const int p0 = blockIdx.x * 32, g0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int pp = p0 + r, gg = g0 + threadIdx.x;
+        if (pp < P && gg < G) tile[r][threadIdx.x] = in[(size_t)pp * G + gg];
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int gg = g0 + r, pp = p0 + threadIdx.x;
+        if (pp < P && gg < G) out[(size_t)gg * P + pp] = tile[threadIdx.x][r];
+    }
+}
+
+struct ResetParams {
+    int P, n;
+    const double *x0, *y0, *theta0;
+    double time_budget;
+    double *x, *y, *theta, *speed, *omega, *last_x, *last_y, *dist, *odom_x, *odom_y, *origin_x, *origin_y, *time, *fitness;
+    uint32_t *flags, *ncollide, *ticks;
+    unsigned long long *nsamp_sonar, *nsamp_coll;
+};
+__global__ void reset_kernel(const ResetParams r) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= r.P) return;
+    const int s = (r.n == 1) ? 0 : i;
+    const double x = r.x0[s], y = r.y0[s];
+    r.x[i] = x; r.y[i] = y; r.theta[i] = r.theta0[s]; r.speed[i] = 0.0; r.omega[i] = 0.0;
+    r.last_x[i] = x; r.last_y[i] = y; r.dist[i] = 0.0;
+    r.odom_x[i] = x; r.odom_y[i] = y; r.origin_x[i] = x; r.origin_y[i] = y;
+    r.time[i] = r.time_budget; r.fitness[i] = 0.0;
+    r.flags[i] = 0u; r.ncollide[i] = 0u; r.ticks[i] = 0u;
+    r.nsamp_sonar[i] = 0ull; r.nsamp_coll[i] = 0ull;
+}
+
+__global__ void sum_counters_kernel(const unsigned long long* __restrict__ a, const unsigned long long* __restrict__ b,
+                                    const uint32_t* __restrict__ ticks, int P, unsigned long long* __restrict__ out3) {
+    unsigned long long sa = 0, sb = 0, st = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P; i += gridDim.x * blockDim.x) { sa += a[i]; sb += b[i]; st += ticks[i]; }
+    for (int o = 16; o > 0; o >>= 1) {
+        sa += __shfl_xor_sync(0xffffffffu, sa, o);
+        sb += __shfl_xor_sync(0xffffffffu, sb, o);
+        st += __shfl_xor_sync(0xffffffffu, st, o);
+    }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(out3, sa); atomicAdd(out3 + 1, sb); atomicAdd(out3 + 2, st); }
+}
+
+// raw rays: one thread per ray, planes read through L1/L2
+__global__ void cast_rays_kernel(StageView sv, const double* __restrict__ sincostab, int n,
+                                 const double* __restrict__ ox, const double* __restrict__ oy, const double* __restrict__ ang,
+                                 const double* __restrict__ limit, int32_t* __restrict__ status, double* __restrict__ hx,
+                                 double* __restrict__ hy, int32_t* __restrict__ kk, uint32_t* __restrict__ nsamp) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int ok = 1;
+    double vs, vc;
+    r2p2_sincos(ang[i], sincostab, &vs, &vc, &ok);
+    if (!ok) { status[i] = -1; hx[i] = -1; hy[i] = -1; kk[i] = -1; nsamp[i] = 0; return; }
+    const Hit h = march(sv, ox[i], oy[i], vc, vs, limit[i]);
+    status[i] = h.fault ? -1 : (h.k >= 0 ? 1 : 0);
+    hx[i] = h.x; hy[i] = h.y; kk[i] = h.k; nsamp[i] = h.nsamp;
+}
+
+}  // namespace r2p2

@@ -1,0 +1,182 @@
+"""BatchSim: Python face of the C ABI -- one population of robots on one GPU.
+
+Host code only (numpy in, numpy out).  All arithmetic happens in the CUDA library.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _lib
+from ._lib import R2P2Error, check
+
+CTRL = {"const": 0, "neuro": 1, "linear": 2}
+ACT = {"identity": 0, "tanh": 1, "relu": 2, "logistic": 3}
+F_COLLIDED, F_FAULT, F_DONE, F_TRIGRANGE = 1, 2, 4, 8
+
+
+def expand_sonars(sonars):
+    """Ray angles as the reference builds them: a list is taken as given
+    (utils.search_in_all_directions_with_angles_and_offset_with_limit, r2p2/utils.py:497-514); an int n
+    means ``range(0, 360, floor(365/n))`` (r2p2/utils.py:465-466) -- 16 'sonars' are 17 rays."""
+    if isinstance(sonars, (list, tuple, np.ndarray)):
+        return [float(a) for a in sonars]
+    return [float(i) for i in range(0, 360, math.floor(365 / int(sonars)))]
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class BatchSim:
+    """A population of identical robots on one stage, evaluated by one kernel launch per ``run``."""
+
+    def __init__(self, device=0):
+        self._L = _lib.lib()
+        h = C.c_void_p()
+        rc = self._L.r2p2_create(int(device), C.byref(h))
+        if rc != 0:
+            msg = self._L.r2p2_last_error(None)
+            raise R2P2Error("r2p2_create failed (%d): %s" % (rc, msg.decode() if msg else "?"))
+        self._h = h
+        self.device = int(device)
+        self.P = self.G = self.R = 0
+        self._trace_T = 0
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.r2p2_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        check(self._h, rc)
+
+    # ---- configuration -----------------------------------------------------------------------
+    def set_stage(self, env):
+        """env[x, y] grey levels as the reference holds them after its transpose (shape (W, H))."""
+        env = np.asarray(env)
+        if env.ndim != 2:
+            raise ValueError("stage must be 2-D (W, H)")
+        if env.dtype == np.uint8:
+            e = np.ascontiguousarray(env)
+            self._ck(self._L.r2p2_set_stage(self._h, e.ctypes.data, e.shape[0], e.shape[1]))
+        else:
+            e = np.ascontiguousarray(env, dtype=np.int32)
+            self._ck(self._L.r2p2_set_stage_i32(self._h, e.ctypes.data, e.shape[0], e.shape[1]))
+        self.W, self.H = e.shape
+
+    def set_robot(self, *, sonar_range, radius, max_speed, sonars):
+        rays = _f64(expand_sonars(sonars))
+        self.R = len(rays)
+        self._ck(self._L.r2p2_set_robot(self._h, float(sonar_range[0]), float(sonar_range[1]), float(radius),
+                                        float(max_speed), rays.ctypes.data, self.R))
+
+    def set_controller(self, kind, hidden_layer=None, activation="tanh"):
+        if kind == "neuro":
+            layers = np.asarray([self.R] + list(hidden_layer) + [2], dtype=np.int32)
+            self._ck(self._L.r2p2_set_controller(self._h, CTRL[kind], layers.ctypes.data, len(layers), ACT[activation]))
+        else:
+            self._ck(self._L.r2p2_set_controller(self._h, CTRL[kind], None, 0, 0))
+
+    def set_mapping(self, lanes_per_robot=0, stage_in_smem=-1):
+        self._ck(self._L.r2p2_set_mapping(self._h, int(lanes_per_robot), int(stage_in_smem)))
+
+    # ---- population ----------------------------------------------------------------------------
+    def upload_genomes(self, genomes):
+        g = _f64(genomes)
+        if g.ndim != 2:
+            raise ValueError("genomes must be [P, G]")
+        self._keep = [g]
+        self.P, self.G = g.shape
+        self._ck(self._L.r2p2_upload_genomes(self._h, g.ctypes.data, self.P, self.G))
+
+    def upload_genomes_ptr(self, host_ptr, P, G):
+        """Host pointer variant (e.g. a pinned torch tensor's data_ptr()); the buffer must stay alive."""
+        self.P, self.G = int(P), int(G)
+        self._ck(self._L.r2p2_upload_genomes(self._h, C.c_void_p(int(host_ptr)), self.P, self.G))
+
+    def set_genomes_device(self, dev_ptr, P, G):
+        self.P, self.G = int(P), int(G)
+        self._ck(self._L.r2p2_set_genomes_device(self._h, C.c_void_p(int(dev_ptr)), self.P, self.G))
+
+    def reset(self, x0, y0, theta0=0.0, time_budget=20000.0):
+        x0, y0, t0 = np.atleast_1d(_f64(x0)), np.atleast_1d(_f64(y0)), np.atleast_1d(_f64(theta0))
+        n = max(len(x0), len(y0), len(t0))
+        if n > 1:
+            x0, y0, t0 = (_f64(np.broadcast_to(a, (n,))) for a in (x0, y0, t0))
+        self._ck(self._L.r2p2_reset(self._h, x0.ctypes.data, y0.ctypes.data, t0.ctypes.data, n, float(time_budget)))
+
+    # ---- execution -----------------------------------------------------------------------------
+    def run(self, T, delta=0.1, delta_ctrl=None, evolve=False):
+        self._ck(self._L.r2p2_run(self._h, int(T), float(delta), float(delta if delta_ctrl is None else delta_ctrl), int(bool(evolve))))
+
+    def sync(self):
+        self._ck(self._L.r2p2_sync(self._h))
+
+    def last_run_ms(self):
+        ms = C.c_float()
+        self._ck(self._L.r2p2_last_run_ms(self._h, C.byref(ms)))
+        return ms.value
+
+    # ---- results ---------------------------------------------------------------------------------
+    def fitness(self, out=None):
+        f = np.empty(self.P) if out is None else out
+        self._ck(self._L.r2p2_read_fitness(self._h, f.ctypes.data))
+        return f
+
+    def read_fitness_ptr(self, host_ptr):
+        self._ck(self._L.r2p2_read_fitness(self._h, C.c_void_p(int(host_ptr))))
+
+    def state(self):
+        P = self.P
+        d = {k: np.empty(P) for k in ("x", "y", "theta", "speed", "omega")}
+        u = {k: np.empty(P, dtype=np.uint32) for k in ("flags", "ncollide", "ticks")}
+        self._ck(self._L.r2p2_read_state(self._h, *[d[k].ctypes.data for k in ("x", "y", "theta", "speed", "omega")],
+                                         *[u[k].ctypes.data for k in ("flags", "ncollide", "ticks")]))
+        d.update(u)
+        return d
+
+    def counters(self):
+        a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self._ck(self._L.r2p2_read_counters(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return {"sonar_samples": a.value, "collision_samples": b.value, "robot_steps": c.value}
+
+    def fitness_device_ptr(self):
+        p = C.c_void_p()
+        self._ck(self._L.r2p2_fitness_device(self._h, C.byref(p)))
+        return p.value
+
+    def launch_count(self):
+        n = C.c_uint64()
+        self._ck(self._L.r2p2_launch_count(self._h, C.byref(n)))
+        return n.value
+
+    # ---- trace -----------------------------------------------------------------------------------
+    def set_trace(self, enable, T_max=1):
+        self._ck(self._L.r2p2_set_trace(self._h, int(bool(enable)), int(T_max)))
+        self._trace_T = int(T_max) if enable else 0
+
+    def trace(self, T):
+        P, R = self.P, self.R
+        out = {"pose": np.empty((T, P, 5)), "dst": np.empty((T, P, R)), "hitk": np.empty((T, P, R), dtype=np.int32),
+               "hitpx": np.empty((T, P, R, 2), dtype=np.int32), "nsamp": np.empty((T, P, R), dtype=np.uint32),
+               "ncoll": np.empty((T, P), dtype=np.uint32)}
+        self._ck(self._L.r2p2_read_trace(self._h, int(T), *[out[k].ctypes.data for k in ("pose", "dst", "hitk", "hitpx", "nsamp", "ncoll")]))
+        return out
+
+    # ---- raw rays ----------------------------------------------------------------------------------
+    def cast_rays(self, ox, oy, angle_rad, limit):
+        ox, oy, ang, lim = (_f64(a) for a in (ox, oy, angle_rad, limit))
+        n = len(ox)
+        st = np.empty(n, dtype=np.int32); k = np.empty(n, dtype=np.int32); ns = np.empty(n, dtype=np.uint32)
+        hx = np.empty(n); hy = np.empty(n)
+        self._ck(self._L.r2p2_cast_rays(self._h, n, ox.ctypes.data, oy.ctypes.data, ang.ctypes.data, lim.ctypes.data,
+                                        st.ctypes.data, hx.ctypes.data, hy.ctypes.data, k.ctypes.data, ns.ctypes.data))
+        return {"status": st, "hx": hx, "hy": hy, "k": k, "nsamp": ns}

@@ -1,0 +1,48 @@
+"""Shared test data: stages, robot configs (numbers of the reference's conf/*.json), golden loaders."""
+import json
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLDEN = os.path.join(HERE, "golden")
+STAGES = ["track_2.png", "stage.png", "track.png"]
+
+# the robot jsons shipped by the reference (conf/robot-neuro.json, robot_omni.json, robot-track.json, robot.json)
+ROBOTS = {
+    "robot-neuro.json": dict(x=230, y=250, orientation=0, sonar_range=[0.5, 25], radius=5, sonars=[0, 45, 70, 290, 315], max_speed=50),
+    "robot_omni.json": dict(x=193, y=249, orientation=0, sonar_range=[1, 50], radius=5, sonars=8, max_speed=50),
+    "robot-track.json": dict(x=260, y=250, orientation=0, sonar_range=[0.5, 40], radius=5, sonars=[0, 45, 70, 290, 315], max_speed=50),
+    "robot.json": dict(x=260, y=200, orientation=0, sonar_range=[0.5, 25], radius=5, sonars=[0, 45, 70, 290, 315], max_speed=50),
+}
+
+
+def load_stage(name):
+    """env[x, y] int32 exactly as the reference builds it (fixture recorded by tests/golden/make_golden.py)."""
+    return np.load(os.path.join(GOLDEN, "stage_%s.npz" % name.replace(".png", "")))["env"].astype(np.int32)
+
+
+def golden(name):
+    return np.load(os.path.join(GOLDEN, name + ".npz"))
+
+
+def episode_specs():
+    e = golden("episodes")
+    return e, json.loads(str(e["specs"]))
+
+
+def oracle_robot_kwargs(rj):
+    from oracle.oracle import expand_sonars
+    r = ROBOTS[rj]
+    return dict(rays=expand_sonars(r["sonars"]), vr=r["sonar_range"], radius=r["radius"], max_speed=r["max_speed"])
+
+
+def make_sim(stage, rj, ctrl, hidden=None, activation="tanh", lpr=0, smem=-1, device=0):
+    import r2p2_b200
+    r = ROBOTS[rj]
+    sim = r2p2_b200.BatchSim(device)
+    sim.set_stage(load_stage(stage) if isinstance(stage, str) else stage)
+    sim.set_robot(sonar_range=r["sonar_range"], radius=r["radius"], max_speed=r["max_speed"], sonars=r["sonars"])
+    sim.set_controller(ctrl, hidden_layer=hidden, activation=activation)
+    sim.set_mapping(lpr, smem)
+    return sim
