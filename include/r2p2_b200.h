@@ -77,6 +77,13 @@ int r2p2_destroy(r2p2_handle h);
 const char* r2p2_last_error(r2p2_handle h);            /* h may be NULL: error of the last failed create */
 int r2p2_version(void);
 
+/* Run everything on the caller's CUDA stream (a cudaStream_t passed as void*, e.g. torch's current
+ * stream) instead of the handle's own non-blocking stream; NULL switches back. */
+int r2p2_set_stream(r2p2_handle h, void* cuda_stream);
+/* Measured FP64 issue peak of this device: a register-resident DFMA loop over all SMs; returns DFMA
+ * thread-instructions per second (the denominator of the FP64-issue roofline). */
+int r2p2_fp64_peak(r2p2_handle h, double* dfma_per_s);
+
 /* ---- configuration ------------------------------------------------------------------------- */
 /* Stage as the reference holds it after the transpose: levels[x*H + y], grey level 0..255
  * (0 = wall; 50 = the "crash" level tested at robot.py:249).  Packed on the device into
@@ -148,6 +155,11 @@ int r2p2_read_trace(r2p2_handle h, int32_t T, double* pose, double* dst, int32_t
  * status: 1 hit, 0 miss, -1 fault (IndexError in the reference). */
 int r2p2_cast_rays(r2p2_handle h, int32_t n, const double* ox, const double* oy, const double* angle_rad,
                    const double* limit, int32_t* status, double* hx, double* hy, int32_t* k, uint32_t* nsamp);
+
+/* Same rays through the plain sample-by-sample restatement of the loop (no distance-field skipping): the
+ * in-library cross-check of r2p2_cast_rays. */
+int r2p2_cast_rays_plain(r2p2_handle h, int32_t n, const double* ox, const double* oy, const double* angle_rad,
+                         const double* limit, int32_t* status, double* hx, double* hy, int32_t* k, uint32_t* nsamp);
 
 #ifdef __cplusplus
 }

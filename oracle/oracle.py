@@ -43,7 +43,7 @@ ROBOT_DTYPE = np.dtype([(n, "<f8") for n in ("x", "y", "theta", "speed", "omega"
 
 def build(force=False):
     """Compile both oracle flavours into oracle/_build/ (gcc; a few seconds)."""
-    libs = [os.path.join(_BUILD, n) for n in ("libr2p2_oracle.so", "libr2p2_oracle_port.so")]
+    libs = [os.path.join(_BUILD, n) for n in ("libr2p2_oracle.so", "libr2p2_oracle_port.so", "libr2p2_mathcheck.so")]
     if force or not all(os.path.exists(p) for p in libs):
         subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
     return libs

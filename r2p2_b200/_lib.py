@@ -40,6 +40,8 @@ _SIGS = {
     "r2p2_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
     "r2p2_destroy": (C.c_int, [C.c_void_p]),
     "r2p2_last_error": (C.c_char_p, [C.c_void_p]),
+    "r2p2_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "r2p2_fp64_peak": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "r2p2_set_stage": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
     "r2p2_set_stage_i32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
     "r2p2_set_robot": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_int32]),
@@ -59,6 +61,7 @@ _SIGS = {
     "r2p2_set_trace": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32]),
     "r2p2_read_trace": (C.c_int, [C.c_void_p, C.c_int32] + [C.c_void_p] * 6),
     "r2p2_cast_rays": (C.c_int, [C.c_void_p, C.c_int32] + [C.c_void_p] * 9),
+    "r2p2_cast_rays_plain": (C.c_int, [C.c_void_p, C.c_int32] + [C.c_void_p] * 9),
 }
 EXPORTS = tuple(_SIGS)
 

@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -31,6 +32,7 @@ struct StateArrays {
 struct r2p2_sim {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t own_stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool ev_valid = false;
     std::string err;
@@ -40,6 +42,7 @@ struct r2p2_sim {
     int W = 0, H = 0, wpr = 0, has50 = 0;
     uint32_t plane_bytes = 0;
     uint32_t *d_wall = nullptr, *d_l50 = nullptr;
+    uint8_t* d_dist = nullptr;       // Chebyshev distance field [H][W]
     // robot
     bool have_robot = false;
     int R = 0;
@@ -146,10 +149,19 @@ int pack_stage(r2p2_handle h, const uint8_t* d_levels, int W, int H) {
     pack_stage_kernel<<<grid, 128, 0, h->stream>>>(d_levels, W, H, wpr, h->d_wall, h->d_l50, d_has);
     h->launches++;
     CK(cudaGetLastError());
+    // distance field (Chebyshev distance to the nearest wall / outer-ring pixel, saturated at 255)
+    uint8_t* d_hrow = nullptr;
+    CK(cudaMalloc(&d_hrow, (size_t)W * H));
+    CK(dalloc(&h->d_dist, (size_t)W * H));
+    dist_rows_kernel<<<(H + 63) / 64, 64, 0, h->stream>>>(d_levels, W, H, d_hrow);
+    dist_cols_kernel<<<dim3((W + 127) / 128, H), 128, 0, h->stream>>>(d_hrow, W, H, h->d_dist);
+    h->launches += 2;
+    CK(cudaGetLastError());
     int has = 0;
     CK(cudaMemcpyAsync(&has, d_has, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     cudaFree(d_has);
+    cudaFree(d_hrow);
     h->W = W; h->H = H; h->wpr = wpr; h->has50 = has; h->plane_bytes = (uint32_t)bytes;
     return R2P2_OK;
 }
@@ -191,16 +203,18 @@ int launch_episode(r2p2_handle h, const KParams& kp, size_t smem) {
 
 template <int LPR>
 int launch_episode_s(r2p2_handle h, const KParams& kp, bool smem_stage) {
-    const size_t smem = episode_smem_bytes(LPR, smem_stage, kp.plane_bytes, kp.has50, kp.maxw);
+    const size_t smem = episode_smem_bytes(LPR, smem_stage, kp.plane_bytes, kp.has50, kp.maxw, kp.w_in_smem, kp.G);
     return smem_stage ? launch_episode<LPR, true>(h, kp, smem) : launch_episode<LPR, false>(h, kp, smem);
 }
 
 int choose_lpr(const r2p2_handle h) {
     if (h->lpr_req) return h->lpr_req;
-    const long long lanes_wanted = (long long)h->sm_count * 1024;   // ~half of the resident-thread capacity
-    if ((long long)h->P >= lanes_wanted) return 1;
-    if ((long long)h->P * 8 >= lanes_wanted) return 8;
-    return 32;
+    // Widest group whose whole population is resident at once (the kernel holds ~128 registers per thread, so an SM
+    // keeps 512 threads in flight).  Measured on B200: P=1024 -> 32 lanes, P=8192 -> 8, P=65536 -> 1.
+    const long long resident = (long long)h->sm_count * 512;
+    for (int lpr = 32; lpr > 1; lpr >>= 1)
+        if ((long long)h->P * lpr <= resident) return lpr;
+    return 1;
 }
 
 }  // namespace
@@ -231,7 +245,8 @@ int r2p2_create(int device, r2p2_handle* out) {
     s->sm_count = prop.multiProcessorCount;
     s->smem_optin = prop.sharedMemPerBlockOptin;
     e = cudaSetDevice(device);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking);
+    s->stream = s->own_stream;
     if (e == cudaSuccess) e = cudaEventCreate(&s->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&s->ev1);
     if (e == cudaSuccess) e = cudaMalloc(&s->d_work, sizeof(unsigned int));
@@ -254,12 +269,43 @@ int r2p2_destroy(r2p2_handle h) {
     StateArrays& s = h->st;
     void* ptrs[] = {s.x, s.y, s.theta, s.speed, s.omega, s.last_x, s.last_y, s.dist, s.odom_x, s.odom_y, s.origin_x, s.origin_y,
                     s.time, s.fitness, s.flags, s.ncollide, s.ticks, s.nsamp_sonar, s.nsamp_coll, h->d_x0, h->d_y0, h->d_t0,
-                    h->d_wall, h->d_l50, h->d_crxy, h->d_sincostab, h->d_genomes, h->d_genomes_t, h->d_work, h->d_cnt3};
+                    h->d_wall, h->d_l50, h->d_dist, h->d_crxy, h->d_sincostab, h->d_genomes, h->d_genomes_t, h->d_work, h->d_cnt3};
     for (void* p : ptrs) cudaFree(p);
     free_trace(h);
     cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
-    cudaStreamDestroy(h->stream);
+    cudaStreamDestroy(h->own_stream);
     delete h;
+    return R2P2_OK;
+}
+
+int r2p2_set_stream(r2p2_handle h, void* cuda_stream) {
+    if (!h) return R2P2_E_ARG;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    h->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : h->own_stream;
+    return R2P2_OK;
+}
+
+int r2p2_fp64_peak(r2p2_handle h, double* dfma_per_s) {
+    if (!h || !dfma_per_s) return R2P2_E_ARG;
+    CK(cudaSetDevice(h->device));
+    const int blocks = h->sm_count * 8, threads = 256, iters = 1 << 16;
+    double* d = nullptr;
+    CK(cudaMalloc(&d, sizeof(double) * blocks * threads));
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+        CK(cudaEventRecord(h->ev0, h->stream));
+        fp64_peak_kernel<<<blocks, threads, 0, h->stream>>>(d, iters);
+        CK(cudaEventRecord(h->ev1, h->stream));
+        h->launches++;
+        CK(cudaEventSynchronize(h->ev1));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+        if (rep > 0) best = std::min(best, ms);
+    }
+    h->ev_valid = false;
+    cudaFree(d);
+    *dfma_per_s = (double)blocks * threads * 8.0 * iters / (best * 1e-3);
     return R2P2_OK;
 }
 
@@ -408,6 +454,9 @@ int r2p2_run(r2p2_handle h, int32_t T, double delta, double delta_ctrl, int32_t 
     memset(&kp, 0, sizeof kp);
     kp.W = h->W; kp.H = h->H; kp.wpr = h->wpr; kp.has50 = h->has50;
     kp.g_wall = h->d_wall; kp.g_lvl50 = h->d_l50; kp.plane_bytes = h->plane_bytes;
+    kp.g_dist = h->d_dist;
+    kp.crash_clear = (int)std::ceil(std::fabs(h->radius)) + 2;
+    if (!(h->radius >= 0.0 && h->radius < 250.0)) kp.crash_clear = 1 << 20;   // never skip the ring
     kp.R = h->R;
     memcpy(kp.ray_deg, h->ray_deg, sizeof(double) * (size_t)h->R);
     kp.vr1 = h->vr1; kp.radius = h->radius; kp.max_speed = h->max_speed;
@@ -457,11 +506,13 @@ int r2p2_run(r2p2_handle h, int32_t T, double delta, double delta_ctrl, int32_t 
         kp.tr_nsamp = h->tr_nsamp; kp.tr_ncoll = h->tr_ncoll;
     }
 
+    // genomes of the robots in flight live in shared memory when the group mapping leaves room for them
+    kp.w_in_smem = (lpr > 1 && (size_t)(kBlock / lpr) * h->G * 8 <= 48 * 1024) ? 1 : 0;
     bool smem_stage;
-    const size_t with_stage = episode_smem_bytes(lpr, true, kp.plane_bytes, kp.has50, kp.maxw);
+    const size_t with_stage = episode_smem_bytes(lpr, true, kp.plane_bytes, kp.has50, kp.maxw, kp.w_in_smem, kp.G);
     if (h->smem_req == 1) smem_stage = true;
     else if (h->smem_req == 0) smem_stage = false;
-    else smem_stage = with_stage <= 100 * 1024;           // keep >= 2 CTAs per SM
+    else smem_stage = false;   // measured on B200: L1-cached global reads of the planes are as fast as the shared copy
     if (smem_stage && with_stage > h->smem_optin) {
         if (h->smem_req == 1) return fail(h, R2P2_E_LIMIT, "stage planes (%zu bytes with tables) exceed shared memory", with_stage);
         smem_stage = false;
@@ -584,8 +635,21 @@ int r2p2_read_trace(r2p2_handle h, int32_t T, double* pose, double* dst, int32_t
     return R2P2_OK;
 }
 
+static int cast_rays_impl(r2p2_handle h, int plain, int32_t n, const double* ox, const double* oy, const double* angle_rad,
+                          const double* limit, int32_t* status, double* hx, double* hy, int32_t* k, uint32_t* nsamp);
+
 int r2p2_cast_rays(r2p2_handle h, int32_t n, const double* ox, const double* oy, const double* angle_rad, const double* limit,
                    int32_t* status, double* hx, double* hy, int32_t* k, uint32_t* nsamp) {
+    return cast_rays_impl(h, 0, n, ox, oy, angle_rad, limit, status, hx, hy, k, nsamp);
+}
+
+int r2p2_cast_rays_plain(r2p2_handle h, int32_t n, const double* ox, const double* oy, const double* angle_rad, const double* limit,
+                         int32_t* status, double* hx, double* hy, int32_t* k, uint32_t* nsamp) {
+    return cast_rays_impl(h, 1, n, ox, oy, angle_rad, limit, status, hx, hy, k, nsamp);
+}
+
+static int cast_rays_impl(r2p2_handle h, int plain, int32_t n, const double* ox, const double* oy, const double* angle_rad,
+                          const double* limit, int32_t* status, double* hx, double* hy, int32_t* k, uint32_t* nsamp) {
     if (!h) return R2P2_E_ARG;
     if (!h->d_wall) return fail(h, R2P2_E_ARG, "no stage");
     if (n < 1 || !ox || !oy || !angle_rad || !limit || !status || !hx || !hy || !k || !nsamp) return fail(h, R2P2_E_ARG, "cast_rays: bad arguments");
@@ -597,8 +661,8 @@ int r2p2_cast_rays(r2p2_handle h, int32_t n, const double* ox, const double* oy,
     CK(cudaMemcpyAsync(d_in + n, oy, nb, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(d_in + 2 * n, angle_rad, nb, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(d_in + 3 * n, limit, nb, cudaMemcpyHostToDevice, h->stream));
-    StageView sv; sv.wall = h->d_wall; sv.lvl50 = h->d_l50; sv.W = h->W; sv.H = h->H; sv.wpr = h->wpr;
-    cast_rays_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(sv, h->d_sincostab, n, d_in, d_in + n, d_in + 2 * n, d_in + 3 * n,
+    StageView sv; sv.wall = h->d_wall; sv.lvl50 = h->d_l50; sv.dist = h->d_dist; sv.W = h->W; sv.H = h->H; sv.wpr = h->wpr;
+    cast_rays_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(sv, plain, h->d_sincostab, n, d_in, d_in + n, d_in + 2 * n, d_in + 3 * n,
                                                              d_i, d_out, d_out + n, d_i + n, reinterpret_cast<uint32_t*>(d_i + 2 * n));
     h->launches++;
     CK(cudaGetLastError());

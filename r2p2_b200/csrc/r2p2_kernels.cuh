@@ -37,7 +37,9 @@ struct KParams {
     int32_t has50;
     const uint32_t* g_wall;            // [H][wpr] bit x of row y set <=> level(x, y) == 0
     const uint32_t* g_lvl50;           //                         <=> level(x, y) == 50
+    const uint8_t* g_dist;             // [H][W] Chebyshev distance to the nearest blocked pixel (wall or outer ring), <= 255
     uint32_t plane_bytes;              // bytes of one plane, multiple of 16
+    int32_t crash_clear;               // distance from which the crash-radius ring cannot touch a wall: ceil(radius) + 2
     // robot
     int32_t R;
     double ray_deg[R2P2_MAX_RAYS];
@@ -46,6 +48,7 @@ struct KParams {
     double rad_p1;                     // radius + 1
     // controller
     int32_t ctrl_kind, n_layers, activation, G, maxw;
+    int32_t w_in_smem;                 // LPR > 1: copy each robot's genome into shared memory at robot start
     int32_t layers[R2P2_MAX_LAYERS];
     const double* genomes;             // [P][G] (LPR > 1) or [G][P] (LPR == 1)
     // run
@@ -67,6 +70,7 @@ struct KParams {
 struct StageView {
     const uint32_t* wall;
     const uint32_t* lvl50;
+    const uint8_t* dist;
     int W, H, wpr;
 };
 
@@ -130,41 +134,160 @@ struct Hit {
 //    own arithmetic sqrt(fma(dy,dy, dx*dx)) < limit.
 //  * `round(p.x) in range(0, W)`: true whenever the truncated pixel index is in [1, W-2]; otherwise the
 //    half-to-even test is evaluated exactly.
-__device__ __forceinline__ Hit march(const StageView& s, double ox, double oy, double vx, double vy, double limit) {
-    Hit r;
-    r.x = -1.0; r.y = -1.0; r.k = -1; r.nsamp = 0u; r.fault = false;
-    int kA = 0, kB = 0x7fffffff;          // k < kA: norm test true; k >= kB: false; else exact
+__device__ __forceinline__ void norm_window(double limit, int& kA, int& kB) {
+    kA = 0; kB = 0x7fffffff;              // k < kA: norm test true; k >= kB: false; else evaluated exactly
     if (limit > -1.0 && limit < 30000.0) {
         kA = (int)ceil(limit - kNormSlack);
         kB = (int)ceil(limit + kNormSlack);
         if (kA < 0) kA = 0;
         if (kB < 0) kB = 0;
     }
+}
+
+// One iteration of the reference loop at (x, y), evaluated with the reference's own tests.
+// returns 0: body ran, no wall; 1: body ran, wall (hit); 2: while-condition false (loop ends); 3: the reference raises
+enum { kSampleFree = 0, kSampleHit = 1, kSampleExit = 2, kSampleFault = 3 };
+__device__ __noinline__ int sample_exact(const uint32_t* __restrict__ wall, int W, int H, int wpr, double x, double y,
+                                         double ox, double oy, double limit, int need_norm) {
+    const int ix = dtrunc(x), iy = dtrunc(y);
+    const bool interior = ((unsigned)(ix - 1) < (unsigned)(W - 2)) & ((unsigned)(iy - 1) < (unsigned)(H - 2));
+    if (!interior) {
+        if (!isfinite(x) || !isfinite(y)) return kSampleFault;               // round(nan/inf) raises
+        const double rx = rint(x), ry = rint(y);
+        if (!(rx >= 0.0 && rx < (double)W && ry >= 0.0 && ry < (double)H)) return kSampleExit;
+    }
+    if (need_norm) {
+        if (!(r2p2_norm2(R2P2_SUB(x, ox), R2P2_SUB(y, oy)) < limit)) return kSampleExit;
+    }
+    int jx = ix, jy = iy;                                                    // env.item(): negative indices wrap
+    if (jx < 0) jx += W;
+    if (jy < 0) jy += H;
+    if ((unsigned)jx >= (unsigned)W || (unsigned)jy >= (unsigned)H) return kSampleFault;
+    return plane_bit(wall, wpr, jx, jy) ? kSampleHit : kSampleFree;
+}
+
+// The plain restatement: every sample goes through sample_exact (kept as the in-kernel cross-check of march).
+__device__ __forceinline__ Hit march_plain(const StageView& s, double ox, double oy, double vx, double vy, double limit) {
+    Hit r;
+    r.x = -1.0; r.y = -1.0; r.k = -1; r.nsamp = 0u; r.fault = false;
+    int kA, kB;
+    norm_window(limit, kA, kB);
     double x = ox, y = oy;
-    const double dW = (double)s.W, dH = (double)s.H;
     for (int k = 0; k < kB; ++k) {
-        const int ix = dtrunc(x), iy = dtrunc(y);
-        const bool interior = ((unsigned)(ix - 1) < (unsigned)(s.W - 2)) & ((unsigned)(iy - 1) < (unsigned)(s.H - 2));
-        if (!interior) {
-            if (!isfinite(x) || !isfinite(y)) { r.fault = true; return r; }     // round(nan/inf) raises
-            const double rx = rint(x), ry = rint(y);
-            if (!(rx >= 0.0 && rx < dW && ry >= 0.0 && ry < dH)) return r;
-        }
-        if (k >= kA) {
-            if (!(r2p2_norm2(R2P2_SUB(x, ox), R2P2_SUB(y, oy)) < limit)) return r;
-        }
+        const int st = sample_exact(s.wall, s.W, s.H, s.wpr, x, y, ox, oy, limit, k >= kA);
+        if (st == kSampleFault) { r.fault = true; return r; }
+        if (st == kSampleExit) return r;
         r.nsamp++;
-        bool w;
-        if (interior) {
-            w = plane_bit(s.wall, s.wpr, ix, iy);
-        } else {
-            bool f = false;
-            w = px_probe(s.wall, s, ix, iy, f);
-            if (f) { r.fault = true; return r; }
-        }
-        if (w) { r.x = x; r.y = y; r.k = k; return r; }
+        if (st == kSampleHit) { r.x = x; r.y = y; r.k = k; return r; }
         x = R2P2_ADD(x, vx);
         y = R2P2_ADD(y, vy);
+    }
+    return r;
+}
+
+// Distance-field march.  s.dist[iy*W + ix] is the Chebyshev distance (saturated at 255) from pixel (ix, iy) to the
+// nearest BLOCKED pixel, blocked = wall (level 0) or the outermost pixel ring of the map.  If the sample at step k
+// falls on a pixel with distance d >= 1 then, because consecutive samples are one unit step apart (pixel indices of
+// sample k+j differ from those of sample k by at most j+1), the samples k .. k+max(1, d-1)-1 all lie on unblocked
+// pixels strictly inside the ring: for them the reference's bounds test is true (pixel index in [1, W-2]), the pixel
+// test is false, and -- for k below the norm window -- the limit test is true.  Only the position has to be carried
+// forward, with the reference's own sequential FP64 additions.  Everything else goes through sample_exact.
+__device__ __forceinline__ Hit march(const StageView& s, double ox, double oy, double vx, double vy, double limit) {
+    Hit r;
+    r.x = -1.0; r.y = -1.0; r.k = -1; r.nsamp = 0u; r.fault = false;
+    int kA, kB;
+    norm_window(limit, kA, kB);
+    double x = ox, y = oy;
+    int k = 0;
+    while (k < kB) {
+        unsigned d = 0u;
+        if (k < kA) {
+            const int ix = dtrunc(x), iy = dtrunc(y);
+            if (((unsigned)ix < (unsigned)s.W) & ((unsigned)iy < (unsigned)s.H)) d = __ldg(s.dist + (size_t)iy * s.W + ix);
+        }
+        if (d == 0u) {
+            const int st = sample_exact(s.wall, s.W, s.H, s.wpr, x, y, ox, oy, limit, k >= kA);
+            if (st == kSampleFault) { r.fault = true; return r; }
+            if (st == kSampleExit) return r;
+            r.nsamp++;
+            if (st == kSampleHit) { r.x = x; r.y = y; r.k = k; return r; }
+            x = R2P2_ADD(x, vx);
+            y = R2P2_ADD(y, vy);
+            ++k;
+        } else {
+            int n = max(1, (int)d - 1);
+            n = min(n, kA - k);
+            r.nsamp += (unsigned)n;
+            k += n;
+            for (; n >= 4; n -= 4) {
+                x = R2P2_ADD(R2P2_ADD(R2P2_ADD(R2P2_ADD(x, vx), vx), vx), vx);
+                y = R2P2_ADD(R2P2_ADD(R2P2_ADD(R2P2_ADD(y, vy), vy), vy), vy);
+            }
+            for (; n > 0; --n) {
+                x = R2P2_ADD(x, vx);
+                y = R2P2_ADD(y, vy);
+            }
+        }
+    }
+    return r;
+}
+
+// Team march: `tl` lanes (tm.mask, this lane is number tm.j) cooperate on ONE ray.  Every lane carries the position
+// forward from the origin with the reference's sequential additions (redundant work is free under SIMT), but lane j
+// only tests the samples of its own contiguous chunk [j*chunk, (j+1)*chunk); the earliest event of the whole ray --
+// hit, loop exit or fault, in the reference's order -- is then picked with one warp-level min-reduction.  A 31-sample
+// sonar ray costs ~ (tl-1)/tl * 31 chained additions + 31/tl pixel tests per lane instead of 31 of each, with no
+// data-dependent branch inside the loops.  tl == 1 degenerates to the plain lock-step loop.
+struct Team {
+    unsigned mask;
+    int j, tl;
+};
+
+__device__ __forceinline__ Hit team_march(const StageView& s, const Team& tm, double ox, double oy, double vx, double vy, double limit) {
+    int kA, kB;
+    norm_window(limit, kA, kB);
+    if (kB == 0x7fffffff) return march_plain(s, ox, oy, vx, vy, limit);     // non-finite / huge limit: uniform in the team
+    Hit r;
+    r.x = -1.0; r.y = -1.0; r.k = -1; r.nsamp = 0u; r.fault = false;
+    const int tl = tm.tl;
+    const int chunk = (kB + tl - 1) / tl;
+    const int k0 = tm.j * chunk;
+    const int k1 = min(kB, k0 + chunk);
+    double x = ox, y = oy;
+    const int pre = min((tl - 1) * chunk, kB);
+    for (int i = 0; i < pre; ++i) {
+        if (i < k0) { x = R2P2_ADD(x, vx); y = R2P2_ADD(y, vy); }
+    }
+    constexpr int kNone = 0x7fffffff;
+    int key = kNone;
+    double hx = -1.0, hy = -1.0;
+    for (int c = 0; c < chunk; ++c) {
+        const int k = k0 + c;
+        if (k < k1 && key == kNone) {
+            const int ix = dtrunc(x), iy = dtrunc(y);
+            const bool interior = ((unsigned)(ix - 1) < (unsigned)(s.W - 2)) & ((unsigned)(iy - 1) < (unsigned)(s.H - 2));
+            int st;
+            if (interior && k < kA) st = plane_bit(s.wall, s.wpr, ix, iy) ? kSampleHit : kSampleFree;
+            else st = sample_exact(s.wall, s.W, s.H, s.wpr, x, y, ox, oy, limit, k >= kA);
+            if (st != kSampleFree) { key = (k << 2) | st; hx = x; hy = y; }
+        }
+        x = R2P2_ADD(x, vx);
+        y = R2P2_ADD(y, vy);
+    }
+    const int best = (tl == 1) ? key : (int)__reduce_min_sync(tm.mask, (unsigned)key);
+    if (best == kNone) { r.nsamp = (unsigned)kB; return r; }
+    const int k = best >> 2, st = best & 3;
+    if (st == kSampleHit) {
+        if (tl > 1) {
+            const int src = __ffs(__ballot_sync(tm.mask, key == best)) - 1;
+            hx = __shfl_sync(tm.mask, hx, src);
+            hy = __shfl_sync(tm.mask, hy, src);
+        }
+        r.x = hx; r.y = hy; r.k = k; r.nsamp = (unsigned)(k + 1);
+    } else if (st == kSampleExit) {
+        r.nsamp = (unsigned)k;
+    } else {
+        r.fault = true; r.nsamp = (unsigned)k;
     }
     return r;
 }
@@ -218,10 +341,12 @@ __device__ __forceinline__ double activate(int kind, double v) {
 //   [.., +plane_bytes)             wall plane      (SMEM_STAGE only)
 //   [.., +plane_bytes)             level-50 plane  (SMEM_STAGE and has50 only)
 //   [.., +2*maxw*NR*8)             MLP / sonar buffers A and B, element i of robot slot r at [i*NR + r]
-__host__ __device__ inline size_t episode_smem_bytes(int lpr, bool smem_stage, uint32_t plane_bytes, int has50, int maxw) {
+//   [.., +NR*G*8)                  genomes of the robots in flight (w_in_smem only), row r at [r*G]
+__host__ __device__ inline size_t episode_smem_bytes(int lpr, bool smem_stage, uint32_t plane_bytes, int has50, int maxw, int w_in_smem, int G) {
     size_t n = 16 + R2P2_SINCOSTAB_LEN * 8 + 720 * 8;
     if (smem_stage) n += (size_t)plane_bytes * (has50 ? 2 : 1);
     n += (size_t)2 * maxw * (kBlock / lpr) * 8;
+    if (w_in_smem) n += (size_t)(kBlock / lpr) * G * 8;
     return n;
 }
 
@@ -242,6 +367,7 @@ __global__ void __launch_bounds__(kBlock) episode_kernel(const __grid_constant__
     }
     double* s_bufA = reinterpret_cast<double*>(cur);
     double* s_bufB = s_bufA + (size_t)p.maxw * NR;
+    double* s_gen = s_bufB + (size_t)p.maxw * NR;         // [NR][G], only when p.w_in_smem
 
     // ---- stage the read-only tables (and the bit planes) into shared memory with the TMA unit ----
     const uint32_t mb = smem_u32(mbar);
@@ -267,6 +393,7 @@ __global__ void __launch_bounds__(kBlock) episode_kernel(const __grid_constant__
     StageView sv;
     sv.wall = SMEM_STAGE ? s_wall : p.g_wall;
     sv.lvl50 = SMEM_STAGE ? s_l50 : p.g_lvl50;
+    sv.dist = p.g_dist;
     sv.W = p.W; sv.H = p.H; sv.wpr = p.wpr;
 
     const Group<LPR> g;
@@ -276,6 +403,8 @@ __global__ void __launch_bounds__(kBlock) episode_kernel(const __grid_constant__
     const int R = p.R;
     const double delta = p.delta;
     const bool tracing = p.tr_pose != nullptr;
+    const int tl = (LPR == 1 || R >= LPR) ? 1 : LPR / R;  // lanes per sonar ray (team size)
+    const int rays_per_round = LPR / tl;
 
     for (;;) {
         // ---- fetch the next robot --------------------------------------------------------------
@@ -292,6 +421,14 @@ __global__ void __launch_bounds__(kBlock) episode_kernel(const __grid_constant__
         double fitness = p.fitness[rb];
         unsigned flags = p.flags[rb], ncollide = p.ncollide[rb], ticks = p.ticks[rb];
         unsigned my_ns_sonar = 0u, ns_coll = 0u;          // my_ns_sonar: this lane's rays only
+        // the genome is read every tick for T ticks: keep it next to the SM
+        const double* gen = p.genomes + (size_t)rb * (size_t)p.G;
+        if (LPR > 1 && p.w_in_smem) {
+            double* dst_g = s_gen + (size_t)slot * p.G;
+            for (int i = g.sub; i < p.G; i += LPR) dst_g[i] = __ldg(gen + i);
+            g.sync();
+            gen = dst_g;
+        }
 
         int t = 0;
         unsigned ncollide0 = ncollide;
@@ -304,26 +441,40 @@ __global__ void __launch_bounds__(kBlock) episode_kernel(const __grid_constant__
             bool fault = !(isfinite(x) && isfinite(y));   // round(nan) / round(inf) raise
             const double ox = rint(x), oy = rint(y);      // Python round(): half to even
             if (!fault) {
-                for (int i = g.sub; i < R; i += LPR) {
-                    const double ang = R2P2_ADD(p.ray_deg[i], theta);
-                    int ok = 1;
-                    double vs, vc;
-                    r2p2_sincos(R2P2_MUL(ang, kRad), s_tab, &vs, &vc, &ok);
-                    if (!ok) { flags |= R2P2_F_TRIGRANGE; fault = true; break; }
-                    const Hit h = march(sv, ox, oy, vc, vs, p.L);
-                    my_ns_sonar += h.nsamp;
-                    if (h.fault) { fault = true; }
-                    double d = (h.k >= 0) ? r2p2_norm2(R2P2_SUB(h.x, ox), R2P2_SUB(h.y, oy)) : r2p2_from_bits(0x7ff0000000000000ULL);
-                    if ((d < p.db_hi && d > p.db_lo) || d > p.L) d = p.L;
-                    bufA[i * NR] = d;
-                    if (tracing) {
-                        p.tr_dst[trow * R + i] = d;
-                        p.tr_hitk[trow * R + i] = h.k;
-                        p.tr_hitpx[(trow * R + i) * 2] = (h.k >= 0) ? dtrunc(h.x) : -1;
-                        p.tr_hitpx[(trow * R + i) * 2 + 1] = (h.k >= 0) ? dtrunc(h.y) : -1;
-                        p.tr_nsamp[trow * R + i] = h.nsamp;
+                // rays are spread over the group: `tl` lanes per ray (team march) when the group has lanes to spare
+                for (int base = 0; base < R; base += rays_per_round) {
+                    const int i = base + g.sub / tl;
+                    if (g.sub < rays_per_round * tl && i < R) {
+                        const double ang = R2P2_ADD(p.ray_deg[i], theta);
+                        int ok = 1;
+                        double vs, vc;
+                        r2p2_sincos(R2P2_MUL(ang, kRad), s_tab, &vs, &vc, &ok);
+                        if (!ok) { flags |= R2P2_F_TRIGRANGE; fault = true; break; }
+                        Hit h;
+                        if (LPR == 1) {
+                            h = march(sv, ox, oy, vc, vs, p.L);
+                        } else {
+                            Team tm;
+                            tm.tl = tl; tm.j = g.sub % tl;
+                            tm.mask = (tl == 32) ? 0xffffffffu : (((1u << tl) - 1u) << ((threadIdx.x & 31) - tm.j));
+                            h = team_march(sv, tm, ox, oy, vc, vs, p.L);
+                        }
+                        if (h.fault) fault = true;
+                        if (LPR == 1 || g.sub % tl == 0) {
+                            my_ns_sonar += h.nsamp;
+                            double d = (h.k >= 0) ? r2p2_norm2(R2P2_SUB(h.x, ox), R2P2_SUB(h.y, oy)) : r2p2_from_bits(0x7ff0000000000000ULL);
+                            if ((d < p.db_hi && d > p.db_lo) || d > p.L) d = p.L;
+                            bufA[i * NR] = d;
+                            if (tracing) {
+                                p.tr_dst[trow * R + i] = d;
+                                p.tr_hitk[trow * R + i] = h.k;
+                                p.tr_hitpx[(trow * R + i) * 2] = (h.k >= 0) ? dtrunc(h.x) : -1;
+                                p.tr_hitpx[(trow * R + i) * 2 + 1] = (h.k >= 0) ? dtrunc(h.y) : -1;
+                                p.tr_nsamp[trow * R + i] = h.nsamp;
+                            }
+                        }
+                        if (h.fault) break;
                     }
-                    if (h.fault) break;
                 }
             }
             if (LPR > 1) {
@@ -361,8 +512,15 @@ __global__ void __launch_bounds__(kBlock) episode_kernel(const __grid_constant__
                             const double* wp = p.genomes + (size_t)(woff + j) * (size_t)p.P + rb;
                             for (int i = 0; i < nin; ++i) acc = R2P2_FMA(hin[i * NR], __ldg(wp + (size_t)i * nout * (size_t)p.P), acc);
                         } else {
-                            const double* wp = p.genomes + (size_t)rb * (size_t)p.G + woff + j;
-                            for (int i = 0; i < nin; ++i) acc = R2P2_FMA(hin[i * NR], __ldg(wp + i * nout), acc);
+                            const double* wp = gen + woff + j;
+                            int i = 0;
+                            for (; i + 4 <= nin; i += 4) {          // loads first, then the (ordered) FMA chain
+                                const double w0 = wp[i * nout], w1 = wp[(i + 1) * nout], w2 = wp[(i + 2) * nout], w3 = wp[(i + 3) * nout];
+                                const double h0 = hin[i * NR], h1 = hin[(i + 1) * NR], h2 = hin[(i + 2) * NR], h3 = hin[(i + 3) * NR];
+                                acc = R2P2_FMA(h0, w0, acc); acc = R2P2_FMA(h1, w1, acc);
+                                acc = R2P2_FMA(h2, w2, acc); acc = R2P2_FMA(h3, w3, acc);
+                            }
+                            for (; i < nin; ++i) acc = R2P2_FMA(hin[i * NR], wp[i * nout], acc);
                         }
                         hout[j * NR] = last ? acc : activate(p.activation, acc);
                     }
@@ -382,15 +540,14 @@ __global__ void __launch_bounds__(kBlock) episode_kernel(const __grid_constant__
                     for (int i = 0; i < m; ++i) lin = R2P2_ADD(lin, R2P2_MUL(__ldg(p.genomes + (size_t)i * p.P + rb), bufA[i * NR]));
                     for (int i = 0; i < m; ++i) angv = R2P2_ADD(angv, R2P2_MUL(__ldg(p.genomes + (size_t)(n + i) * p.P + rb), bufA[i * NR]));
                 } else {
-                    const double* gp = p.genomes + (size_t)rb * (size_t)p.G;
-                    for (int i = 0; i < m; ++i) lin = R2P2_ADD(lin, R2P2_MUL(__ldg(gp + i), bufA[i * NR]));
-                    for (int i = 0; i < m; ++i) angv = R2P2_ADD(angv, R2P2_MUL(__ldg(gp + n + i), bufA[i * NR]));
+                    for (int i = 0; i < m; ++i) lin = R2P2_ADD(lin, R2P2_MUL(gen[i], bufA[i * NR]));
+                    for (int i = 0; i < m; ++i) angv = R2P2_ADD(angv, R2P2_MUL(gen[n + i], bufA[i * NR]));
                 }
                 v = lin; w = angv;
                 g.sync();
             } else {
                 if (LPR == 1) { v = __ldg(p.genomes + rb); w = __ldg(p.genomes + (size_t)p.P + rb); }
-                else { v = __ldg(p.genomes + (size_t)rb * p.G); w = __ldg(p.genomes + (size_t)rb * p.G + 1); }
+                else { v = gen[0]; w = gen[1]; }
             }
             // Robot.control clamp (robot.py:386-387)
             if (r2p2_fabs(v) > p.max_speed) v = R2P2_MUL(R2P2_DIV(v, r2p2_fabs(v)), p.max_speed);
@@ -412,7 +569,14 @@ __global__ void __launch_bounds__(kBlock) episode_kernel(const __grid_constant__
                 double cs_, cc_;
                 r2p2_sincos(R2P2_MUL(angle, kRad), s_tab, &cs_, &cc_, &ok);
                 if (!ok) { flags |= R2P2_F_TRIGRANGE | R2P2_F_FAULT; break; }   // NaN displacement: the reference faults two statements later
-                const Hit ms = march(sv, x, y, cc_, cs_, R2P2_ADD(r2p2_norm2(dx, dy), p.radius));
+                Hit ms;
+                if (LPR == 1) {
+                    ms = march(sv, x, y, cc_, cs_, R2P2_ADD(r2p2_norm2(dx, dy), p.radius));
+                } else {                                   // the whole group is one team on the collision ray
+                    Team tm;
+                    tm.tl = LPR; tm.j = g.sub; tm.mask = g.mask;
+                    ms = team_march(sv, tm, x, y, cc_, cs_, R2P2_ADD(r2p2_norm2(dx, dy), p.radius));
+                }
                 ns_coll += ms.nsamp;
                 if (ms.fault) { flags |= R2P2_F_FAULT; break; }
                 x = cx; y = cy;
@@ -455,7 +619,15 @@ __global__ void __launch_bounds__(kBlock) episode_kernel(const __grid_constant__
                 if (p.has50) crash = px_probe(sv.lvl50, sv, dtrunc(x), dtrunc(y), f);
                 else { int ix = dtrunc(x), iy = dtrunc(y); if (ix < 0) ix += p.W; if (iy < 0) iy += p.H; f = ((unsigned)ix >= (unsigned)p.W) | ((unsigned)iy >= (unsigned)p.H); }
                 if (f) { flags |= R2P2_F_FAULT; break; }
-                if (!crash) {
+                // Far enough from every blocked pixel (wall or outer ring): none of the 360 probes -- all within
+                // ceil(radius)+1 pixels of the centre pixel -- can be a wall or leave the map, so the ring is skipped.
+                bool ring_clear = false;
+                {
+                    const int cxp = dtrunc(x), cyp = dtrunc(y);
+                    if (((unsigned)cxp < (unsigned)p.W) & ((unsigned)cyp < (unsigned)p.H))
+                        ring_clear = (int)__ldg(p.g_dist + (size_t)cyp * p.W + cxp) >= p.crash_clear;
+                }
+                if (!crash && !ring_clear) {
                     // 360 probes spread over the group; the reference stops at the first wall, so an
                     // IndexError only counts if it comes before the first wall probe
                     int first_wall = 360, first_fault = 360;
@@ -527,6 +699,39 @@ __global__ void pack_stage_kernel(const uint8_t* __restrict__ levels, int W, int
     if (b5) atomicOr(has50, 1);
 }
 
+// Distance field, pass 1: per map row, distance along x to the nearest blocked pixel (wall or outer ring), <= 255.
+// One thread per row (one-time setup work; the walk is sequential in x by nature).
+__global__ void dist_rows_kernel(const uint8_t* __restrict__ levels, int W, int H, uint8_t* __restrict__ hrow) {
+    const int iy = blockIdx.x * blockDim.x + threadIdx.x;
+    if (iy >= H) return;
+    const bool ring_row = (iy == 0) | (iy == H - 1);
+    int run = 0;
+    for (int ix = 0; ix < W; ++ix) {
+        const bool blocked = ring_row | (ix == 0) | (ix == W - 1) | (levels[(size_t)ix * H + iy] == 0);
+        run = blocked ? 0 : min(run + 1, 255);
+        hrow[(size_t)iy * W + ix] = (uint8_t)run;
+    }
+    run = 0;
+    for (int ix = W - 1; ix >= 0; --ix) {
+        const int cur = hrow[(size_t)iy * W + ix];
+        run = (cur == 0) ? 0 : min(run + 1, 255);
+        hrow[(size_t)iy * W + ix] = (uint8_t)min(cur, run);
+    }
+}
+// pass 2: Chebyshev distance D(x, y) = min over dy of max(|dy|, hrow(x, y + dy)); rows outside the map are blocked.
+__global__ void dist_cols_kernel(const uint8_t* __restrict__ hrow, int W, int H, uint8_t* __restrict__ dist) {
+    const int ix = blockIdx.x * blockDim.x + threadIdx.x;
+    const int iy = blockIdx.y;
+    if (ix >= W) return;
+    int best = hrow[(size_t)iy * W + ix];
+    for (int dy = 1; dy < best; ++dy) {
+        const int up = (iy - dy >= 0) ? hrow[(size_t)(iy - dy) * W + ix] : 0;
+        const int dn = (iy + dy < H) ? hrow[(size_t)(iy + dy) * W + ix] : 0;
+        best = min(best, max(dy, min(up, dn)));
+    }
+    dist[(size_t)iy * W + ix] = (uint8_t)best;
+}
+
 __global__ void i32_to_u8_kernel(const int32_t* __restrict__ in, uint8_t* __restrict__ out, size_t n, int* __restrict__ bad) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -583,8 +788,19 @@ __global__ void sum_counters_kernel(const unsigned long long* __restrict__ a, co
     if ((threadIdx.x & 31) == 0) { atomicAdd(out3, sa); atomicAdd(out3 + 1, sb); atomicAdd(out3 + 2, st); }
 }
 
+// FP64 issue-rate probe: 8 independent DFMA chains per thread
+__global__ void fp64_peak_kernel(double* __restrict__ out, int iters) {
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1e-9, a2 = a0 + 2e-9, a3 = a0 + 3e-9, a4 = a0 + 4e-9, a5 = a0 + 5e-9, a6 = a0 + 6e-9, a7 = a0 + 7e-9;
+    const double m = 0.999999999, c = 1e-12;
+    for (int i = 0; i < iters; ++i) {
+        a0 = __fma_rn(a0, m, c); a1 = __fma_rn(a1, m, c); a2 = __fma_rn(a2, m, c); a3 = __fma_rn(a3, m, c);
+        a4 = __fma_rn(a4, m, c); a5 = __fma_rn(a5, m, c); a6 = __fma_rn(a6, m, c); a7 = __fma_rn(a7, m, c);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
 // raw rays: one thread per ray, planes read through L1/L2
-__global__ void cast_rays_kernel(StageView sv, const double* __restrict__ sincostab, int n,
+__global__ void cast_rays_kernel(StageView sv, int plain, const double* __restrict__ sincostab, int n,
                                  const double* __restrict__ ox, const double* __restrict__ oy, const double* __restrict__ ang,
                                  const double* __restrict__ limit, int32_t* __restrict__ status, double* __restrict__ hx,
                                  double* __restrict__ hy, int32_t* __restrict__ kk, uint32_t* __restrict__ nsamp) {
@@ -594,7 +810,7 @@ __global__ void cast_rays_kernel(StageView sv, const double* __restrict__ sincos
     double vs, vc;
     r2p2_sincos(ang[i], sincostab, &vs, &vc, &ok);
     if (!ok) { status[i] = -1; hx[i] = -1; hy[i] = -1; kk[i] = -1; nsamp[i] = 0; return; }
-    const Hit h = march(sv, ox[i], oy[i], vc, vs, limit[i]);
+    const Hit h = plain ? march_plain(sv, ox[i], oy[i], vc, vs, limit[i]) : march(sv, ox[i], oy[i], vc, vs, limit[i]);
     status[i] = h.fault ? -1 : (h.k >= 0 ? 1 : 0);
     hx[i] = h.x; hy[i] = h.y; kk[i] = h.k; nsamp[i] = h.nsamp;
 }

@@ -58,6 +58,16 @@ class BatchSim:
     def _ck(self, rc):
         check(self._h, rc)
 
+    def set_stream(self, cuda_stream):
+        """Run on the caller's CUDA stream (integer cudaStream_t, e.g. torch.cuda.current_stream().cuda_stream)."""
+        self._ck(self._L.r2p2_set_stream(self._h, C.c_void_p(int(cuda_stream)) if cuda_stream else None))
+
+    def fp64_peak(self):
+        """Measured DFMA thread-instructions per second on this device."""
+        v = C.c_double()
+        self._ck(self._L.r2p2_fp64_peak(self._h, C.byref(v)))
+        return v.value
+
     # ---- configuration -----------------------------------------------------------------------
     def set_stage(self, env):
         """env[x, y] grey levels as the reference holds them after its transpose (shape (W, H))."""
@@ -172,11 +182,12 @@ class BatchSim:
         return out
 
     # ---- raw rays ----------------------------------------------------------------------------------
-    def cast_rays(self, ox, oy, angle_rad, limit):
+    def cast_rays(self, ox, oy, angle_rad, limit, plain=False):
         ox, oy, ang, lim = (_f64(a) for a in (ox, oy, angle_rad, limit))
         n = len(ox)
         st = np.empty(n, dtype=np.int32); k = np.empty(n, dtype=np.int32); ns = np.empty(n, dtype=np.uint32)
         hx = np.empty(n); hy = np.empty(n)
-        self._ck(self._L.r2p2_cast_rays(self._h, n, ox.ctypes.data, oy.ctypes.data, ang.ctypes.data, lim.ctypes.data,
-                                        st.ctypes.data, hx.ctypes.data, hy.ctypes.data, k.ctypes.data, ns.ctypes.data))
+        fn = self._L.r2p2_cast_rays_plain if plain else self._L.r2p2_cast_rays
+        self._ck(fn(self._h, n, ox.ctypes.data, oy.ctypes.data, ang.ctypes.data, lim.ctypes.data,
+                st.ctypes.data, hx.ctypes.data, hy.ctypes.data, k.ctypes.data, ns.ctypes.data))
         return {"status": st, "hx": hx, "hy": hy, "k": k, "nsamp": ns}

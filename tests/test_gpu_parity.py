@@ -1,0 +1,307 @@
+"""Parity of the CUDA path (through the C ABI) on a real B200.
+
+Three anchors:
+  * golden vectors recorded from the unmodified reference (rays, single ticks, episodes) -- bit-exact wherever the
+    reference's own arithmetic is reproducible (everything except the sklearn/numpy MLP forward);
+  * the port-flavour oracle on seeded populations -- bit-exact on every output (it runs the same r2p2_math.h);
+  * size-independent properties at BASELINE.json's full sizes (mapping invariance, determinism, counters).
+"""
+import numpy as np
+import pytest
+
+import common
+
+pytestmark = pytest.mark.gpu
+
+MAPPINGS = [(1, 0), (1, 1), (8, 0), (8, 1), (32, 0), (32, 1), (4, -1), (16, -1)]
+
+
+def test_rays_golden():
+    """r2p2_cast_rays == utils.search_edge_in_angle_with_limit (reference r2p2/utils.py:420-432) on 8118 rays."""
+    import r2p2_b200
+    r = common.golden("rays")
+    for si, st in enumerate(list(r["stages"])):
+        m = r["stage"] == si
+        sim = r2p2_b200.BatchSim(0)
+        sim.set_stage(common.load_stage(st))
+        out = sim.cast_rays(r["ox"][m], r["oy"][m], r["angle"][m], r["limit"][m])
+        assert np.array_equal(out["status"], r["hit"][m])
+        assert np.array_equal(out["hx"], r["hx"][m]) and np.array_equal(out["hy"], r["hy"][m])
+        assert np.array_equal(out["nsamp"], r["nsamp"][m].astype(np.uint32))
+        plain = sim.cast_rays(r["ox"][m], r["oy"][m], r["angle"][m], r["limit"][m], plain=True)
+        for k in out:
+            assert np.array_equal(out[k], plain[k]), k
+        sim.close()
+
+
+def test_distance_field_march_equals_plain_march():
+    """The distance-field march (skips pixel look-ups where no wall can be) against the sample-by-sample loop on
+    400k random rays per stage, long limits included: status, hit point bits, hit step and sample count."""
+    import r2p2_b200
+    rs = np.random.RandomState(42)
+    for st in common.STAGES:
+        env = common.load_stage(st)
+        W, H = env.shape
+        n = 400_000
+        ox = np.where(rs.rand(n) < 0.5, rs.randint(0, W, n).astype(float), rs.uniform(-2, W + 2, n))
+        oy = np.where(rs.rand(n) < 0.5, rs.randint(0, H, n).astype(float), rs.uniform(-2, H + 2, n))
+        ang = np.radians(rs.uniform(-720, 720, n))
+        lim = np.where(rs.rand(n) < 0.5, rs.choice([30.0, 45.0, 55.0, 200.0, 1000.0], n), rs.uniform(0.5, 80.0, n))
+        sim = r2p2_b200.BatchSim(0)
+        sim.set_stage(env)
+        a = sim.cast_rays(ox, oy, ang, lim)
+        b = sim.cast_rays(ox, oy, ang, lim, plain=True)
+        for k in a:
+            assert np.array_equal(a[k], b[k]), (st, k)
+        assert (a["status"] == 1).sum() > n // 4
+        sim.close()
+
+
+@pytest.mark.parametrize("lpr,smem", MAPPINGS)
+def test_single_ticks_golden(lpr, smem):
+    """One Robot.update from 4200 reference-recorded states, scripted command: pose, speed, sonar distances and
+    collide() count bit-identical to the reference for every lane mapping."""
+    t = common.golden("ticks")
+    sn, rn = list(t["stages"]), list(t["robots"])
+    total = 0
+    for si, st in enumerate(sn):
+        for ri, rj in enumerate(rn):
+            for delta in np.unique(t["delta"]):
+                m = (t["stage"] == si) & (t["robot"] == ri) & (t["delta"] == delta)
+                if not m.any():
+                    continue
+                sim = common.make_sim(st, rj, "const", lpr=lpr, smem=smem)
+                sim.upload_genomes(np.stack([t["v"][m], t["w"][m]], axis=1))
+                sim.reset(t["x"][m], t["y"][m], t["theta"][m])
+                sim.set_trace(True, 1)
+                sim.run(1, delta=float(delta))
+                s, tr = sim.state(), sim.trace(1)
+                for a, b in (("x", "nx"), ("y", "ny"), ("theta", "ntheta"), ("speed", "nspeed")):
+                    assert np.array_equal(s[a], t[b][m]), (st, rj, a)
+                assert np.array_equal(s["ncollide"], t["ncollide"][m].astype(np.uint32))
+                assert np.array_equal(tr["dst"][0], t["dst"][m][:, :sim.R])
+                assert not (s["flags"] & 2).any()
+                total += int(m.sum())
+                sim.close()
+    assert total == len(t["x"])
+
+
+@pytest.mark.parametrize("lpr", [1, 8, 32])
+def test_episodes_golden(lpr):
+    """Free-running episodes against the reference: linear / constant-command runs bit-identical on every tick; MLP
+    runs (numpy BLAS order + SIMD tanh in the reference) identical in hit steps and collisions, poses and fitness
+    within 1e-9 relative (north-star tolerance 1e-5)."""
+    e, specs = common.episode_specs()
+    for sp in specs:
+        n, rob = sp["name"], common.ROBOTS[sp["robot"]]
+        sim = common.make_sim(sp["stage"], sp["robot"], sp["kind"], hidden=sp["layers"][1:-1] if sp["layers"] else None, lpr=lpr)
+        sim.upload_genomes(e[n + "/genome"][None, :])
+        sim.reset(rob["x"], rob["y"], 0.0)
+        sim.set_trace(True, sp["T"])
+        sim.run(sp["T"], delta=sp["delta"])
+        tr = sim.trace(sp["T"])
+        pose, gp = tr["pose"][:, 0], e[n + "/pose"]
+        assert np.array_equal(np.cumsum(tr["ncoll"][:, 0]), e[n + "/ncoll"]), n
+        if sp["kind"] == "neuro":
+            assert np.array_equal(np.rint(tr["dst"][:, 0]), np.rint(e[n + "/dst"])), n
+            assert np.max(np.abs(pose[:, :3] - gp[:, :3]) / np.maximum(1, np.abs(gp[:, :3]))) < 1e-9, n
+            gf = e[n + "/fitness"][-1]
+            assert abs(sim.fitness()[0] - gf) <= 1e-9 * abs(gf), n
+        else:
+            assert np.array_equal(pose, gp), n
+            assert np.array_equal(tr["dst"][:, 0], e[n + "/dst"]), n
+            if sp["kind"] == "linear":
+                assert sim.fitness()[0] == e[n + "/fitness"][-1], n
+        sim.close()
+
+
+CASES = [("track_2.png", "robot-neuro.json", "neuro", [10, 7, 4], 156, 1.0),
+         ("stage.png", "robot-neuro.json", "neuro", [10, 7, 4], 156, 1.0),
+         ("track.png", "robot-track.json", "neuro", [1], 7, 3.0),
+         ("track_2.png", "robot_omni.json", "linear", None, 18, 0.05),
+         ("track_2.png", "robot-neuro.json", "linear", None, 12, 0.08)]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "%s-%s-%s" % (c[0], c[1], c[2]))
+@pytest.mark.parametrize("evolve", [False, True])
+def test_population_vs_port_oracle(case, evolve, oracle_port):
+    """Seeded populations, 300 ticks: every pose, fitness, flag, tick count, collide count and the sonar / collision
+    sample counters bit-identical to the port-flavour oracle, for 1-, 8- and 32-lane mappings."""
+    stage, rj, kind, hidden, G, scale = case
+    P, T = 384, 300
+    genomes = np.random.RandomState(1234).uniform(-1, 1, (P, G)) * scale
+    rob = common.ROBOTS[rj]
+    kw = common.oracle_robot_kwargs(rj)
+    layers = [len(kw["rays"])] + hidden + [2] if hidden else []
+    ref = oracle_port.run(common.load_stage(stage), ctrl=kind, genomes=genomes, x0=rob["x"], y0=rob["y"], theta0=0.0, T=T, layers=layers,
+                          evolve=evolve, delta_ctrl=33.0, time_budget=20000.0, threads=8, **kw)
+    st = ref["state"]
+    for lpr, smem in ((1, -1), (8, 1), (8, 0), (32, -1)):
+        sim = common.make_sim(stage, rj, kind, hidden=hidden, lpr=lpr, smem=smem)
+        sim.upload_genomes(genomes)
+        sim.reset(rob["x"], rob["y"], 0.0, time_budget=20000.0)
+        sim.run(T, delta=0.1, delta_ctrl=33.0, evolve=evolve)
+        s, f, c = sim.state(), sim.fitness(), sim.counters()
+        for k in ("x", "y", "theta", "speed", "omega", "ncollide", "flags", "ticks"):
+            assert np.array_equal(s[k], st[k]), (k, lpr, smem)
+        assert np.array_equal(f, ref["fitness"])
+        assert c["sonar_samples"] == int(st["nsamp_sonar"].sum()) and c["collision_samples"] == int(st["nsamp_coll"].sum())
+        assert c["robot_steps"] == int(st["ticks"].sum())
+        sim.close()
+
+
+def test_trace_matches_port_oracle(oracle_port):
+    """Per-tick trace (hit step, hit pixel, distance, samples per ray, pose) bit-identical to the oracle."""
+    stage, rj = "track_2.png", "robot-neuro.json"
+    P, T = 64, 120
+    genomes = np.random.RandomState(5).uniform(-1, 1, (P, 156))
+    rob, kw = common.ROBOTS[rj], common.oracle_robot_kwargs(rj)
+    ref = oracle_port.run(common.load_stage(stage), ctrl="neuro", genomes=genomes, x0=rob["x"], y0=rob["y"], theta0=0.0, T=T,
+                          layers=[5, 10, 7, 4, 2], trace=True, **kw)
+    for lpr in (1, 8, 32):
+        sim = common.make_sim(stage, rj, "neuro", hidden=[10, 7, 4], lpr=lpr)
+        sim.upload_genomes(genomes)
+        sim.reset(rob["x"], rob["y"], 0.0)
+        sim.set_trace(True, T)
+        sim.run(T)
+        tr = sim.trace(T)
+        for k in ("pose", "dst", "hitk", "hitpx", "nsamp", "ncoll"):
+            assert np.array_equal(tr[k], ref[k]), (k, lpr)
+        sim.close()
+
+
+def test_per_tick_api_equals_one_launch():
+    """Robot.update drop-in use: T launches of one tick == one launch of T ticks (state round-trips HBM)."""
+    stage, rj = "track_2.png", "robot-neuro.json"
+    genomes = np.random.RandomState(11).uniform(-1, 1, (200, 156))
+    rob = common.ROBOTS[rj]
+    a = common.make_sim(stage, rj, "neuro", hidden=[10, 7, 4])
+    b = common.make_sim(stage, rj, "neuro", hidden=[10, 7, 4])
+    for s in (a, b):
+        s.upload_genomes(genomes)
+        s.reset(rob["x"], rob["y"], 0.0)
+    a.run(50)
+    for _ in range(50):
+        b.run(1)
+    sa, sb = a.state(), b.state()
+    for k in sa:
+        assert np.array_equal(sa[k], sb[k]), k
+    assert np.array_equal(a.fitness(), b.fitness())
+    assert a.counters() == b.counters()
+    a.close(); b.close()
+
+
+def test_start_poses_per_robot_and_faults(oracle_port):
+    """Per-robot start poses (BASELINE config D/E style) incl. robots that start inside a wall or off the map: the
+    reference raises there (IndexError / ValueError); the device sets the fault flag and freezes the robot."""
+    stage, rj = "track.png", "robot-track.json"
+    env = common.load_stage(stage)
+    rs = np.random.RandomState(3)
+    P = 512
+    x0 = rs.uniform(-20, env.shape[0] + 20, P); y0 = rs.uniform(-20, env.shape[1] + 20, P); th0 = rs.uniform(0, 360, P)
+    x0[:4] = [np.nan, np.inf, 100.0, 1e300]
+    genomes = rs.uniform(-3, 3, (P, 7))
+    kw = common.oracle_robot_kwargs(rj)
+    ref = oracle_port.run(env, ctrl="neuro", genomes=genomes, x0=x0, y0=y0, theta0=th0, T=80, layers=[5, 1, 2], threads=4, **kw)
+    for lpr in (1, 8, 32):
+        sim = common.make_sim(stage, rj, "neuro", hidden=[1], lpr=lpr)
+        sim.upload_genomes(genomes)
+        sim.reset(x0, y0, th0)
+        sim.run(80)
+        s = sim.state()
+        assert np.array_equal(s["flags"] & 7, ref["state"]["flags"] & 7)
+        ok = (ref["state"]["flags"] & 2) == 0          # compare poses of the robots the reference keeps alive
+        for k in ("x", "y", "theta", "ncollide", "ticks"):
+            assert np.array_equal(s[k][ok], ref["state"][k][ok]), k
+        assert np.array_equal(sim.fitness()[ok], ref["fitness"][ok])
+        assert int(((ref["state"]["flags"] & 2) != 0).sum()) > 20
+        sim.close()
+
+
+def test_full_size_properties():
+    """BASELINE config B at full size (1024 x 1000): mapping invariance (1/8/32 lanes, smem / L1), run-to-run
+    determinism, sample counters consistent with the trace-free counters of a second run."""
+    stage, rj = "track_2.png", "robot-neuro.json"
+    genomes = np.random.RandomState(1234).uniform(-1, 1, (1024, 156))
+    rob = common.ROBOTS[rj]
+    res = []
+    for lpr, smem in ((32, 1), (32, 0), (8, 1), (1, 0), (32, 1)):
+        sim = common.make_sim(stage, rj, "neuro", hidden=[10, 7, 4], lpr=lpr, smem=smem)
+        sim.upload_genomes(genomes)
+        sim.reset(rob["x"], rob["y"], 0.0)
+        sim.run(1000)
+        res.append((sim.fitness(), sim.state(), sim.counters()))
+        sim.close()
+    f0, s0, c0 = res[0]
+    assert c0["robot_steps"] == 1024 * 1000 and c0["sonar_samples"] > 100 * 1024 * 1000
+    for f, s, c in res[1:]:
+        assert np.array_equal(f, f0) and c == c0
+        for k in s0:
+            assert np.array_equal(s[k], s0[k]), k
+
+
+def test_full_size_vs_oracle_sample(oracle_port):
+    """Config B: a 96-robot sample of the full 1000-tick run bit-identical to the port oracle (fitness + counters)."""
+    stage, rj = "track_2.png", "robot-neuro.json"
+    genomes = np.random.RandomState(1234).uniform(-1, 1, (1024, 156))
+    rob, kw = common.ROBOTS[rj], common.oracle_robot_kwargs(rj)
+    sim = common.make_sim(stage, rj, "neuro", hidden=[10, 7, 4])
+    sim.upload_genomes(genomes)
+    sim.reset(rob["x"], rob["y"], 0.0)
+    sim.run(1000)
+    f = sim.fitness()
+    sel = np.arange(0, 1024, 11)[:96]
+    ref = oracle_port.run(common.load_stage(stage), ctrl="neuro", genomes=genomes[sel], x0=rob["x"], y0=rob["y"], theta0=0.0, T=1000,
+                          layers=[5, 10, 7, 4, 2], threads=8, **kw)
+    assert np.array_equal(f[sel], ref["fitness"])
+    sim.close()
+
+
+def test_activations_and_widths(oracle_port):
+    """relu / logistic / identity activations and a wider net (32-16-8-2 on 32 list-form rays, BASELINE config E shape)."""
+    import r2p2_b200
+    env = common.load_stage("stage.png")
+    rays = [i * 11.25 for i in range(32)]
+    P, T = 128, 60
+    rs = np.random.RandomState(9)
+    free = np.argwhere(env[8:-8, 8:-8] != 0) + 8
+    pick = free[rs.randint(0, len(free), P)]
+    x0, y0, th0 = pick[:, 0].astype(float) + 0.25, pick[:, 1].astype(float) + 0.5, rs.uniform(0, 360, P)
+    for act in ("tanh", "relu", "logistic", "identity"):
+        genomes = rs.uniform(-1, 1, (P, 32 * 16 + 16 * 8 + 8 * 2)) * (0.3 if act in ("relu", "identity") else 1.0)
+        ref = oracle_port.run(env, rays=rays, vr=(0.5, 25), radius=5, max_speed=50, ctrl="neuro", genomes=genomes, x0=x0, y0=y0, theta0=th0,
+                              T=T, layers=[32, 16, 8, 2], activation=act, threads=4)
+        for lpr in (1, 8, 32):
+            sim = r2p2_b200.BatchSim(0)
+            sim.set_stage(env)
+            sim.set_robot(sonar_range=(0.5, 25), radius=5, max_speed=50, sonars=rays)
+            sim.set_controller("neuro", hidden_layer=[16, 8], activation=act)
+            sim.set_mapping(lpr, -1)
+            sim.upload_genomes(genomes)
+            sim.reset(x0, y0, th0)
+            sim.run(T)
+            s = sim.state()
+            assert np.array_equal(s["flags"], ref["state"]["flags"]), (act, lpr)
+            ok = (s["flags"] & 2) == 0
+            assert np.array_equal(s["x"][ok], ref["state"]["x"][ok]) and np.array_equal(s["theta"][ok], ref["state"]["theta"][ok]), (act, lpr)
+            assert np.array_equal(sim.fitness()[ok], ref["fitness"][ok]), (act, lpr)
+            sim.close()
+
+
+def test_error_conventions():
+    """Errors come back as codes + message (never an abort): bad call order, bad sizes."""
+    import r2p2_b200
+    sim = r2p2_b200.BatchSim(0)
+    with pytest.raises(r2p2_b200.R2P2Error):
+        sim.run(1)                                           # nothing configured
+    sim.set_stage(common.load_stage("track.png"))
+    sim.set_robot(sonar_range=(0.5, 25), radius=5, max_speed=50, sonars=[0, 45])
+    sim.set_controller("neuro", hidden_layer=[3])
+    sim.upload_genomes(np.zeros((4, 5)))                     # wrong genome length for 2-3-2
+    sim.reset(100.0, 100.0)
+    with pytest.raises(r2p2_b200.R2P2Error) as ei:
+        sim.run(1)
+    assert "genome length" in str(ei.value)
+    with pytest.raises(r2p2_b200.R2P2Error):
+        sim.set_mapping(3, 0)
+    sim.close()
