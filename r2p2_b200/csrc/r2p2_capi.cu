@@ -181,9 +181,9 @@ int upload_crxy(r2p2_handle h) {
     return R2P2_OK;
 }
 
-template <int LPR, bool SMEM>
+template <int LPR, bool SMEM, class NET>
 int launch_episode(r2p2_handle h, const KParams& kp, size_t smem) {
-    auto kern = episode_kernel<LPR, SMEM>;
+    auto kern = episode_kernel<LPR, SMEM, NET>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kBlock, smem));
@@ -201,10 +201,31 @@ int launch_episode(r2p2_handle h, const KParams& kp, size_t smem) {
     return R2P2_OK;
 }
 
+template <class NET>
+bool net_matches(const KParams& kp) {
+    if (kp.ctrl_kind != R2P2_CTRL_NEURO || kp.n_layers != NET::kLayers) return false;
+    for (int l = 0; l < NET::kLayers; ++l)
+        if (kp.layers[l] != NET::sz(l)) return false;
+    return true;
+}
+
 template <int LPR>
-int launch_episode_s(r2p2_handle h, const KParams& kp, bool smem_stage) {
+int launch_episode_s(r2p2_handle h, KParams& kp, bool smem_stage) {
+    // the reference's shipped network shapes have fixed-shape instances (weights in registers; chosen unless the shared-memory
+    // stage copy is requested, which keeps the run-time-shaped path reachable for tests); LPR == 1 would need
+    // the whole net in one thread's registers, so it stays on the generic path
+    if constexpr (LPR >= 16) if (!smem_stage) {   // wide groups = latency-bound runs; at LPR <= 8 the extra registers cost occupancy (measured)
+        if (net_matches<NetNeuro>(kp)) {
+            kp.w_in_smem = 0;
+            return launch_episode<LPR, false, NetNeuro>(h, kp, episode_smem_bytes(LPR, false, kp.plane_bytes, kp.has50, kp.maxw, 0, kp.G));
+        }
+        if (net_matches<NetSimple>(kp)) {
+            kp.w_in_smem = 0;
+            return launch_episode<LPR, false, NetSimple>(h, kp, episode_smem_bytes(LPR, false, kp.plane_bytes, kp.has50, kp.maxw, 0, kp.G));
+        }
+    }
     const size_t smem = episode_smem_bytes(LPR, smem_stage, kp.plane_bytes, kp.has50, kp.maxw, kp.w_in_smem, kp.G);
-    return smem_stage ? launch_episode<LPR, true>(h, kp, smem) : launch_episode<LPR, false>(h, kp, smem);
+    return smem_stage ? launch_episode<LPR, true, GenericNet>(h, kp, smem) : launch_episode<LPR, false, GenericNet>(h, kp, smem);
 }
 
 int choose_lpr(const r2p2_handle h) {
@@ -677,3 +698,16 @@ static int cast_rays_impl(r2p2_handle h, int plain, int32_t n, const double* ox,
 }
 
 }  // extern "C"
+
+#ifdef R2P2_PHASE_TIMING
+// profiling build only (tools/phase_timing.py); not part of the ABI
+extern "C" int r2p2_debug_phase_cycles(unsigned long long* out16, int reset) {
+    cudaDeviceSynchronize();
+    if (out16 && cudaMemcpyFromSymbol(out16, r2p2::g_phase_cycles, 16 * sizeof(unsigned long long)) != cudaSuccess) return -1;
+    if (reset) {
+        unsigned long long z[16] = {0};
+        if (cudaMemcpyToSymbol(r2p2::g_phase_cycles, z, sizeof z) != cudaSuccess) return -1;
+    }
+    return 0;
+}
+#endif

@@ -26,6 +26,17 @@
 
 namespace r2p2 {
 
+#ifdef R2P2_PHASE_TIMING      // profiling build only (tools/phase_timing.py): cycles per tick phase of robot 0
+__device__ unsigned long long g_phase_cycles[16];
+#define PT_DECL long long pt_last = clock64(); unsigned long long pt_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#define PT(n) { const long long pt_now = clock64(); pt_acc[n] += (unsigned long long)(pt_now - pt_last); pt_last = pt_now; }
+#define PT_FLUSH(cond) if (cond) { for (int q = 0; q < 12; ++q) atomicAdd(&g_phase_cycles[q], pt_acc[q]); }
+#else
+#define PT_DECL
+#define PT(n)
+#define PT_FLUSH(cond)
+#endif
+
 constexpr int kBlock = 128;                    // threads per CTA
 constexpr double kRad = 3.14159265358979323846 / 180.0;   // CPython math.radians multiplier
 constexpr double kDeg = 180.0 / 3.14159265358979323846;   // CPython math.degrees multiplier
@@ -243,34 +254,55 @@ struct Team {
     int j, tl;
 };
 
-__device__ __forceinline__ Hit team_march(const StageView& s, const Team& tm, double ox, double oy, double vx, double vy, double limit) {
-    int kA, kB;
-    norm_window(limit, kA, kB);
+// Norm window and per-lane chunk of a ray of a given limit (hoisted out of the tick loop for the sonar rays, whose
+// limit is a per-run constant; integer division by a run-time team size is ~100 cycles on the critical path).
+struct MarchPlan {
+    int kA, kB, chunk;
+};
+__device__ __forceinline__ MarchPlan make_plan(double limit, int tl) {
+    MarchPlan m;
+    norm_window(limit, m.kA, m.kB);
+    m.chunk = (m.kB == 0x7fffffff) ? 0 : (m.kB + tl - 1) / tl;
+    return m;
+}
+
+__device__ __forceinline__ Hit team_march(const StageView& s, const Team& tm, const MarchPlan& mp, double ox, double oy,
+                                          double vx, double vy, double limit) {
+    const int kA = mp.kA, kB = mp.kB;
     if (kB == 0x7fffffff) return march_plain(s, ox, oy, vx, vy, limit);     // non-finite / huge limit: uniform in the team
     Hit r;
     r.x = -1.0; r.y = -1.0; r.k = -1; r.nsamp = 0u; r.fault = false;
     const int tl = tm.tl;
-    const int chunk = (kB + tl - 1) / tl;
+    const int chunk = mp.chunk;
     const int k0 = tm.j * chunk;
     const int k1 = min(kB, k0 + chunk);
     double x = ox, y = oy;
+    // phase 1: carry the position to this lane's first sample.  Lanes that are already there add 0.0 (exact), so the
+    // loop is branch-free and the additions form the only dependent chain.
     const int pre = min((tl - 1) * chunk, kB);
-    for (int i = 0; i < pre; ++i) {
-        if (i < k0) { x = R2P2_ADD(x, vx); y = R2P2_ADD(y, vy); }
+    for (int i = 0; i < pre; i += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const bool on = (i + u) < k0;
+            x = R2P2_ADD(x, on ? vx : 0.0);
+            y = R2P2_ADD(y, on ? vy : 0.0);
+        }
     }
+    // phase 2: test this lane's chunk.  The common case (interior pixel below the norm window) is one bit-plane load
+    // with no branch; anything else goes through the reference's own tests.
     constexpr int kNone = 0x7fffffff;
     int key = kNone;
     double hx = -1.0, hy = -1.0;
+#pragma unroll 2
     for (int c = 0; c < chunk; ++c) {
         const int k = k0 + c;
-        if (k < k1 && key == kNone) {
-            const int ix = dtrunc(x), iy = dtrunc(y);
-            const bool interior = ((unsigned)(ix - 1) < (unsigned)(s.W - 2)) & ((unsigned)(iy - 1) < (unsigned)(s.H - 2));
-            int st;
-            if (interior && k < kA) st = plane_bit(s.wall, s.wpr, ix, iy) ? kSampleHit : kSampleFree;
-            else st = sample_exact(s.wall, s.W, s.H, s.wpr, x, y, ox, oy, limit, k >= kA);
-            if (st != kSampleFree) { key = (k << 2) | st; hx = x; hy = y; }
-        }
+        const int ix = dtrunc(x), iy = dtrunc(y);
+        const bool act = k < k1;
+        const bool fast = act & (k < kA) & ((unsigned)(ix - 1) < (unsigned)(s.W - 2)) & ((unsigned)(iy - 1) < (unsigned)(s.H - 2));
+        const unsigned word = fast ? s.wall[iy * s.wpr + (ix >> 5)] : 0u;
+        int st = ((word >> (ix & 31)) & 1u) ? kSampleHit : kSampleFree;
+        if (act && !fast && key == kNone) st = sample_exact(s.wall, s.W, s.H, s.wpr, x, y, ox, oy, limit, k >= kA);
+        if (st != kSampleFree && key == kNone) { key = (k << 2) | st; hx = x; hy = y; }
         x = R2P2_ADD(x, vx);
         y = R2P2_ADD(y, vy);
     }
@@ -319,6 +351,36 @@ struct Group {
     __device__ __forceinline__ unsigned bcast_u(unsigned v) const { return (LPR == 1) ? v : __shfl_sync(mask, v, 0, LPR); }
 };
 
+// Robot.__crashing_radius (r2p2/robot.py:181-186), only reached when the centre pixel is within ceil(radius)+1 of a
+// blocked pixel.  returns 0 clear, 1 crashing, 2 the reference raises (IndexError before the first wall probe).
+template <int LPR>
+__device__ __forceinline__ int crash_ring(const StageView& sv, const Group<LPR>& g, double x, double y,
+                                       const double* s_crx, const double* s_cry) {
+    int first_wall = 360, first_fault = 360;
+    for (int i = g.sub; i < 360; i += LPR) {
+        bool pf = false;
+        const bool wl = px_probe(sv.wall, sv, dtrunc(R2P2_ADD(x, s_crx[i])), dtrunc(R2P2_ADD(y, s_cry[i])), pf);
+        if (pf) first_fault = min(first_fault, i);
+        if (wl) first_wall = min(first_wall, i);
+    }
+    if (LPR > 1) { first_wall = g.min_i(first_wall); first_fault = g.min_i(first_fault); }
+    if (first_fault < first_wall) return 2;
+    return first_wall < 360 ? 1 : 0;
+}
+
+// (Measured: making sincos / tanh out-of-line calls to shrink the code footprint costs more in call overhead and
+// spills than it saves in instruction-cache misses: 7.3 -> 8.5 ms on config B.  They stay inlined.)
+struct SinCos {
+    double s, c;
+    int ok;
+};
+__device__ __forceinline__ SinCos sincos_call(double a, const double* tab) {
+    SinCos r;
+    r.ok = 1;
+    r2p2_sincos(a, tab, &r.s, &r.c, &r.ok);
+    return r;
+}
+
 __device__ __forceinline__ double activate(int kind, double v) {
     switch (kind) {
         case R2P2_ACT_TANH: return r2p2_tanh(v);
@@ -350,7 +412,92 @@ __host__ __device__ inline size_t episode_smem_bytes(int lpr, bool smem_stage, u
     return n;
 }
 
-template <int LPR, bool SMEM_STAGE>
+// ---------------------------------------------------------------------------------------------
+// fixed-shape MLP: weights in registers, activations exchanged by warp shuffles
+// ---------------------------------------------------------------------------------------------
+// The reference's shipped networks (conf/controller-neuro.json 5-10-7-4-2, controller-neuro-simple.json 5-1-2) get a
+// kernel instance whose layer sizes are compile-time constants: every loop unrolls, lane j keeps the weights of
+// "its" neurons (j, j+LPR, ...) in registers for the whole episode and reads the previous layer with __shfl_sync.
+// The arithmetic is the generic path's (ordered FMA chain per neuron), so results are bit-identical to it.
+template <int N0, int N1, int N2, int N3, int N4>
+struct NetShape {
+    static constexpr int kLayers = (N4 > 0) ? 5 : (N3 > 0) ? 4 : (N2 > 0) ? 3 : 2;       // layer sizes incl. input/output
+    __host__ __device__ static constexpr int sz(int l) { return l == 0 ? N0 : l == 1 ? N1 : l == 2 ? N2 : l == 3 ? N3 : N4; }
+    __host__ __device__ static constexpr int woff(int l) {       // offset of layer l's weights in the flat genome
+        int o = 0;
+        for (int q = 0; q < l; ++q) o += sz(q) * sz(q + 1);
+        return o;
+    }
+    __host__ __device__ static constexpr int sum_in() {           // sum of the input widths of all weight layers
+        int t = 0;
+        for (int q = 0; q + 1 < kLayers; ++q) t += sz(q);
+        return t;
+    }
+    __host__ __device__ static constexpr int maxw() {
+        int m = 0;
+        for (int q = 0; q < kLayers; ++q) m = sz(q) > m ? sz(q) : m;
+        return m;
+    }
+};
+struct GenericNet {
+    static constexpr int kLayers = 0;
+};
+using NetNeuro = NetShape<5, 10, 7, 4, 2>;     // conf/controller-neuro.json on robot-neuro.json (5 rays)
+using NetSimple = NetShape<5, 1, 2, 0, 0>;     // conf/controller-neuro-simple.json
+
+template <int LPR, class NET>
+struct FixedMlp {
+    static constexpr int kMaxW = NET::maxw();
+    static constexpr int kSlots = (kMaxW + LPR - 1) / LPR;           // neurons per lane (layer width above LPR)
+    static constexpr int kWPerLane = kSlots * NET::sum_in();         // upper bound; slots a layer does not need are never touched
+    double w[kWPerLane];
+
+    // lane `sub` loads the weight columns of its neurons: layer l, slot s, input i -> W_l[i][sub + s*LPR]
+    __device__ __forceinline__ void load(const double* __restrict__ gen, int sub) {
+        int q = 0;
+#pragma unroll
+        for (int l = 0; l + 1 < NET::kLayers; ++l) {
+#pragma unroll
+            for (int s = 0; s < kSlots; ++s) {
+                const int j = sub + s * LPR;
+#pragma unroll
+                for (int i = 0; i < NET::sz(l); ++i) {
+                    w[q] = (s * LPR < NET::sz(l + 1) && j < NET::sz(l + 1)) ? gen[NET::woff(l) + i * NET::sz(l + 1) + j] : 0.0;
+                    ++q;
+                }
+            }
+        }
+    }
+    // h[s] on entry: input (s*LPR + sub) of layer 0 (unused slots ignored); returns outputs 0 and 1 in all lanes
+    __device__ __forceinline__ void forward(unsigned mask, int sub, double (&h)[kSlots], int activation, double& out0, double& out1) const {
+        int q = 0;
+#pragma unroll
+        for (int l = 0; l + 1 < NET::kLayers; ++l) {
+            double hn[kSlots];
+#pragma unroll
+            for (int s = 0; s < kSlots; ++s) {
+                double acc = 0.0;
+#pragma unroll
+                for (int i = 0; i < NET::sz(l); ++i) {
+                    const double hi = (LPR == 1) ? h[i] : __shfl_sync(mask, h[i / LPR], i % LPR, LPR);
+                    if (s * LPR < NET::sz(l + 1)) acc = R2P2_FMA(hi, w[q], acc);
+                    ++q;
+                }
+                hn[s] = (l + 2 < NET::kLayers) ? activate(activation, acc) : acc;
+            }
+#pragma unroll
+            for (int s = 0; s < kSlots; ++s) h[s] = hn[s];
+        }
+        out0 = (LPR == 1) ? h[0] : __shfl_sync(mask, h[0], 0, LPR);
+        out1 = (LPR == 1) ? h[1] : __shfl_sync(mask, h[(1 / LPR)], 1 % LPR, LPR);
+    }
+};
+template <int LPR>
+struct FixedMlp<LPR, GenericNet> {
+    static constexpr int kSlots = 1;
+};
+
+template <int LPR, bool SMEM_STAGE, class NET>
 __global__ void __launch_bounds__(kBlock) episode_kernel(const __grid_constant__ KParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NR = kBlock / LPR;                      // robots in flight per CTA
@@ -405,6 +552,11 @@ __global__ void __launch_bounds__(kBlock) episode_kernel(const __grid_constant__
     const bool tracing = p.tr_pose != nullptr;
     const int tl = (LPR == 1 || R >= LPR) ? 1 : LPR / R;  // lanes per sonar ray (team size)
     const int rays_per_round = LPR / tl;
+    const int team_ray = g.sub / tl, team_j = g.sub % tl; // this lane's ray slot and position inside its team
+    Team sonar_team;
+    sonar_team.tl = tl; sonar_team.j = team_j;
+    sonar_team.mask = (tl >= 32) ? 0xffffffffu : (((1u << tl) - 1u) << ((threadIdx.x & 31) - team_j));
+    const MarchPlan sonar_plan = make_plan(p.L, tl);
 
     for (;;) {
         // ---- fetch the next robot --------------------------------------------------------------
@@ -423,13 +575,17 @@ __global__ void __launch_bounds__(kBlock) episode_kernel(const __grid_constant__
         unsigned my_ns_sonar = 0u, ns_coll = 0u;          // my_ns_sonar: this lane's rays only
         // the genome is read every tick for T ticks: keep it next to the SM
         const double* gen = p.genomes + (size_t)rb * (size_t)p.G;
-        if (LPR > 1 && p.w_in_smem) {
+        FixedMlp<LPR, NET> mlp;
+        if constexpr (NET::kLayers > 0) {
+            mlp.load(gen, g.sub);
+        } else if (LPR > 1 && p.w_in_smem) {
             double* dst_g = s_gen + (size_t)slot * p.G;
             for (int i = g.sub; i < p.G; i += LPR) dst_g[i] = __ldg(gen + i);
             g.sync();
             gen = dst_g;
         }
 
+        PT_DECL
         int t = 0;
         unsigned ncollide0 = ncollide;
         for (; t < p.T; ++t) {
@@ -437,30 +593,30 @@ __global__ void __launch_bounds__(kBlock) episode_kernel(const __grid_constant__
             ncollide0 = ncollide;
             const size_t trow = (size_t)t * (size_t)p.P + rb;
 
+            PT(11)
             // ---- sense: Robot.check_sensors (robot.py:287-318) --------------------------------
             bool fault = !(isfinite(x) && isfinite(y));   // round(nan) / round(inf) raise
             const double ox = rint(x), oy = rint(y);      // Python round(): half to even
             if (!fault) {
                 // rays are spread over the group: `tl` lanes per ray (team march) when the group has lanes to spare
                 for (int base = 0; base < R; base += rays_per_round) {
-                    const int i = base + g.sub / tl;
-                    if (g.sub < rays_per_round * tl && i < R) {
+                    const int i = base + team_ray;
+                    if (team_ray < rays_per_round && i < R) {
                         const double ang = R2P2_ADD(p.ray_deg[i], theta);
-                        int ok = 1;
-                        double vs, vc;
-                        r2p2_sincos(R2P2_MUL(ang, kRad), s_tab, &vs, &vc, &ok);
-                        if (!ok) { flags |= R2P2_F_TRIGRANGE; fault = true; break; }
+                        PT(11)
+                        const SinCos sc = sincos_call(R2P2_MUL(ang, kRad), s_tab);
+                        const double vs = sc.s, vc = sc.c;
+                        PT(8)
+                        if (!sc.ok) { flags |= R2P2_F_TRIGRANGE; fault = true; break; }
                         Hit h;
                         if (LPR == 1) {
                             h = march(sv, ox, oy, vc, vs, p.L);
                         } else {
-                            Team tm;
-                            tm.tl = tl; tm.j = g.sub % tl;
-                            tm.mask = (tl == 32) ? 0xffffffffu : (((1u << tl) - 1u) << ((threadIdx.x & 31) - tm.j));
-                            h = team_march(sv, tm, ox, oy, vc, vs, p.L);
+                            h = team_march(sv, sonar_team, sonar_plan, ox, oy, vc, vs, p.L);
                         }
+                        PT(9)
                         if (h.fault) fault = true;
-                        if (LPR == 1 || g.sub % tl == 0) {
+                        if (LPR == 1 || team_j == 0) {
                             my_ns_sonar += h.nsamp;
                             double d = (h.k >= 0) ? r2p2_norm2(R2P2_SUB(h.x, ox), R2P2_SUB(h.y, oy)) : r2p2_from_bits(0x7ff0000000000000ULL);
                             if ((d < p.db_hi && d > p.db_lo) || d > p.L) d = p.L;
@@ -484,6 +640,7 @@ __global__ void __launch_bounds__(kBlock) episode_kernel(const __grid_constant__
             if (g.any(fault)) { flags |= R2P2_F_FAULT; break; }
             g.sync();
 
+            PT(0)
             // ---- control: Neuro_controller.control / Inspyred_controller.control -----------------
             dist = R2P2_ADD(dist, r2p2_norm2(R2P2_SUB(x, odom_x), R2P2_SUB(y, odom_y)));
             odom_x = x; odom_y = y;
@@ -496,8 +653,19 @@ __global__ void __launch_bounds__(kBlock) episode_kernel(const __grid_constant__
                     break;
                 }
             }
+            PT(1)
             double v, w;
-            if (p.ctrl_kind == R2P2_CTRL_NEURO) {
+            if constexpr (NET::kLayers > 0) {
+                double h[FixedMlp<LPR, NET>::kSlots];
+#pragma unroll
+                for (int s = 0; s < FixedMlp<LPR, NET>::kSlots; ++s) {
+                    const int i = g.sub + s * LPR;
+                    h[s] = (i < NET::sz(0)) ? R2P2_DIV(p.vr1, bufA[i * NR]) : 0.0;                     // 25/dst (inf when dst == 0)
+                }
+                mlp.forward(g.mask, g.sub, h, p.activation, v, w);
+                if (v > 180.0) v = R2P2_SUB(v, 360.0);
+                g.sync();                                  // bufA is rewritten by the next tick's sense
+            } else if (p.ctrl_kind == R2P2_CTRL_NEURO) {
                 for (int i = g.sub; i < R; i += LPR) bufA[i * NR] = R2P2_DIV(p.vr1, bufA[i * NR]);   // 25/dst (inf when dst == 0)
                 g.sync();
                 double* hin = bufA;
@@ -512,15 +680,21 @@ __global__ void __launch_bounds__(kBlock) episode_kernel(const __grid_constant__
                             const double* wp = p.genomes + (size_t)(woff + j) * (size_t)p.P + rb;
                             for (int i = 0; i < nin; ++i) acc = R2P2_FMA(hin[i * NR], __ldg(wp + (size_t)i * nout * (size_t)p.P), acc);
                         } else {
+                            // batches of 8: all loads first (independent of the chain), then the ordered FMA chain;
+                            // out-of-range slots read a clamped (valid) address and are predicated off
                             const double* wp = gen + woff + j;
-                            int i = 0;
-                            for (; i + 4 <= nin; i += 4) {          // loads first, then the (ordered) FMA chain
-                                const double w0 = wp[i * nout], w1 = wp[(i + 1) * nout], w2 = wp[(i + 2) * nout], w3 = wp[(i + 3) * nout];
-                                const double h0 = hin[i * NR], h1 = hin[(i + 1) * NR], h2 = hin[(i + 2) * NR], h3 = hin[(i + 3) * NR];
-                                acc = R2P2_FMA(h0, w0, acc); acc = R2P2_FMA(h1, w1, acc);
-                                acc = R2P2_FMA(h2, w2, acc); acc = R2P2_FMA(h3, w3, acc);
+                            for (int i0 = 0; i0 < nin; i0 += 8) {
+                                double wv[8], hv[8];
+#pragma unroll
+                                for (int u = 0; u < 8; ++u) {
+                                    const int i = min(i0 + u, nin - 1);
+                                    wv[u] = wp[i * nout];
+                                    hv[u] = hin[i * NR];
+                                }
+#pragma unroll
+                                for (int u = 0; u < 8; ++u)
+                                    if (i0 + u < nin) acc = R2P2_FMA(hv[u], wv[u], acc);
                             }
-                            for (; i < nin; ++i) acc = R2P2_FMA(hin[i * NR], wp[i * nout], acc);
                         }
                         hout[j * NR] = last ? acc : activate(p.activation, acc);
                     }
@@ -549,6 +723,7 @@ __global__ void __launch_bounds__(kBlock) episode_kernel(const __grid_constant__
                 if (LPR == 1) { v = __ldg(p.genomes + rb); w = __ldg(p.genomes + (size_t)p.P + rb); }
                 else { v = gen[0]; w = gen[1]; }
             }
+            PT(2)
             // Robot.control clamp (robot.py:386-387)
             if (r2p2_fabs(v) > p.max_speed) v = R2P2_MUL(R2P2_DIV(v, r2p2_fabs(v)), p.max_speed);
             speed = v; omega = w;
@@ -556,29 +731,32 @@ __global__ void __launch_bounds__(kBlock) episode_kernel(const __grid_constant__
             // ---- integrate: __update_angle, __update_position (robot.py:188-267) ------------------
             theta = R2P2_ADD(theta, R2P2_MUL(omega, delta));
             {
-                int ok = 1;
-                double hs, hc;
-                r2p2_sincos(R2P2_MUL(theta, kRad), s_tab, &hs, &hc, &ok);
-                if (!ok) { flags |= R2P2_F_TRIGRANGE | R2P2_F_FAULT; break; }
+                const SinCos hsc = sincos_call(R2P2_MUL(theta, kRad), s_tab);
+                const double hs = hsc.s, hc = hsc.c;
+                if (!hsc.ok) { flags |= R2P2_F_TRIGRANGE | R2P2_F_FAULT; break; }
                 const double cx = R2P2_ADD(x, R2P2_MUL(R2P2_MUL(hc, speed), delta));
                 const double cy = R2P2_ADD(y, R2P2_MUL(R2P2_MUL(hs, speed), delta));
                 const double dx = R2P2_SUB(cx, x), dy = R2P2_SUB(cy, y);
+                PT(3)
                 double angle = R2P2_MUL(r2p2_atan2(dy, dx), kDeg);
                 // Python float % 360 for |angle| <= 180: fmod is the identity, then the sign fix-up
                 if (angle != 0.0) { if (angle < 0.0) angle = R2P2_ADD(angle, 360.0); } else angle = 0.0;
-                double cs_, cc_;
-                r2p2_sincos(R2P2_MUL(angle, kRad), s_tab, &cs_, &cc_, &ok);
-                if (!ok) { flags |= R2P2_F_TRIGRANGE | R2P2_F_FAULT; break; }   // NaN displacement: the reference faults two statements later
+                const SinCos csc = sincos_call(R2P2_MUL(angle, kRad), s_tab);
+                const double cs_ = csc.s, cc_ = csc.c;
+                if (!csc.ok) { flags |= R2P2_F_TRIGRANGE | R2P2_F_FAULT; break; }   // NaN displacement: the reference faults two statements later
+                PT(4)
                 Hit ms;
                 if (LPR == 1) {
                     ms = march(sv, x, y, cc_, cs_, R2P2_ADD(r2p2_norm2(dx, dy), p.radius));
                 } else {                                   // the whole group is one team on the collision ray
                     Team tm;
                     tm.tl = LPR; tm.j = g.sub; tm.mask = g.mask;
-                    ms = team_march(sv, tm, x, y, cc_, cs_, R2P2_ADD(r2p2_norm2(dx, dy), p.radius));
+                    const double climit = R2P2_ADD(r2p2_norm2(dx, dy), p.radius);
+                    ms = team_march(sv, tm, make_plan(climit, LPR), x, y, cc_, cs_, climit);
                 }
                 ns_coll += ms.nsamp;
                 if (ms.fault) { flags |= R2P2_F_FAULT; break; }
+                PT(5)
                 x = cx; y = cy;
                 if (ms.k >= 0) {
                     if (!(isfinite(cx) && isfinite(cy))) { flags |= R2P2_F_FAULT; break; }   // int(inf) raises
@@ -612,6 +790,7 @@ __global__ void __launch_bounds__(kBlock) episode_kernel(const __grid_constant__
                     ncollide++; tmr = 0.0;
                     y = rad;
                 }
+                PT(6)
                 // env[int(x), int(y)] is 50 or __crashing_radius (robot.py:249, 181-186)
                 if (!(isfinite(x) && isfinite(y))) { flags |= R2P2_F_FAULT; break; }
                 bool f = false;
@@ -630,20 +809,14 @@ __global__ void __launch_bounds__(kBlock) episode_kernel(const __grid_constant__
                 if (!crash && !ring_clear) {
                     // 360 probes spread over the group; the reference stops at the first wall, so an
                     // IndexError only counts if it comes before the first wall probe
-                    int first_wall = 360, first_fault = 360;
-                    for (int i = g.sub; i < 360; i += LPR) {
-                        bool pf = false;
-                        const bool wl = px_probe(sv.wall, sv, dtrunc(R2P2_ADD(x, s_crx[i])), dtrunc(R2P2_ADD(y, s_cry[i])), pf);
-                        if (pf) first_fault = min(first_fault, i);
-                        if (wl) first_wall = min(first_wall, i);
-                    }
-                    if (LPR > 1) { first_wall = g.min_i(first_wall); first_fault = g.min_i(first_fault); }
-                    if (first_fault < first_wall) { flags |= R2P2_F_FAULT; break; }
-                    crash = first_wall < 360;
+                    const int cr = crash_ring<LPR>(sv, g, x, y, s_crx, s_cry);
+                    if (cr == 2) { flags |= R2P2_F_FAULT; break; }
+                    crash = cr == 1;
                 }
                 if (crash) { x = last_x; y = last_y; ncollide++; tmr = 0.0; }
                 else { last_x = x; last_y = y; }
             }
+            PT(7)
             ticks++;
             if (ncollide != ncollide0) flags |= R2P2_F_COLLIDED;
             if (tracing && g.sub == 0) {
@@ -652,6 +825,7 @@ __global__ void __launch_bounds__(kBlock) episode_kernel(const __grid_constant__
                 p.tr_ncoll[trow] = ncollide - ncollide0;
             }
         }
+        PT_FLUSH(rb == 0 && g.sub == 0)
         if (ncollide != p.ncollide[rb]) flags |= R2P2_F_COLLIDED;
         if (tracing && g.sub == 0) {     // rows of ticks that did not complete: frozen pose (as the oracle records them)
             for (int t2 = t; t2 < p.T; ++t2) {

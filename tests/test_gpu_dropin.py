@@ -1,0 +1,78 @@
+"""The r2p2-facing Python surface on a real B200: Robot.update, scenario loading, evolution callback."""
+import os
+
+import numpy as np
+import pytest
+
+import common
+from test_host_logic import write_conf
+
+pytestmark = pytest.mark.gpu
+
+
+def test_robot_update_reproduces_reference_episode():
+    """`for t: robot.update(env, 0.1)` with the linear controller == the reference's KAT3 run, tick by tick, bit for bit
+    (pose, sonar distances handed to the controller, collide() calls, fitness)."""
+    from r2p2_b200.controllers.inspyred import Inspyred_controller
+    from r2p2_b200.robot import Robot
+    e, specs = common.episode_specs()
+    sp = next(s for s in specs if s["name"] == "kat3_linear")
+    rob = common.ROBOTS[sp["robot"]]
+    env = common.load_stage(sp["stage"])
+    ctrl = Inspyred_controller({"controllers": [{"class": "inspyred.Inspyred_controller", "weights": list(e["kat3_linear/genome"]), "time": 20, "evolve": False}]})
+    r = Robot(identifier=0, x=rob["x"], y=rob["y"], orientation=rob["orientation"], vision_range=tuple(rob["sonar_range"]), sensors=rob["sonars"],
+              radius=rob["radius"], max_speed=rob["max_speed"], controller=ctrl)
+    gp, gd, gc = e["kat3_linear/pose"], e["kat3_linear/dst"], e["kat3_linear/ncoll"]
+    for t in range(120):
+        r.update(env, 0.1, True)
+        assert (r.x, r.y, r.orientation, r.speed, r.angular_velocity) == tuple(gp[t]), t
+        assert ctrl.dst == list(gd[t]), t
+        assert r.collisions == gc[t]
+    assert ctrl.fitness() == e["kat3_linear/fitness"][119]
+
+
+def test_robot_facade_neuro_and_check_sensors():
+    from r2p2_b200.controllers.neurocontroller import Neuro_controller
+    from r2p2_b200.robot import Robot
+    e, specs = common.episode_specs()
+    rob = common.ROBOTS["robot-neuro.json"]
+    env = common.load_stage("track_2.png")
+    ctrl = Neuro_controller({"controllers": [{"class": "neurocontroller.Neuro_controller", "weights": list(e["kat2_neuro/genome"]),
+                                              "hidden_layer": [10, 7, 4], "activation": "tanh", "time": 20, "evolve": False}]})
+    r = Robot(identifier=0, x=rob["x"], y=rob["y"], orientation=0, vision_range=tuple(rob["sonar_range"]), sensors=rob["sonars"],
+              radius=rob["radius"], max_speed=rob["max_speed"], controller=ctrl)
+    col, dst, ang = r.check_sensors(env)
+    assert dst == list(e["kat2_neuro/dst"][0]) and ang == [0.0, 45.0, 70.0, 290.0, 315.0]
+    assert (r.x, r.y) == (rob["x"], rob["y"])
+    gp = e["kat2_neuro/pose"]
+    for t in range(100):
+        r.update(env, 0.1)
+        assert abs(r.x - gp[t, 0]) < 1e-9 and abs(r.y - gp[t, 1]) < 1e-9 and abs(r.orientation - gp[t, 2]) < 1e-9
+        assert np.array_equal(np.rint(ctrl.dst), np.rint(e["kat2_neuro/dst"][t]))
+    r.has_noise = True
+    with pytest.raises(NotImplementedError):
+        r.update(env, 0.1)
+
+
+def test_scenario_files_and_evolution_callback(tmp_path, oracle_port):
+    """Unchanged scenario / robot / controller JSON files -> Simulation and the batched evolution callback; the callback's
+    fitness list equals the port oracle's for the same genomes (evolve semantics, 30 Hz time units of SURVEY H17)."""
+    from r2p2_b200 import evolution
+    from r2p2_b200.simulation import load_simulation
+    conf = write_conf(str(tmp_path))
+    sim = load_simulation(os.path.join(conf, "scenario-neuro-simple.json"))
+    assert len(sim.robots) == 1 and sim.env.shape == (460, 321)
+    sim.robots[0].controller.set_network_params(list(np.random.RandomState(5).uniform(-1, 1, 7)))
+    sim.run(20, delta=0.1)
+    assert sim.robots[0].x != 230
+
+    ev = evolution.configure(os.path.join(conf, "scenario-neuro.json"), ticks=300)
+    genomes = np.random.RandomState(3).uniform(-1, 1, (64, 156))
+    fit = evolution.evaluator(genomes.tolist(), {})
+    rob, kw = common.ROBOTS["robot-neuro.json"], common.oracle_robot_kwargs("robot-neuro.json")
+    ref = oracle_port.run(common.load_stage("track_2.png"), ctrl="neuro", genomes=genomes, x0=rob["x"], y0=rob["y"], theta0=0.0, T=300,
+                          delta=1.0 / 30.0, delta_ctrl=1000.0 / 30.0, time_budget=20000.0, evolve=True, layers=[5, 10, 7, 4, 2], **kw)
+    assert fit == ref["fitness"].tolist()
+    assert evolution.evaluate_ann(genomes[7].tolist(), {}) == fit[7]
+    assert evolution.evaluator([[0.0] * 3], {}) == [0]            # evolution.py:49-52: a failing candidate scores 0
+    ev.close()

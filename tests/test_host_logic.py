@@ -1,0 +1,90 @@
+"""Host-side logic that needs no GPU: config merging, sonar expansion, plugin loading, stage loading."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import common
+from r2p2_b200 import expand_sonars
+from r2p2_b200.config_manager import ConfigManager
+from r2p2_b200.controllers.controllers import get_controllers, load_controller
+
+
+def write_conf(tmp, stage="track_2"):
+    """A scenario tree with the shape of the reference's conf/ + res/ (numbers of the shipped JSON files)."""
+    from PIL import Image
+    os.makedirs(os.path.join(tmp, "conf")); os.makedirs(os.path.join(tmp, "res"))
+    env = common.load_stage(stage + ".png").astype(np.uint8)                # env[x, y]
+    Image.fromarray(np.ascontiguousarray(env.T), mode="L").save(os.path.join(tmp, "res", stage + ".png"))
+    rob = dict(common.ROBOTS["robot-neuro.json"], id=0)
+    json.dump(rob, open(os.path.join(tmp, "conf", "robot-neuro.json"), "w"))
+    json.dump({"class": "neurocontroller.Neuro_controller", "weights": [0.0, 0.0], "hidden_layer": [10, 7, 4], "activation": "tanh",
+               "time": 20, "evolve": True}, open(os.path.join(tmp, "conf", "controller-neuro.json"), "w"))
+    json.dump({"controller_type": "NEURO", "weights": [0] * 7, "hidden_layer": [1], "activation": "tanh", "time": 20, "evolve": False},
+              open(os.path.join(tmp, "conf", "controller-neuro-simple.json"), "w"))
+    json.dump({"class": "inspyred.Inspyred_controller", "weights": [0] * 10, "time": 20, "evolve": True},
+              open(os.path.join(tmp, "conf", "controller-inspyred.json"), "w"))
+    for name, ctrl in (("scenario-neuro.json", "controller-neuro.json"), ("scenario-neuro-simple.json", "controller-neuro-simple.json"),
+                       ("scenario-inspyred.json", "controller-inspyred.json")):
+        json.dump({"stage": "../res/%s.png" % stage, "robot": "../conf/robot-neuro.json", "controller": "../conf/" + ctrl, "gui": False},
+                  open(os.path.join(tmp, "conf", name), "w"))
+    return os.path.join(tmp, "conf")
+
+
+def test_expand_sonars_matches_reference_quirk():
+    """utils.py:465-466: range(0, 360, floor(365/n)) -- 8 -> 8 rays, 16 -> 17, 32 -> 33."""
+    assert expand_sonars([0, 45, 70, 290, 315]) == [0.0, 45.0, 70.0, 290.0, 315.0]
+    assert len(expand_sonars(8)) == 8 and expand_sonars(8)[:3] == [0.0, 45.0, 90.0]
+    assert len(expand_sonars(16)) == 17 and len(expand_sonars(32)) == 33
+
+
+def test_config_manager_merge_rules(tmp_path):
+    conf = write_conf(str(tmp_path))
+    cm = ConfigManager(os.path.join(conf, "scenario-neuro.json"), params={"evolve": False, "extra": 1})
+    cfg = cm.get_config()
+    assert cfg["extra"] == 1 and cfg["gui"] is False
+    assert cfg["controllers"][0]["class"] == "neurocontroller.Neuro_controller"
+    assert cfg["controllers"][0]["evolve"] is False                     # scenario / CLI keys override controller keys
+    assert ConfigManager(os.path.join(conf, "scenario-neuro.json")).get_config()["controllers"][0]["evolve"] is True
+    cm2 = ConfigManager(os.path.join(conf, "scenario-neuro.json"), controller_config=os.path.join(conf, "controller-inspyred.json"))
+    assert cm2.get_config()["controllers"][0]["class"] == "inspyred.Inspyred_controller"
+
+
+def test_plugin_loading_by_class_string(tmp_path):
+    assert load_controller("neurocontroller.Neuro_controller").__name__ == "Neuro_controller"
+    assert load_controller("inspyred.Inspyred_controller").device_kind == "linear"
+    conf = write_conf(str(tmp_path))
+    c = get_controllers(ConfigManager(os.path.join(conf, "scenario-neuro.json")).get_config())[0]
+    assert c.hidden_layer == [10, 7, 4] and c.activation == "tanh" and c.time == 20000 and c.evolve is True
+    assert c.genome_length(5) == 156
+    s = get_controllers(ConfigManager(os.path.join(conf, "scenario-neuro-simple.json")).get_config())[0]   # no "class" key
+    assert s.hidden_layer == [1] and s.genome_length(5) == 7
+    lin = get_controllers(ConfigManager(os.path.join(conf, "scenario-inspyred.json")).get_config())[0]
+    lin.set_network_params(list(range(12)))
+    assert lin.linCoefs == [0, 1, 2, 3, 4] and lin.angCoefs == [5, 6, 7, 8, 9] and (lin.vlinmax, lin.vangmax) == (10, 11)
+
+
+def test_stage_loading_is_the_reference_transpose(tmp_path):
+    """PNG -> load_image -> flipud(rot90()) equals the env the reference builds (fixture recorded from it)."""
+    from r2p2_b200.simulation import load_image, stage_env
+    conf = write_conf(str(tmp_path))
+    env = stage_env(load_image(os.path.join(conf, "..", "res", "track_2.png")))
+    ref = common.load_stage("track_2.png")
+    assert env.shape == ref.shape == (460, 321) and np.array_equal(env, ref)
+
+
+def test_controller_base_contract():
+    from r2p2_b200.controller import Controller, upd_sensor_angles
+    import math
+    c = Controller("X")
+    c.set_ang([1, 2]); c.set_dst([3.0, math.inf])
+    assert c.control([3.0, math.inf]) == (0, 0)
+    assert c.cur_detected_edges_distances == [3.0, 10000]                 # controller.py:121-125
+
+    class K(Controller):
+        @upd_sensor_angles
+        def control(self, dst):
+            return 1, 2
+    k = K(); k.set_ang([0])
+    assert k.control([5.0]) == (1, 2) and k.actual_sensor_angles == [0]
