@@ -194,14 +194,14 @@ def run_ours(args, w):
     g_dev = torch.from_numpy(genomes_np).to(dev)
     g_pin = torch.from_numpy(genomes_np).pin_memory()
     f_pin = torch.empty(P, dtype=torch.float64).pin_memory()
-    fit_all = torch.empty(world * P, dtype=torch.float64, device=dev) if world > 1 else None
+    from r2p2_b200.distributed import gather_fitness
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
 
     def one_step_resident():
         ev.launch_resident()
         if world > 1:
             local_fit = _as_tensor(sim.fitness_device_ptr(), P, dev)
-            dist.all_gather_into_tensor(fit_all, local_fit)
+            gather_fitness(local_fit, P * world)   # per-generation exchange: every rank gets all P*world fitness values
 
     sim.set_genomes_device(g_dev.data_ptr(), P, G)
     for _ in range(max(args.warmup, 3)):
@@ -245,7 +245,7 @@ def run_ours(args, w):
         ev.evaluate_ptr(g_pin.data_ptr(), P, G, f_pin.data_ptr())
         if world > 1:
             local_fit = _as_tensor(sim.fitness_device_ptr(), P, dev)
-            dist.all_gather_into_tensor(fit_all, local_fit)
+            gather_fitness(local_fit, P * world)   # per-generation exchange: every rank gets all P*world fitness values
             torch.cuda.synchronize()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
