@@ -250,19 +250,35 @@ __device__ __forceinline__ Hit march(const StageView& s, double ox, double oy, d
 // sonar ray costs ~ (tl-1)/tl * 31 chained additions + 31/tl pixel tests per lane instead of 31 of each, with no
 // data-dependent branch inside the loops.  tl == 1 degenerates to the plain lock-step loop.
 struct Team {
-    unsigned mask;
+    unsigned mask;    // lanes of this team
+    unsigned sync;    // member mask for the collectives: the same value in every lane that calls team_march together
     int j, tl;
 };
 
 // Norm window and per-lane chunk of a ray of a given limit (hoisted out of the tick loop for the sonar rays, whose
 // limit is a per-run constant; integer division by a run-time team size is ~100 cycles on the critical path).
 struct MarchPlan {
-    int kA, kB, chunk;
+    int kA, kB;       // norm window
+    int nfast;        // lanes that test the samples below the window; with a knife-edge sample and tl > 1 the last
+                      // lane of the team is reserved for it
+    int chunk;        // samples below the window per such lane
+    double qstar;     // sqrt(q) < limit  <=>  q < qstar  (sqrt is monotone): the knife-edge test without the sqrt
 };
 __device__ __forceinline__ MarchPlan make_plan(double limit, int tl) {
     MarchPlan m;
     norm_window(limit, m.kA, m.kB);
-    m.chunk = (m.kB == 0x7fffffff) ? 0 : (m.kB + tl - 1) / tl;
+    m.nfast = tl; m.chunk = 0; m.qstar = 0.0;
+    if (m.kB == 0x7fffffff) return m;
+    if (m.kB > m.kA) {
+        // smallest double whose square root reaches the limit
+        double q = R2P2_MUL(limit, limit);
+        for (int it = 0; it < 8 && q > 0.0 && R2P2_SQRT(r2p2_from_bits(r2p2_bits(q) - 1)) >= limit; ++it) q = r2p2_from_bits(r2p2_bits(q) - 1);
+        for (int it = 0; it < 8 && R2P2_SQRT(q) < limit; ++it) q = r2p2_from_bits(r2p2_bits(q) + 1);
+        m.qstar = q;
+        if (tl > 1) m.nfast = tl - 1;
+    }
+    // two divisions by (tl) and (tl - 1) rather than one by nfast: tl is a compile-time constant at the hot call site
+    m.chunk = (m.nfast == tl) ? (m.kA + tl - 1) / tl : (m.kA + tl - 2) / (tl - 1);
     return m;
 }
 
@@ -273,13 +289,14 @@ __device__ __forceinline__ Hit team_march(const StageView& s, const Team& tm, co
     Hit r;
     r.x = -1.0; r.y = -1.0; r.k = -1; r.nsamp = 0u; r.fault = false;
     const int tl = tm.tl;
-    const int chunk = mp.chunk;
-    const int k0 = tm.j * chunk;
-    const int k1 = min(kB, k0 + chunk);
+    // this lane's samples below the norm window: [k0, k1) (empty for the lane reserved for the window)
+    const bool window_lane = (tl == 1) | ((mp.nfast < tl) & (tm.j == tl - 1));
+    const int k0 = (tl == 1) ? 0 : ((tm.j < mp.nfast) ? min(kA, tm.j * mp.chunk) : kA);
+    const int k1 = (tl == 1) ? kA : ((tm.j < mp.nfast) ? min(kA, k0 + mp.chunk) : kA);
     double x = ox, y = oy;
     // phase 1: carry the position to this lane's first sample.  Lanes that are already there add 0.0 (exact), so the
     // loop is branch-free and the additions form the only dependent chain.
-    const int pre = min((tl - 1) * chunk, kB);
+    const int pre = (tl == 1) ? 0 : ((mp.nfast < tl) ? kA : min((tl - 1) * mp.chunk, kA));
     for (int i = 0; i < pre; i += 4) {
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -288,38 +305,74 @@ __device__ __forceinline__ Hit team_march(const StageView& s, const Team& tm, co
             y = R2P2_ADD(y, on ? vy : 0.0);
         }
     }
-    // phase 2: test this lane's chunk.  The common case (interior pixel below the norm window) is one bit-plane load
-    // with no branch; anything else goes through the reference's own tests.
+    // phase 2: test this lane's samples, four at a time and without a branch: positions first (the only dependent
+    // chain), then four independent truncation / address / bit-plane-load / test pipelines.  A sample that is not on
+    // an interior pixel (map border, off the map, NaN) makes the whole team fall back to the plain loop below.
     constexpr int kNone = 0x7fffffff;
     int key = kNone;
     double hx = -1.0, hy = -1.0;
-#pragma unroll 2
-    for (int c = 0; c < chunk; ++c) {
-        const int k = k0 + c;
+    bool slow = false;
+    const int n2 = (tl == 1) ? kA : mp.chunk;
+    for (int c0 = 0; c0 < n2; c0 += 4) {
+        double xs[4], ys[4];
+        unsigned word[4];
+        int ixs[4];
+        bool act[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {           // advance only through this lane's own samples: it must end on sample k1
+            act[u] = (k0 + c0 + u) < k1;
+            xs[u] = x; ys[u] = y;
+            x = R2P2_ADD(x, act[u] ? vx : 0.0);
+            y = R2P2_ADD(y, act[u] ? vy : 0.0);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int ix = dtrunc(xs[u]), iy = dtrunc(ys[u]);
+            const bool interior = ((unsigned)(ix - 1) < (unsigned)(s.W - 2)) & ((unsigned)(iy - 1) < (unsigned)(s.H - 2));
+            slow |= act[u] & !interior;
+            ixs[u] = ix;
+            word[u] = s.wall[interior ? (iy * s.wpr + (ix >> 5)) : 0];       // always a valid address
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const bool hit = act[u] & (((word[u] >> (ixs[u] & 31)) & 1u) != 0u);
+            if (hit && key == kNone) { key = ((k0 + c0 + u) << 2) | kSampleHit; hx = xs[u]; hy = ys[u]; }
+        }
+    }
+    // the norm window [kA, kB) (at most one sample): the reference's own limit test, sqrt-free through qstar
+    for (int k = kA; k < kB; ++k) {
         const int ix = dtrunc(x), iy = dtrunc(y);
-        const bool act = k < k1;
-        const bool fast = act & (k < kA) & ((unsigned)(ix - 1) < (unsigned)(s.W - 2)) & ((unsigned)(iy - 1) < (unsigned)(s.H - 2));
-        const unsigned word = fast ? s.wall[iy * s.wpr + (ix >> 5)] : 0u;
-        int st = ((word >> (ix & 31)) & 1u) ? kSampleHit : kSampleFree;
-        if (act && !fast && key == kNone) st = sample_exact(s.wall, s.W, s.H, s.wpr, x, y, ox, oy, limit, k >= kA);
-        if (st != kSampleFree && key == kNone) { key = (k << 2) | st; hx = x; hy = y; }
+        const bool interior = ((unsigned)(ix - 1) < (unsigned)(s.W - 2)) & ((unsigned)(iy - 1) < (unsigned)(s.H - 2));
+        const unsigned w = s.wall[interior ? (iy * s.wpr + (ix >> 5)) : 0];
+        const bool in_range = r2p2_norm2sq(R2P2_SUB(x, ox), R2P2_SUB(y, oy)) < mp.qstar;
+        const bool live = window_lane & (key == kNone);
+        slow |= live & !interior;
+        const int st = !in_range ? kSampleExit : (((w >> (ix & 31)) & 1u) ? kSampleHit : kSampleFree);
+        if (live && st != kSampleFree) { key = (k << 2) | st; hx = x; hy = y; }
         x = R2P2_ADD(x, vx);
         y = R2P2_ADD(y, vy);
     }
-    const int best = (tl == 1) ? key : (int)__reduce_min_sync(tm.mask, (unsigned)key);
+    // Earliest event of the ray = the event of the lowest lane of the team that has one (lanes own ascending sample
+    // ranges).  All collectives are issued with tm.sync, ONE mask value shared by every lane that executes this code
+    // together: a warp-level instruction whose lanes carry different member masks is executed once per distinct
+    // mask (the compiler emits a MATCH.ANY loop), which serialises the teams.
+    int best = key;
+    if (tl > 1) {
+        const unsigned slow_b = __ballot_sync(tm.sync, slow);
+        const unsigned ev_b = __ballot_sync(tm.sync, key != kNone) & tm.mask;
+        const int src = ev_b ? (__ffs(ev_b) - 1) : (int)(threadIdx.x & 31);
+        best = __shfl_sync(tm.sync, key, src);
+        hx = __shfl_sync(tm.sync, hx, src);
+        hy = __shfl_sync(tm.sync, hy, src);
+        slow = (slow_b & tm.mask) != 0u;
+    }
+    if (slow) return march_plain(s, ox, oy, vx, vy, limit);
     if (best == kNone) { r.nsamp = (unsigned)kB; return r; }
     const int k = best >> 2, st = best & 3;
     if (st == kSampleHit) {
-        if (tl > 1) {
-            const int src = __ffs(__ballot_sync(tm.mask, key == best)) - 1;
-            hx = __shfl_sync(tm.mask, hx, src);
-            hy = __shfl_sync(tm.mask, hy, src);
-        }
         r.x = hx; r.y = hy; r.k = k; r.nsamp = (unsigned)(k + 1);
-    } else if (st == kSampleExit) {
-        r.nsamp = (unsigned)k;
     } else {
-        r.fault = true; r.nsamp = (unsigned)k;
+        r.nsamp = (unsigned)k;          // the while-condition failed at sample k
     }
     return r;
 }
@@ -554,7 +607,7 @@ __global__ void __launch_bounds__(kBlock) episode_kernel(const __grid_constant__
     const int rays_per_round = LPR / tl;
     const int team_ray = g.sub / tl, team_j = g.sub % tl; // this lane's ray slot and position inside its team
     Team sonar_team;
-    sonar_team.tl = tl; sonar_team.j = team_j;
+    sonar_team.tl = tl; sonar_team.j = team_j; sonar_team.sync = g.mask;
     sonar_team.mask = (tl >= 32) ? 0xffffffffu : (((1u << tl) - 1u) << ((threadIdx.x & 31) - team_j));
     const MarchPlan sonar_plan = make_plan(p.L, tl);
 
@@ -597,26 +650,29 @@ __global__ void __launch_bounds__(kBlock) episode_kernel(const __grid_constant__
             // ---- sense: Robot.check_sensors (robot.py:287-318) --------------------------------
             bool fault = !(isfinite(x) && isfinite(y));   // round(nan) / round(inf) raise
             const double ox = rint(x), oy = rint(y);      // Python round(): half to even
-            if (!fault) {
-                // rays are spread over the group: `tl` lanes per ray (team march) when the group has lanes to spare
+            if (!fault) {                                 // (uniform in the group)
+                // Rays are spread over the group: `tl` lanes per ray (team march) when the group has lanes to spare.
+                // Every lane of the group walks through the same code (lanes without a ray march a dummy one), so that
+                // the warp-level collectives inside team_march see one member mask.
                 for (int base = 0; base < R; base += rays_per_round) {
                     const int i = base + team_ray;
-                    if (team_ray < rays_per_round && i < R) {
-                        const double ang = R2P2_ADD(p.ray_deg[i], theta);
+                    const bool have_ray = (team_ray < rays_per_round) & (i < R);
+                    {
+                        const double ang = R2P2_ADD(p.ray_deg[have_ray ? i : 0], theta);
                         PT(11)
                         const SinCos sc = sincos_call(R2P2_MUL(ang, kRad), s_tab);
                         const double vs = sc.s, vc = sc.c;
                         PT(8)
-                        if (!sc.ok) { flags |= R2P2_F_TRIGRANGE; fault = true; break; }
+                        if (!sc.ok && have_ray) { flags |= R2P2_F_TRIGRANGE; fault = true; }
                         Hit h;
                         if (LPR == 1) {
-                            h = march(sv, ox, oy, vc, vs, p.L);
+                            h = sc.ok ? march(sv, ox, oy, vc, vs, p.L) : Hit{-1.0, -1.0, -1, 0u, true};
                         } else {
                             h = team_march(sv, sonar_team, sonar_plan, ox, oy, vc, vs, p.L);
                         }
                         PT(9)
-                        if (h.fault) fault = true;
-                        if (LPR == 1 || team_j == 0) {
+                        if (h.fault && have_ray) fault = true;
+                        if (have_ray && (LPR == 1 || team_j == 0)) {
                             my_ns_sonar += h.nsamp;
                             double d = (h.k >= 0) ? r2p2_norm2(R2P2_SUB(h.x, ox), R2P2_SUB(h.y, oy)) : r2p2_from_bits(0x7ff0000000000000ULL);
                             if ((d < p.db_hi && d > p.db_lo) || d > p.L) d = p.L;
@@ -629,7 +685,6 @@ __global__ void __launch_bounds__(kBlock) episode_kernel(const __grid_constant__
                                 p.tr_nsamp[trow * R + i] = h.nsamp;
                             }
                         }
-                        if (h.fault) break;
                     }
                 }
             }
@@ -750,7 +805,7 @@ __global__ void __launch_bounds__(kBlock) episode_kernel(const __grid_constant__
                     ms = march(sv, x, y, cc_, cs_, R2P2_ADD(r2p2_norm2(dx, dy), p.radius));
                 } else {                                   // the whole group is one team on the collision ray
                     Team tm;
-                    tm.tl = LPR; tm.j = g.sub; tm.mask = g.mask;
+                    tm.tl = LPR; tm.j = g.sub; tm.mask = g.mask; tm.sync = g.mask;
                     const double climit = R2P2_ADD(r2p2_norm2(dx, dy), p.radius);
                     ms = team_march(sv, tm, make_plan(climit, LPR), x, y, cc_, cs_, climit);
                 }
