@@ -214,7 +214,10 @@ int launch_episode_s(r2p2_handle h, KParams& kp, bool smem_stage) {
     // the reference's shipped network shapes have fixed-shape instances (weights in registers; chosen unless the shared-memory
     // stage copy is requested, which keeps the run-time-shaped path reachable for tests); LPR == 1 would need
     // the whole net in one thread's registers, so it stays on the generic path
-    if constexpr (LPR >= 16) if (!smem_stage) {   // wide groups = latency-bound runs; at LPR <= 8 the extra registers cost occupancy (measured)
+    // LPR >= 16: weights in registers (latency-bound runs).  Below that the extra registers cost occupancy (measured:
+    // LPR 8 with register weights 25 ms vs 17 ms generic on 8192 robots; LPR 1 fully unrolled = 255 registers + spills,
+    // 148 ms vs 81 ms on 65536 robots), so those mappings stay on the run-time-shaped path.
+    if constexpr (LPR >= 16) if (!smem_stage) {
         if (net_matches<NetNeuro>(kp)) {
             kp.w_in_smem = 0;
             return launch_episode<LPR, false, NetNeuro>(h, kp, episode_smem_bytes(LPR, false, kp.plane_bytes, kp.has50, kp.maxw, 0, kp.G));

@@ -502,7 +502,7 @@ template <int LPR, class NET>
 struct FixedMlp {
     static constexpr int kMaxW = NET::maxw();
     static constexpr int kSlots = (kMaxW + LPR - 1) / LPR;           // neurons per lane (layer width above LPR)
-    static constexpr int kWPerLane = kSlots * NET::sum_in();         // upper bound; slots a layer does not need are never touched
+    static constexpr int kWPerLane = (LPR == 1) ? 1 : kSlots * NET::sum_in();   // upper bound; slots a layer does not need are never touched
     double w[kWPerLane];
 
     // lane `sub` loads the weight columns of its neurons: layer l, slot s, input i -> W_l[i][sub + s*LPR]
@@ -536,13 +536,35 @@ struct FixedMlp {
                     if (s * LPR < NET::sz(l + 1)) acc = R2P2_FMA(hi, w[q], acc);
                     ++q;
                 }
-                hn[s] = (l + 2 < NET::kLayers) ? activate(activation, acc) : acc;
+                hn[s] = (s * LPR < NET::sz(l + 1)) ? ((l + 2 < NET::kLayers) ? activate(activation, acc) : acc) : 0.0;
             }
 #pragma unroll
             for (int s = 0; s < kSlots; ++s) h[s] = hn[s];
         }
         out0 = (LPR == 1) ? h[0] : __shfl_sync(mask, h[0], 0, LPR);
         out1 = (LPR == 1) ? h[1] : __shfl_sync(mask, h[(1 / LPR)], 1 % LPR, LPR);
+    }
+    // One lane per robot: the whole net in this thread.  Activations stay in registers, every loop is unrolled, and
+    // the weights stream from the transposed genome array (wt = genomes_t + robot, element q at wt[q * P]: one
+    // coalesced line per warp and weight).  Same ordered FMA chains as everywhere else.
+    __device__ __forceinline__ void forward_global(const double* __restrict__ wt, size_t P, double (&h)[kSlots], int activation,
+                                                   double& out0, double& out1) const {
+#pragma unroll
+        for (int l = 0; l + 1 < NET::kLayers; ++l) {
+            double hn[kSlots];
+#pragma unroll
+            for (int j = 0; j < NET::sz(l + 1); ++j) {
+                double acc = 0.0;
+#pragma unroll
+                for (int i = 0; i < NET::sz(l); ++i)
+                    acc = R2P2_FMA(h[i], __ldg(wt + (size_t)(NET::woff(l) + i * NET::sz(l + 1) + j) * P), acc);
+                hn[j] = (l + 2 < NET::kLayers) ? activate(activation, acc) : acc;
+            }
+#pragma unroll
+            for (int j = 0; j < NET::sz(l + 1); ++j) h[j] = hn[j];
+        }
+        out0 = h[0];
+        out1 = h[1];
     }
 };
 template <int LPR>
@@ -630,7 +652,7 @@ __global__ void __launch_bounds__(kBlock) episode_kernel(const __grid_constant__
         const double* gen = p.genomes + (size_t)rb * (size_t)p.G;
         FixedMlp<LPR, NET> mlp;
         if constexpr (NET::kLayers > 0) {
-            mlp.load(gen, g.sub);
+            if constexpr (LPR > 1) mlp.load(gen, g.sub);
         } else if (LPR > 1 && p.w_in_smem) {
             double* dst_g = s_gen + (size_t)slot * p.G;
             for (int i = g.sub; i < p.G; i += LPR) dst_g[i] = __ldg(gen + i);
@@ -717,7 +739,8 @@ __global__ void __launch_bounds__(kBlock) episode_kernel(const __grid_constant__
                     const int i = g.sub + s * LPR;
                     h[s] = (i < NET::sz(0)) ? R2P2_DIV(p.vr1, bufA[i * NR]) : 0.0;                     // 25/dst (inf when dst == 0)
                 }
-                mlp.forward(g.mask, g.sub, h, p.activation, v, w);
+                if constexpr (LPR > 1) mlp.forward(g.mask, g.sub, h, p.activation, v, w);
+                else mlp.forward_global(p.genomes + rb, (size_t)p.P, h, p.activation, v, w);
                 if (v > 180.0) v = R2P2_SUB(v, 360.0);
                 g.sync();                                  // bufA is rewritten by the next tick's sense
             } else if (p.ctrl_kind == R2P2_CTRL_NEURO) {
