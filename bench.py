@@ -51,11 +51,58 @@ WORKLOADS = {
                stage="track_2", robot="robot_omni.json", ctrl="linear", hidden=None, P=8192, T=1000, scale=0.05),
     "B64k": dict(name="P=65536 x T=1000 on one GPU, track_2.png, robot-neuro.json, MLP 5-10-7-4-2 tanh",
                  stage="track_2", robot="robot-neuro.json", ctrl="neuro", hidden=[10, 7, 4], P=65536, T=1000, scale=1.0),
+    # BASELINE.json configs[3]: track robot on res/track.png, 16,384 robots x 4 episodes (4 start headings)
+    "D": dict(name="scenario-track: 16384 robots x 4 start headings (0/90/180/270), track.png, robot-track.json, MLP 5-10-7-4-2 tanh, T=1000",
+              stage="track", robot="robot-track.json", ctrl="neuro", hidden=[10, 7, 4], P=65536, T=1000, scale=1.0, start="headings4"),
+    # BASELINE.json configs[4]: synthetic sweep: 4096^2 stage, 32 list-form rays, MLP 32-16-8-2
+    "E": dict(name="synthetic sweep: 4096x4096 stage (4096 random rectangles), 32 rays, MLP 32-16-8-2 tanh, P=262144 x T=1000",
+              stage="synthetic4096", robot="robot-synth32", ctrl="neuro", hidden=[16, 8], P=262144, T=1000, scale=1.0, start="free_space"),
 }
+ROBOTS["robot-track.json"] = dict(x=260.0, y=250.0, orientation=0.0, sonar_range=[0.5, 40], radius=5, sonars=[0, 45, 70, 290, 315], max_speed=50)
+ROBOTS["robot-synth32"] = dict(x=100.0, y=100.0, orientation=0.0, sonar_range=[0.5, 25], radius=5, sonars=[i * 11.25 for i in range(32)], max_speed=50)
+_stage_cache = {}
+
+
+def synthetic_stage(n=4096, n_rect=4096, seed=2026):
+    """white n x n stage, black border 8 px, n_rect random axis-aligned black rectangles of side U(8,128)."""
+    rs = np.random.RandomState(seed)
+    env = np.full((n, n), 255, dtype=np.uint8)
+    env[:8, :] = 0; env[-8:, :] = 0; env[:, :8] = 0; env[:, -8:] = 0
+    for _ in range(n_rect):
+        w_, h_ = rs.randint(8, 129, 2)
+        x_, y_ = rs.randint(0, n - w_), rs.randint(0, n - h_)
+        env[x_:x_ + w_, y_:y_ + h_] = 0
+    return env
+
+
+def start_poses(w, P, seed):
+    """(x0, y0, theta0) per robot for the workloads that do not start everybody at the robot json pose."""
+    rob = ROBOTS[w["robot"]]
+    kind = w.get("start")
+    if kind == "headings4":
+        return (np.full(P, rob["x"]), np.full(P, rob["y"]), np.tile(np.array([0.0, 90.0, 180.0, 270.0]), P // 4 + 1)[:P])
+    if kind == "free_space":
+        env = load_stage(w["stage"])
+        rs = np.random.RandomState(seed)
+        wall = env == 0
+        # clearance >= 8 px: erode free space with an integral image of the wall mask
+        c = 8
+        ii = np.pad(wall.astype(np.int32), ((1, 0), (1, 0))).cumsum(0).cumsum(1)
+        n = env.shape[0]
+        xs, ys = [], []
+        while len(xs) < P:
+            cx, cy = rs.randint(c + 1, n - c - 1, 2 * P), rs.randint(c + 1, n - c - 1, 2 * P)
+            cnt = ii[cx + c + 1, cy + c + 1] - ii[cx - c, cy + c + 1] - ii[cx + c + 1, cy - c] + ii[cx - c, cy - c]
+            ok = cnt == 0
+            xs.extend((cx[ok] + rs.uniform(0, 1, ok.sum())).tolist()); ys.extend((cy[ok] + rs.uniform(0, 1, ok.sum())).tolist())
+        return np.array(xs[:P]), np.array(ys[:P]), rs.uniform(0, 360, P)
+    return rob["x"], rob["y"], rob["orientation"]
 
 
 def load_stage(name):
-    return np.load(os.path.join(GOLDEN, "stage_%s.npz" % name))["env"]
+    if name not in _stage_cache:
+        _stage_cache[name] = synthetic_stage() if name == "synthetic4096" else np.load(os.path.join(GOLDEN, "stage_%s.npz" % name))["env"]
+    return _stage_cache[name]
 
 
 def genome_len(w):
@@ -115,10 +162,11 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_port_run(w, genomes, threads, reps=1):
+def cpu_port_run(w, genomes, threads, reps=1, poses=None):
     """The oracle (C restatement of the reference, libm flavour) on the host cores. Returns (robot_steps/s, dict)."""
     from oracle.oracle import Oracle, expand_sonars
     rob = ROBOTS[w["robot"]]
+    x0, y0, t0_ = poses if poses is not None else (rob["x"], rob["y"], rob["orientation"])
     O = Oracle(port=False)
     env = load_stage(w["stage"]).astype(np.int32)
     _, R = genome_len(w)
@@ -127,7 +175,7 @@ def cpu_port_run(w, genomes, threads, reps=1):
     steps = 0
     for _ in range(reps):
         out = O.run(env, rays=expand_sonars(rob["sonars"]), vr=rob["sonar_range"], radius=rob["radius"], max_speed=rob["max_speed"],
-                    ctrl=w["ctrl"], genomes=genomes, x0=rob["x"], y0=rob["y"], theta0=rob["orientation"], T=w["T"], layers=layers,
+                    ctrl=w["ctrl"], genomes=genomes, x0=x0, y0=y0, theta0=t0_, T=w["T"], layers=layers,
                     evolve=False, threads=threads)
         steps += int(out["state"]["ticks"].sum())
     dt = time.perf_counter() - t0
@@ -142,12 +190,14 @@ def run_reference(args, w):
     cores = os.cpu_count() or 1
     P = min(w["P"], 1024)
     genomes = make_genomes(w, 1234, P)
+    px, py, pt = start_poses(w, w["P"], 4321)
+    poses = tuple(np.asarray(a)[:P] if np.ndim(a) else a for a in (px, py, pt))
     for _ in range(args.warmup):
-        cpu_port_run(w, genomes[:64], cores)
+        cpu_port_run(w, genomes[:64], cores, poses=tuple(a[:64] if np.ndim(a) else a for a in poses))
     t = []
     steps_per_s = []
     for _ in range(args.steps):
-        v, _, dt = cpu_port_run(w, genomes, cores)
+        v, _, dt = cpu_port_run(w, genomes, cores, poses=poses)
         steps_per_s.append(v); t.append(dt)
     total_steps = P * w["T"] * args.steps
     value = total_steps / sum(t)
@@ -183,9 +233,10 @@ def run_ours(args, w):
     rob = ROBOTS[w["robot"]]
     P, T = w["P"], w["T"]
     G, R = genome_len(w)
+    px, py, pt = start_poses(w, P, 4321 + rank)
     ev = PopulationEvaluator(load_stage(w["stage"]), sonar_range=rob["sonar_range"], radius=rob["radius"], max_speed=rob["max_speed"],
-                             sonars=rob["sonars"], controller=w["ctrl"], hidden_layer=w["hidden"], x=rob["x"], y=rob["y"],
-                             orientation=rob["orientation"], ticks=T, delta=0.1, evolve=False, device=local,
+                             sonars=rob["sonars"], controller=w["ctrl"], hidden_layer=w["hidden"], x=px, y=py,
+                             orientation=pt, ticks=T, delta=0.1, evolve=False, device=local,
                              lanes_per_robot=args.lpr, stage_in_smem=args.smem)
     sim = ev.sim
     sim.set_stream(stream.cuda_stream)
@@ -297,11 +348,12 @@ def run_ours(args, w):
             cores = os.cpu_count() or 1
             n_ind = min(P, 1024)
             reps = 1
-            v, out, dt = cpu_port_run(w, genomes_np[:n_ind], cores)
+            cposes = tuple(np.asarray(a)[:n_ind] if np.ndim(a) else a for a in (px, py, pt))
+            v, out, dt = cpu_port_run(w, genomes_np[:n_ind], cores, poses=cposes)
             while dt * reps < 8.0 and reps < 16:
                 reps *= 2
             if reps > 1:
-                v, out, dt = cpu_port_run(w, genomes_np[:n_ind], cores, reps)
+                v, out, dt = cpu_port_run(w, genomes_np[:n_ind], cores, reps, poses=cposes)
             cpu_fit = out["fitness"]
             rel = np.abs(cpu_fit - fitness_dev[:n_ind]) / np.maximum(1e-300, np.abs(cpu_fit))
             cpu = {"value": v, "unit": "robot-steps/s", "cores": cores, "kind": "port",

@@ -101,6 +101,17 @@ int r2p2_set_robot(r2p2_handle h, double vr0, double vr1, double radius, double 
  * For CONST / LINEAR pass layers = NULL, n_layers = 0. */
 int r2p2_set_controller(r2p2_handle h, int32_t kind, const int32_t* layers, int32_t n_layers, int32_t activation);
 
+/* Sensor noise, Robot.has_noise / __generate_noise = np.random.normal(0, 0.5) (r2p2/robot.py:96,139-140,308-310): one draw
+ * per unclamped sonar ray, in ray order.
+ *   mode 0  off (the reference with has_noise = False)
+ *   mode 1  replay: stream[P][len] holds each robot's draws, consumed sequentially -- with
+ *           np.random.seed(s); np.random.normal(0, 0.5, len) a single robot reproduces the reference bit for bit
+ *   mode 2  device generator: Philox4x32-10 keyed by `seed`, counter (draw index, robot), Box-Muller, sigma 0.5
+ * Takes effect at the next r2p2_run; draw counters are zeroed by r2p2_reset. */
+int r2p2_set_noise(r2p2_handle h, int32_t mode, uint64_t seed, const double* stream, int32_t P, int32_t len);
+/* Draws consumed per robot since the last reset (uint32[P]). */
+int r2p2_read_noise_draws(r2p2_handle h, uint32_t* ndraws);
+
 /* Thread mapping: lanes per robot (1, 2, 4, 8, 16, 32) or R2P2_LPR_AUTO; stage_in_smem: 1 force the
  * shared-memory copy of the bit planes, 0 read them through L1/L2, -1 choose. */
 int r2p2_set_mapping(r2p2_handle h, int32_t lanes_per_robot, int32_t stage_in_smem);

@@ -25,20 +25,21 @@ class _Cfg(C.Structure):
                 ("ctrl_kind", C.c_int32), ("n_layers", C.c_int32), ("layers", C.c_int32 * MAX_LAYERS),
                 ("activation", C.c_int32), ("G", C.c_int32), ("evolve", C.c_int32),
                 ("delta", C.c_double), ("delta_ctrl", C.c_double), ("time_budget", C.c_double),
-                ("noise", C.c_void_p)]
+                ("noise", C.c_void_p), ("noise_len", C.c_int32)]
 
 
 class _Robot(C.Structure):
     _fields_ = [(n, C.c_double) for n in ("x", "y", "theta", "speed", "omega", "last_x", "last_y", "dist",
                                           "odom_x", "odom_y", "origin_x", "origin_y", "time", "fitness")] + \
                [("flags", C.c_uint32), ("ncollide", C.c_uint32), ("ticks", C.c_uint32),
-                ("nsamp_sonar", C.c_uint64), ("nsamp_coll", C.c_uint64), ("npixel", C.c_uint64)]
+                ("nsamp_sonar", C.c_uint64), ("nsamp_coll", C.c_uint64), ("npixel", C.c_uint64),
+                ("ndraws", C.c_uint32), ("pad_", C.c_uint32)]
 
 
 ROBOT_DTYPE = np.dtype([(n, "<f8") for n in ("x", "y", "theta", "speed", "omega", "last_x", "last_y", "dist",
                                              "odom_x", "odom_y", "origin_x", "origin_y", "time", "fitness")] +
                        [("flags", "<u4"), ("ncollide", "<u4"), ("ticks", "<u4"), ("_pad", "<u4"),
-                        ("nsamp_sonar", "<u8"), ("nsamp_coll", "<u8"), ("npixel", "<u8")])
+                        ("nsamp_sonar", "<u8"), ("nsamp_coll", "<u8"), ("npixel", "<u8"), ("ndraws", "<u4"), ("pad_", "<u4")])
 
 
 def build(force=False):
@@ -113,8 +114,9 @@ class Oracle:
         cfg.time_budget = float(time_budget)
         if noise is not None:
             noise = np.ascontiguousarray(noise, dtype=np.float64)
-            assert noise.shape == (P, T, len(rays))
+            assert noise.ndim == 2 and noise.shape[0] == P      # per-robot stream of N(0, 0.5) draws, consumed sequentially
             cfg.noise = noise.ctypes.data
+            cfg.noise_len = noise.shape[1]
         st = np.zeros(P, dtype=ROBOT_DTYPE)
         x0 = np.broadcast_to(np.asarray(x0, dtype=np.float64), (P,))
         y0 = np.broadcast_to(np.asarray(y0, dtype=np.float64), (P,))

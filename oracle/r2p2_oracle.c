@@ -83,7 +83,9 @@ typedef struct {
     double delta;              /* Robot.update(env, delta)                       */
     double delta_ctrl;         /* u.delta seen by the controller timer            */
     double time_budget;        /* controller self.time at episode start           */
-    const double* noise;       /* optional host noise stream [P][T][R] or NULL (has_noise False) */
+    const double* noise;       /* has_noise (robot.py:96,308-310): per-robot stream [P][noise_len] of N(0, 0.5) draws, consumed
+                                  one per unclamped ray in ray order exactly as np.random.normal is called; NULL = noise off */
+    int32_t noise_len;
 } orc_cfg;
 
 typedef struct {
@@ -95,6 +97,8 @@ typedef struct {
     uint32_t flags, ncollide, ticks;
     uint64_t nsamp_sonar, nsamp_coll;
     uint64_t npixel;           /* every env.item() the reference would have executed */
+    uint32_t ndraws;           /* noise draws consumed so far */
+    uint32_t pad_;
 } orc_robot;
 
 static const double ORC_RAD = 3.14159265358979323846 / 180.0;  /* CPython degToRad */
@@ -159,7 +163,7 @@ typedef struct {             /* optional per-tick trace rows for one robot (all 
 } orc_trace_row;
 
 /* robot.py:287-318 */
-static int orc_sense(const orc_cfg* c, orc_robot* rb, double* dst, const orc_trace_row* tr, const double* noise_row) {
+static int orc_sense(const orc_cfg* c, orc_robot* rb, double* dst, const orc_trace_row* tr, const double* noise_stream) {
     int64_t ox, oy;
     if (!orc_pyround(rb->x, &ox) || !orc_pyround(rb->y, &oy)) { rb->flags |= ORC_F_FAULT; return 0; }
     const double L = c->vr1 + c->radius;
@@ -176,7 +180,7 @@ static int orc_sense(const orc_cfg* c, orc_robot* rb, double* dst, const orc_tra
             tr->hitpx[2 * i + 1] = h.hit ? (int32_t)(int64_t)h.y : -1;
         }
         if ((d < c->vr0 + c->radius && d > c->vr0 * 0.125 + c->radius) || d > c->vr1 + c->radius) d = c->vr1 + c->radius;
-        else if (noise_row) d += noise_row[i];
+        else if (noise_stream) { d += (rb->ndraws < (uint32_t)c->noise_len) ? noise_stream[rb->ndraws] : 0.0; rb->ndraws++; }
         dst[i] = d;
         if (tr && tr->dst) tr->dst[i] = d;
     }
@@ -321,9 +325,9 @@ static int orc_move(const orc_cfg* c, orc_robot* rb, const double* crx, const do
 
 /* Robot.update (robot.py:389-402).  returns 1 if the robot keeps running. */
 static int orc_tick(const orc_cfg* c, orc_robot* rb, const double* genome, const double* crx, const double* cry,
-                    const orc_trace_row* tr, const double* noise_row) {
+                    const orc_trace_row* tr, const double* noise_stream) {
     double dst[ORC_MAX_RAYS];
-    if (!orc_sense(c, rb, dst, tr, noise_row)) return 0;
+    if (!orc_sense(c, rb, dst, tr, noise_stream)) return 0;
     double v, w;
     if (!orc_control(c, rb, genome, dst, &v, &w)) { rb->speed = 0; rb->omega = 0; return 0; }
     if (fabs(v) > c->max_speed) v = v / fabs(v) * c->max_speed;
@@ -384,7 +388,7 @@ static void* orc_worker(void* arg) {
             const uint32_t ncoll0 = rb->ncollide;
             int alive = 0;
             if (!(rb->flags & (ORC_F_FAULT | ORC_F_DONE))) {
-                const double* nz = c->noise ? c->noise + ((size_t)p * (size_t)j->T + (size_t)t) * R : NULL;
+                const double* nz = c->noise ? c->noise + (size_t)p * (size_t)c->noise_len : NULL;
                 alive = orc_tick(c, rb, genome, crx, cry, &tr, nz);
             }
             if (j->tr_pose) {

@@ -24,7 +24,7 @@ struct StateArrays {
     double *x = nullptr, *y = nullptr, *theta = nullptr, *speed = nullptr, *omega = nullptr, *last_x = nullptr, *last_y = nullptr,
            *dist = nullptr, *odom_x = nullptr, *odom_y = nullptr, *origin_x = nullptr, *origin_y = nullptr, *time = nullptr,
            *fitness = nullptr;
-    uint32_t *flags = nullptr, *ncollide = nullptr, *ticks = nullptr;
+    uint32_t *flags = nullptr, *ncollide = nullptr, *ticks = nullptr, *ndraws = nullptr;
     unsigned long long *nsamp_sonar = nullptr, *nsamp_coll = nullptr;
 };
 }  // namespace
@@ -66,6 +66,10 @@ struct r2p2_sim {
     double *d_x0 = nullptr, *d_y0 = nullptr, *d_t0 = nullptr;
     // mapping
     int lpr_req = 0, smem_req = -1;
+    // sensor noise
+    int noise_mode = 0, noise_len = 0, noise_P = 0;
+    unsigned long long noise_seed = 0;
+    double* d_noise = nullptr;
     // trace
     bool trace = false;
     int trace_T = 0, trace_P = 0, trace_R = 0;
@@ -109,7 +113,7 @@ int ensure_state(r2p2_handle h, int P) {
                       &s.origin_x, &s.origin_y, &s.time, &s.fitness, &h->d_x0, &h->d_y0, &h->d_t0};
     for (double** p : dbl) CK(dalloc(p, (size_t)P));
     CK(dalloc(&s.flags, (size_t)P)); CK(dalloc(&s.ncollide, (size_t)P)); CK(dalloc(&s.ticks, (size_t)P));
-    CK(dalloc(&s.nsamp_sonar, (size_t)P)); CK(dalloc(&s.nsamp_coll, (size_t)P));
+    CK(dalloc(&s.nsamp_sonar, (size_t)P)); CK(dalloc(&s.nsamp_coll, (size_t)P)); CK(dalloc(&s.ndraws, (size_t)P));
     h->state_cap = P;
     h->have_reset = false;
     return R2P2_OK;
@@ -292,7 +296,7 @@ int r2p2_destroy(r2p2_handle h) {
     cudaStreamSynchronize(h->stream);
     StateArrays& s = h->st;
     void* ptrs[] = {s.x, s.y, s.theta, s.speed, s.omega, s.last_x, s.last_y, s.dist, s.odom_x, s.odom_y, s.origin_x, s.origin_y,
-                    s.time, s.fitness, s.flags, s.ncollide, s.ticks, s.nsamp_sonar, s.nsamp_coll, h->d_x0, h->d_y0, h->d_t0,
+                    s.time, s.fitness, s.flags, s.ncollide, s.ticks, s.ndraws, s.nsamp_sonar, s.nsamp_coll, h->d_noise, h->d_x0, h->d_y0, h->d_t0,
                     h->d_wall, h->d_l50, h->d_dist, h->d_crxy, h->d_sincostab, h->d_genomes, h->d_genomes_t, h->d_work, h->d_cnt3};
     for (void* p : ptrs) cudaFree(p);
     free_trace(h);
@@ -398,6 +402,32 @@ int r2p2_set_controller(r2p2_handle h, int32_t kind, const int32_t* layers, int3
     return R2P2_OK;
 }
 
+int r2p2_set_noise(r2p2_handle h, int32_t mode, uint64_t seed, const double* stream, int32_t P, int32_t len) {
+    if (!h) return R2P2_E_ARG;
+    if (mode < 0 || mode > 2) return fail(h, R2P2_E_ARG, "noise mode must be 0 (off), 1 (host stream) or 2 (device generator)");
+    CK(cudaSetDevice(h->device));
+    if (mode == 1) {
+        if (!stream || P < 1 || len < 1) return fail(h, R2P2_E_ARG, "noise mode 1 needs a stream [P][len]");
+        CK(cudaStreamSynchronize(h->stream));
+        CK(dalloc(&h->d_noise, (size_t)P * len));
+        CK(cudaMemcpyAsync(h->d_noise, stream, sizeof(double) * (size_t)P * len, cudaMemcpyHostToDevice, h->stream));
+        if (h->st.ndraws && P <= h->state_cap) CK(cudaMemsetAsync(h->st.ndraws, 0, sizeof(uint32_t) * P, h->stream));   // a new stream is read from its start
+        CK(cudaStreamSynchronize(h->stream));
+        h->noise_P = P; h->noise_len = len;
+    }
+    h->noise_mode = mode; h->noise_seed = seed;
+    return R2P2_OK;
+}
+
+int r2p2_read_noise_draws(r2p2_handle h, uint32_t* ndraws) {
+    if (!h || !ndraws) return R2P2_E_ARG;
+    if (h->P < 1) return fail(h, R2P2_E_ARG, "no population");
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync(ndraws, h->st.ndraws, sizeof(uint32_t) * h->P, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return R2P2_OK;
+}
+
 int r2p2_set_mapping(r2p2_handle h, int32_t lanes_per_robot, int32_t stage_in_smem) {
     if (!h) return R2P2_E_ARG;
     const int l = lanes_per_robot;
@@ -443,7 +473,7 @@ int r2p2_reset(r2p2_handle h, const double* x0, const double* y0, const double* 
     r.x = s.x; r.y = s.y; r.theta = s.theta; r.speed = s.speed; r.omega = s.omega; r.last_x = s.last_x; r.last_y = s.last_y;
     r.dist = s.dist; r.odom_x = s.odom_x; r.odom_y = s.odom_y; r.origin_x = s.origin_x; r.origin_y = s.origin_y;
     r.time = s.time; r.fitness = s.fitness; r.flags = s.flags; r.ncollide = s.ncollide; r.ticks = s.ticks;
-    r.nsamp_sonar = s.nsamp_sonar; r.nsamp_coll = s.nsamp_coll;
+    r.nsamp_sonar = s.nsamp_sonar; r.nsamp_coll = s.nsamp_coll; r.ndraws = s.ndraws;
     reset_kernel<<<(h->P + 255) / 256, 256, 0, h->stream>>>(r);
     h->launches++;
     CK(cudaGetLastError());
@@ -502,6 +532,9 @@ int r2p2_run(r2p2_handle h, int32_t T, double delta, double delta_ctrl, int32_t 
     kp.dist = s.dist; kp.odom_x = s.odom_x; kp.odom_y = s.odom_y; kp.origin_x = s.origin_x; kp.origin_y = s.origin_y;
     kp.time = s.time; kp.fitness = s.fitness; kp.flags = s.flags; kp.ncollide = s.ncollide; kp.ticks = s.ticks;
     kp.nsamp_sonar = s.nsamp_sonar; kp.nsamp_coll = s.nsamp_coll;
+    kp.ndraws = s.ndraws;
+    kp.noise_mode = h->noise_mode; kp.noise_len = h->noise_len; kp.noise_seed = h->noise_seed; kp.noise_stream = h->d_noise;
+    if (h->noise_mode == 1 && h->noise_P != h->P) return fail(h, R2P2_E_ARG, "noise stream was uploaded for %d robots, population is %d", h->noise_P, h->P);
     kp.work_counter = h->d_work;
 
     if (lpr == 1) {

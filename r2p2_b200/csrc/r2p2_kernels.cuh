@@ -72,6 +72,12 @@ struct KParams {
     double *x, *y, *theta, *speed, *omega, *last_x, *last_y, *dist, *odom_x, *odom_y, *origin_x, *origin_y, *time, *fitness;
     uint32_t *flags, *ncollide, *ticks;
     unsigned long long *nsamp_sonar, *nsamp_coll;
+    // sensor noise (robot.py:96,139-140,308-310)
+    int32_t noise_mode;                // 0 off, 1 host stream, 2 device generator
+    int32_t noise_len;                 // draws per robot in noise_stream
+    unsigned long long noise_seed;
+    const double* noise_stream;        // [P][noise_len], consumed one per unclamped ray in ray order
+    uint32_t* ndraws;                  // [P] draws consumed so far
     // trace (optional)
     double* tr_pose; double* tr_dst; int32_t* tr_hitk; int32_t* tr_hitpx; uint32_t* tr_nsamp; uint32_t* tr_ncoll;
     // scheduling
@@ -404,6 +410,28 @@ struct Group {
     __device__ __forceinline__ unsigned bcast_u(unsigned v) const { return (LPR == 1) ? v : __shfl_sync(mask, v, 0, LPR); }
 };
 
+// ---------------------------------------------------------------------------------------------
+// sensor noise: Robot.__generate_noise = np.random.normal(0, 0.5) (r2p2/robot.py:139-140)
+// ---------------------------------------------------------------------------------------------
+// mode 1 replays a host-generated stream (bit-exact with the reference: np.random.seed(s); np.random.normal(0, 0.5, n)
+// is the reference's own draw sequence); mode 2 is the production generator: Philox4x32-10 keyed by the
+// seed, counter = (draw index, robot), Box-Muller, sigma 0.5 -- statistically equivalent, order independent.
+__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    c[0] = hi1 ^ c[1] ^ k0; c[1] = lo1; c[2] = hi0 ^ c[3] ^ k1; c[3] = lo0;
+}
+__device__ __forceinline__ double noise_draw(const KParams& p, unsigned rb, unsigned idx) {
+    if (p.noise_mode == 1) return (idx < (unsigned)p.noise_len) ? __ldg(p.noise_stream + (size_t)rb * p.noise_len + idx) : 0.0;
+    uint32_t c[4] = {idx, rb, 0u, 0u};
+    uint32_t k0 = (uint32_t)p.noise_seed, k1 = (uint32_t)(p.noise_seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) { philox_round(c, k0, k1); k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
+    const double u1 = ((double)(((unsigned long long)c[0] << 21) ^ (c[1] >> 11)) + 1.0) * (1.0 / 9007199254740992.0);   // (0, 1]
+    const double u2 = (double)(((unsigned long long)c[2] << 21) ^ (c[3] >> 11)) * (1.0 / 9007199254740992.0);           // [0, 1)
+    return 0.5 * sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+}
+
 // Robot.__crashing_radius (r2p2/robot.py:181-186), only reached when the centre pixel is within ceil(radius)+1 of a
 // blocked pixel.  returns 0 clear, 1 crashing, 2 the reference raises (IndexError before the first wall probe).
 template <int LPR>
@@ -647,6 +675,7 @@ __global__ void __launch_bounds__(kBlock) episode_kernel(const __grid_constant__
         double tmr = p.time[rb];
         double fitness = p.fitness[rb];
         unsigned flags = p.flags[rb], ncollide = p.ncollide[rb], ticks = p.ticks[rb];
+        unsigned ndraws = p.noise_mode ? p.ndraws[rb] : 0u;
         unsigned my_ns_sonar = 0u, ns_coll = 0u;          // my_ns_sonar: this lane's rays only
         // the genome is read every tick for T ticks: keep it next to the SM
         const double* gen = p.genomes + (size_t)rb * (size_t)p.G;
@@ -694,10 +723,27 @@ __global__ void __launch_bounds__(kBlock) episode_kernel(const __grid_constant__
                         }
                         PT(9)
                         if (h.fault && have_ray) fault = true;
-                        if (have_ray && (LPR == 1 || team_j == 0)) {
+                        const bool leader = have_ray && (LPR == 1 || team_j == 0);
+                        double d = 0.0;
+                        bool unclamped = false;
+                        if (leader) {
                             my_ns_sonar += h.nsamp;
-                            double d = (h.k >= 0) ? r2p2_norm2(R2P2_SUB(h.x, ox), R2P2_SUB(h.y, oy)) : r2p2_from_bits(0x7ff0000000000000ULL);
+                            d = (h.k >= 0) ? r2p2_norm2(R2P2_SUB(h.x, ox), R2P2_SUB(h.y, oy)) : r2p2_from_bits(0x7ff0000000000000ULL);
                             if ((d < p.db_hi && d > p.db_lo) || d > p.L) d = p.L;
+                            else unclamped = true;
+                        }
+                        if (p.noise_mode) {
+                            // robot.py:308-310: one N(0, 0.5) draw per unclamped ray, in ray order (= lane order here)
+                            unsigned nb = unclamped ? 1u : 0u, below = 0u;
+                            if (LPR > 1) {
+                                const unsigned gbase = (threadIdx.x & 31u) & ~(unsigned)(LPR - 1);
+                                nb = (__ballot_sync(g.mask, unclamped) >> gbase) & ((LPR == 32) ? 0xffffffffu : ((1u << LPR) - 1u));
+                                below = nb & ((1u << g.sub) - 1u);
+                            }
+                            if (unclamped) d = R2P2_ADD(d, noise_draw(p, rb, ndraws + (unsigned)__popc(below)));
+                            ndraws += (unsigned)__popc(nb);
+                        }
+                        if (leader) {
                             bufA[i * NR] = d;
                             if (tracing) {
                                 p.tr_dst[trow * R + i] = d;
@@ -923,6 +969,7 @@ __global__ void __launch_bounds__(kBlock) episode_kernel(const __grid_constant__
             p.time[rb] = tmr; p.fitness[rb] = fitness;
             p.flags[rb] = flags; p.ncollide[rb] = ncollide; p.ticks[rb] = ticks;
             p.nsamp_sonar[rb] += ns_sonar; p.nsamp_coll[rb] += ns_coll;
+            if (p.noise_mode) p.ndraws[rb] = ndraws;
         }
         g.sync();
     }
@@ -1014,6 +1061,7 @@ struct ResetParams {
     double *x, *y, *theta, *speed, *omega, *last_x, *last_y, *dist, *odom_x, *odom_y, *origin_x, *origin_y, *time, *fitness;
     uint32_t *flags, *ncollide, *ticks;
     unsigned long long *nsamp_sonar, *nsamp_coll;
+    uint32_t* ndraws;
 };
 __global__ void reset_kernel(const ResetParams r) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1026,6 +1074,7 @@ __global__ void reset_kernel(const ResetParams r) {
     r.time[i] = r.time_budget; r.fitness[i] = 0.0;
     r.flags[i] = 0u; r.ncollide[i] = 0u; r.ticks[i] = 0u;
     r.nsamp_sonar[i] = 0ull; r.nsamp_coll[i] = 0ull;
+    r.ndraws[i] = 0u;
 }
 
 __global__ void sum_counters_kernel(const unsigned long long* __restrict__ a, const unsigned long long* __restrict__ b,

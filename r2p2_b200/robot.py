@@ -30,7 +30,7 @@ class Robot:
         self.controller = controller if controller is not None else Controller()
         self.color = color
         self.name = name
-        self.has_noise = False          # device noise is not implemented: runs correspond to has_noise = False
+        self.has_noise = True           # the reference's default (robot.py:96)
         self.device = device
         self.collisions = 0
         self.flags = 0
@@ -73,13 +73,25 @@ class Robot:
 
     def update(self, env, delta, write_stats=False):
         """Robot.update (robot.py:389-402): sense, control, turn, move -- one fused kernel launch."""
-        if self.has_noise:
-            raise NotImplementedError("sensor noise (robot.py:308-310) is not generated on the device; set has_noise = False")
         sim = self._ensure(env)
         self._push(sim)
         ctrl = self.controller
         evolve = bool(getattr(ctrl, "evolve", False))
-        sim.run(1, delta=delta, delta_ctrl=getattr(ctrl, "delta_ctrl", delta), evolve=evolve)
+        if self.has_noise:
+            # robot.py:139-140, 308-310: np.random.normal(0, 0.5) per unclamped ray, from numpy's global stream.  The tick
+            # gets the next R draws of that stream to replay; afterwards the global generator is advanced by exactly the
+            # number the tick consumed, so a seeded run reproduces the reference draw for draw.
+            state = np.random.get_state()
+            draws = np.random.normal(0, 0.5, size=sim.R)
+            sim.set_noise("replay", stream=draws[None, :])
+            sim.run(1, delta=delta, delta_ctrl=getattr(ctrl, "delta_ctrl", delta), evolve=evolve)
+            used = int(sim.noise_draws()[0])
+            np.random.set_state(state)
+            if used:
+                np.random.normal(0, 0.5, size=used)
+        else:
+            sim.set_noise("off")
+            sim.run(1, delta=delta, delta_ctrl=getattr(ctrl, "delta_ctrl", delta), evolve=evolve)
         self._pull(sim)
 
     # ---- plumbing --------------------------------------------------------------------------------

@@ -95,6 +95,23 @@ class BatchSim:
         else:
             self._ck(self._L.r2p2_set_controller(self._h, CTRL[kind], None, 0, 0))
 
+    def set_noise(self, mode="off", seed=0, stream=None):
+        """Sensor noise (Robot.has_noise): "off", "replay" (stream[P, len] of N(0, 0.5) draws, bit-exact with the
+        reference's np.random.normal sequence) or "device" (Philox generator keyed by seed)."""
+        m = {"off": 0, "replay": 1, "device": 2}[mode]
+        if m == 1:
+            s = _f64(stream)
+            if s.ndim != 2:
+                raise ValueError("noise stream must be [P, len]")
+            self._ck(self._L.r2p2_set_noise(self._h, 1, int(seed), s.ctypes.data, s.shape[0], s.shape[1]))
+        else:
+            self._ck(self._L.r2p2_set_noise(self._h, m, int(seed), None, 0, 0))
+
+    def noise_draws(self):
+        n = np.empty(self.P, dtype=np.uint32)
+        self._ck(self._L.r2p2_read_noise_draws(self._h, n.ctypes.data))
+        return n
+
     def set_mapping(self, lanes_per_robot=0, stage_in_smem=-1):
         self._ck(self._L.r2p2_set_mapping(self._h, int(lanes_per_robot), int(stage_in_smem)))
 

@@ -265,12 +265,65 @@ def gen_episodes(E):
     np.savez_compressed(os.path.join(OUT, "episodes.npz"), meta=meta(), specs=json.dumps(specs), **out)
 
 
+def gen_noisy_episodes(E):
+    """has_noise = True (the reference's default, robot.py:96,308-310): np.random.normal(0, 0.5) is drawn once per
+    unclamped ray, in ray order, from the global legacy MT19937 stream.  Seeded runs; the same stream is reproduced
+    for the oracle / device with np.random.seed(s); np.random.normal(0, 0.5, size=n)."""
+    Scripted = make_scripted(E)
+    out, specs = {}, []
+
+    def run(name, stage, robot_json, ctrl, T, genome, kind, seed, layers=()):
+        env = counting(E.load_env(stage))
+        with contextlib.redirect_stdout(io.StringIO()):
+            r = E.make_robot(robot_json, ctrl)
+        r.has_noise = True
+        ncol = [0]
+        orig = ctrl.on_collision
+
+        def oc(pos):
+            ncol[0] += 1
+            orig(pos)
+        ctrl.on_collision = oc
+        R = len(r.sensors) if isinstance(r.sensors, list) else len(range(0, 360, math.floor(365 / r.sensors)))
+        pose = np.zeros((T, 5)); dst = np.zeros((T, R)); ncoll = np.zeros(T, dtype=np.int32)
+        np.random.seed(seed)
+        for t in range(T):
+            r.update(env, 0.1, False)
+            pose[t] = (r.x, r.y, r.orientation, r.speed, r.angular_velocity)
+            dst[t] = ctrl.dst
+            ncoll[t] = ncol[0]
+        nxt = np.random.normal(0, 0.5)                     # the draw after the last one consumed: fixes the draw count
+        np.random.seed(seed)
+        stream = np.random.normal(0, 0.5, size=T * R + 1)
+        ndraws = int(np.argmax(stream == nxt))
+        assert stream[ndraws] == nxt
+        out[name + "/pose"] = pose; out[name + "/dst"] = dst; out[name + "/ncoll"] = ncoll
+        out[name + "/genome"] = np.asarray(genome, dtype=np.float64); out[name + "/ndraws"] = np.int64(ndraws)
+        out[name + "/fitness"] = np.float64(ctrl.fitness() if hasattr(ctrl, "fitness") else 0.0)
+        specs.append({"name": name, "stage": stage, "robot": robot_json, "T": T, "kind": kind, "layers": list(layers), "seed": seed})
+        print("noisy episode", name, "T", T, "collides", ncol[0], "draws", ndraws)
+
+    c = np.random.RandomState(7).uniform(-1, 1, 18) * 0.05
+    run("noise_linear_omni", "track_2.png", "robot_omni.json", E.linear_controller(c), 250, c, "linear", 42)
+    c = np.random.RandomState(10).uniform(-1, 1, 12) * 0.08
+    run("noise_linear_ring", "track_2.png", "robot-neuro.json", E.linear_controller(c), 250, c, "linear", 43)
+    sc = Scripted(); sc.cmd = (12.0, 5.0)
+    run("noise_const", "stage.png", "robot.json", sc, 200, [12.0, 5.0], "const", 44)
+    w = np.random.RandomState(1).uniform(-1, 1, 156)
+    run("noise_neuro", "track_2.png", "robot-neuro.json", E.neuro_controller(w, [10, 7, 4]), 300, w, "neuro", 45, (5, 10, 7, 4, 2))
+    np.savez_compressed(os.path.join(OUT, "episodes_noise.npz"), meta=meta(), specs=json.dumps(specs), **out)
+
+
 def main():
     E = ref_harness.RefEnv()
     try:
+        if "--noise-only" in sys.argv:
+            gen_noisy_episodes(E)
+            return
         gen_rays(E)
         gen_ticks(E)
         gen_episodes(E)
+        gen_noisy_episodes(E)
         # stage bitmaps as the reference loads them (env[x, y], int32) -- fixtures for the GPU box
         for stage in STAGES:
             env = np.ascontiguousarray(E.load_env(stage)).astype(np.uint8)

@@ -22,6 +22,8 @@ def test_robot_update_reproduces_reference_episode():
     ctrl = Inspyred_controller({"controllers": [{"class": "inspyred.Inspyred_controller", "weights": list(e["kat3_linear/genome"]), "time": 20, "evolve": False}]})
     r = Robot(identifier=0, x=rob["x"], y=rob["y"], orientation=rob["orientation"], vision_range=tuple(rob["sonar_range"]), sensors=rob["sonars"],
               radius=rob["radius"], max_speed=rob["max_speed"], controller=ctrl)
+    assert r.has_noise is True                     # the reference's default (robot.py:96); golden runs switch it off
+    r.has_noise = False
     gp, gd, gc = e["kat3_linear/pose"], e["kat3_linear/dst"], e["kat3_linear/ncoll"]
     for t in range(120):
         r.update(env, 0.1, True)
@@ -41,6 +43,7 @@ def test_robot_facade_neuro_and_check_sensors():
                                               "hidden_layer": [10, 7, 4], "activation": "tanh", "time": 20, "evolve": False}]})
     r = Robot(identifier=0, x=rob["x"], y=rob["y"], orientation=0, vision_range=tuple(rob["sonar_range"]), sensors=rob["sonars"],
               radius=rob["radius"], max_speed=rob["max_speed"], controller=ctrl)
+    r.has_noise = False
     col, dst, ang = r.check_sensors(env)
     assert dst == list(e["kat2_neuro/dst"][0]) and ang == [0.0, 45.0, 70.0, 290.0, 315.0]
     assert (r.x, r.y) == (rob["x"], rob["y"])
@@ -49,9 +52,26 @@ def test_robot_facade_neuro_and_check_sensors():
         r.update(env, 0.1)
         assert abs(r.x - gp[t, 0]) < 1e-9 and abs(r.y - gp[t, 1]) < 1e-9 and abs(r.orientation - gp[t, 2]) < 1e-9
         assert np.array_equal(np.rint(ctrl.dst), np.rint(e["kat2_neuro/dst"][t]))
-    r.has_noise = True
-    with pytest.raises(NotImplementedError):
+
+
+def test_robot_facade_with_noise_replays_numpy_stream():
+    """has_noise = True: the facade feeds numpy's global legacy stream to the device, so a seeded run equals the
+    reference's seeded run draw for draw (golden: noise_linear_omni, np.random.seed(42))."""
+    import json
+    from r2p2_b200.controllers.inspyred import Inspyred_controller
+    from r2p2_b200.robot import Robot
+    e = common.golden("episodes_noise")
+    sp = next(s for s in json.loads(str(e["specs"])) if s["name"] == "noise_linear_omni")
+    rob = common.ROBOTS[sp["robot"]]
+    env = common.load_stage(sp["stage"])
+    ctrl = Inspyred_controller({"controllers": [{"class": "inspyred.Inspyred_controller", "weights": list(e["noise_linear_omni/genome"]), "time": 20, "evolve": False}]})
+    r = Robot(identifier=0, x=rob["x"], y=rob["y"], orientation=0, vision_range=tuple(rob["sonar_range"]), sensors=rob["sonars"],
+              radius=rob["radius"], max_speed=rob["max_speed"], controller=ctrl)
+    np.random.seed(sp["seed"])
+    for t in range(80):
         r.update(env, 0.1)
+        assert (r.x, r.y, r.orientation) == tuple(e["noise_linear_omni/pose"][t, :3]), t
+        assert ctrl.dst == list(e["noise_linear_omni/dst"][t]), t
 
 
 def test_scenario_files_and_evolution_callback(tmp_path, oracle_port):

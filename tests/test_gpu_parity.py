@@ -305,3 +305,81 @@ def test_error_conventions():
     with pytest.raises(r2p2_b200.R2P2Error):
         sim.set_mapping(3, 0)
     sim.close()
+
+
+@pytest.mark.parametrize("lpr", [1, 8, 32])
+def test_noise_replay_golden(lpr):
+    """Robot.has_noise = True (reference default): with the reference's own np.random.normal draws replayed on the device
+    (one per unclamped ray, ray order), poses / noisy distances / collide counts / number of draws are bit-identical to the
+    seeded reference runs (linear and constant-command controllers; MLP runs to 1e-9)."""
+    import json
+    e = common.golden("episodes_noise")
+    for sp in json.loads(str(e["specs"])):
+        n, rob = sp["name"], common.ROBOTS[sp["robot"]]
+        sim = common.make_sim(sp["stage"], sp["robot"], sp["kind"], hidden=sp["layers"][1:-1] if sp["layers"] else None, lpr=lpr)
+        np.random.seed(sp["seed"])
+        stream = np.random.normal(0, 0.5, size=sp["T"] * sim.R + 8)
+        sim.upload_genomes(e[n + "/genome"][None, :])
+        sim.reset(rob["x"], rob["y"], 0.0)
+        sim.set_noise("replay", stream=stream[None, :])
+        sim.set_trace(True, sp["T"])
+        sim.run(sp["T"])
+        tr = sim.trace(sp["T"])
+        assert int(sim.noise_draws()[0]) == int(e[n + "/ndraws"]), n
+        assert np.array_equal(np.cumsum(tr["ncoll"][:, 0]), e[n + "/ncoll"]), n
+        if sp["kind"] == "neuro":
+            assert np.max(np.abs(tr["pose"][:, 0, :3] - e[n + "/pose"][:, :3])) < 1e-9 * 500, n
+        else:
+            assert np.array_equal(tr["pose"][:, 0], e[n + "/pose"]), n
+            assert np.array_equal(tr["dst"][:, 0], e[n + "/dst"]), n
+        sim.close()
+
+
+def test_noise_replay_population_vs_oracle(oracle_port):
+    """Per-robot streams on a population: bit-identical to the port oracle for every mapping."""
+    stage, rj = "track_2.png", "robot_omni.json"
+    P, T = 200, 150
+    rs = np.random.RandomState(8)
+    genomes = rs.uniform(-1, 1, (P, 18)) * 0.05
+    streams = rs.normal(0, 0.5, (P, T * 8))
+    rob, kw = common.ROBOTS[rj], common.oracle_robot_kwargs(rj)
+    ref = oracle_port.run(common.load_stage(stage), ctrl="linear", genomes=genomes, x0=rob["x"], y0=rob["y"], theta0=0.0, T=T, noise=streams, threads=4, **kw)
+    for lpr in (1, 4, 8, 32):
+        sim = common.make_sim(stage, rj, "linear", lpr=lpr)
+        sim.upload_genomes(genomes)
+        sim.reset(rob["x"], rob["y"], 0.0)
+        sim.set_noise("replay", stream=streams)
+        sim.run(T)
+        s = sim.state()
+        assert np.array_equal(s["x"], ref["state"]["x"]) and np.array_equal(s["theta"], ref["state"]["theta"]), lpr
+        assert np.array_equal(sim.fitness(), ref["fitness"]) and np.array_equal(sim.noise_draws(), ref["state"]["ndraws"]), lpr
+        sim.close()
+
+
+def test_noise_device_generator_statistics():
+    """Mode "device": Philox + Box-Muller.  Draws are N(0, 0.5): sample mean / std / kurtosis over ~1e5 draws, reproducible
+    for a seed, different across seeds and robots."""
+    stage, rj = "stage.png", "robot_omni.json"
+    P, T = 4096, 8
+    genomes = np.zeros((P, 2))                                  # constant command (0, 0): the robots stand still
+    res = {}
+    for seed, mode in ((0, "off"), (1, "device"), (1, "device"), (2, "device")):
+        sim = common.make_sim(stage, rj, "const", lpr=8)
+        sim.upload_genomes(genomes)
+        sim.reset(260.0, 200.0, np.linspace(0, 359, P))
+        sim.set_noise(mode, seed=seed)
+        sim.set_trace(True, T)
+        sim.run(T)
+        res.setdefault((seed, mode), []).append(sim.trace(T)["dst"].copy())
+        sim.close()
+    clean = res[(0, "off")][0]
+    a, a2 = res[(1, "device")]
+    b = res[(2, "device")][0]
+    assert np.array_equal(a, a2) and not np.array_equal(a, b)
+    unclamped = clean < 55.0                                     # clamped rays (dst == L) get no noise
+    assert np.array_equal(a[~unclamped], clean[~unclamped])
+    d = (a - clean)[unclamped]
+    assert d.size > 30_000
+    assert abs(d.mean()) < 0.01 and abs(d.std() - 0.5) < 0.01
+    assert abs(((d / d.std()) ** 4).mean() - 3.0) < 0.1
+    assert abs(np.corrcoef(d[:-1], d[1:])[0, 1]) < 0.02

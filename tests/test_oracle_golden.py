@@ -115,3 +115,26 @@ def test_evolve_semantics(oracle_libm):
     assert ev["fitness"][0] == free["fitness"][0]                                    # pose frozen afterwards (SURVEY KAT2)
     tm = oracle_libm.run(env, T=1000, evolve=True, delta_ctrl=100.0, time_budget=20000.0, **kw)   # timer: 200 control() calls
     assert tm["state"]["ticks"][0] == 199 and tm["state"]["flags"][0] & 4
+
+
+@pytest.mark.parametrize("flavour", ["libm", "port"])
+def test_noisy_episodes(flavour, oracle_libm, oracle_port):
+    """has_noise = True (reference default, robot.py:96,308-310): seeded reference runs; the oracle consumes the same
+    np.random.normal(0, 0.5) stream one draw per unclamped ray in ray order.  Linear / constant-command runs are
+    bit-identical (pose, noisy distances, collide counts, number of draws); the MLP run to 1e-9."""
+    import json
+    O = oracle_libm if flavour == "libm" else oracle_port
+    e = common.golden("episodes_noise")
+    for sp in json.loads(str(e["specs"])):
+        n, rob, kw = sp["name"], common.ROBOTS[sp["robot"]], common.oracle_robot_kwargs(sp["robot"])
+        np.random.seed(sp["seed"])
+        stream = np.random.normal(0, 0.5, size=sp["T"] * len(kw["rays"]) + 8)
+        out = O.run(common.load_stage(sp["stage"]), ctrl=sp["kind"], genomes=e[n + "/genome"][None, :], x0=rob["x"], y0=rob["y"], theta0=0.0,
+                    T=sp["T"], layers=sp["layers"], noise=stream[None, :], trace=True, **kw)
+        assert int(out["state"]["ndraws"][0]) == int(e[n + "/ndraws"]), n
+        assert np.array_equal(np.cumsum(out["ncoll"][:, 0]), e[n + "/ncoll"]), n
+        if sp["kind"] == "neuro":
+            assert np.max(np.abs(out["pose"][:, 0, :3] - e[n + "/pose"][:, :3])) < 1e-9 * 500, n
+        else:
+            assert np.array_equal(out["pose"][:, 0], e[n + "/pose"]), n
+            assert np.array_equal(out["dst"][:, 0], e[n + "/dst"]), n

@@ -14,8 +14,9 @@ a = ap.parse_args()
 w = dict(bench.WORKLOADS[a.workload])
 if a.ticks: w["T"] = a.ticks
 rob = bench.ROBOTS[w["robot"]]
+px, py, pt = bench.start_poses(w, w["P"], 4321)
 ev = PopulationEvaluator(bench.load_stage(w["stage"]), sonar_range=rob["sonar_range"], radius=rob["radius"], max_speed=rob["max_speed"],
-                         sonars=rob["sonars"], controller=w["ctrl"], hidden_layer=w["hidden"], x=rob["x"], y=rob["y"], ticks=w["T"],
+                         sonars=rob["sonars"], controller=w["ctrl"], hidden_layer=w["hidden"], x=px, y=py, orientation=pt, ticks=w["T"],
                          lanes_per_robot=a.lpr, stage_in_smem=a.smem)
 g = bench.make_genomes(w, 1234, w["P"])
 for i in range(a.iters):
