@@ -88,3 +88,18 @@ def test_controller_base_contract():
             return 1, 2
     k = K(); k.set_ang([0])
     assert k.control([5.0]) == (1, 2) and k.actual_sensor_angles == [0]
+
+
+def test_ga_improves_and_is_deterministic():
+    """The GA driver (r2p2_b200/ea.py) on the reference's stub evaluator evaluate_test = sum(candidate) (evolution.py:54-56)."""
+    from r2p2_b200.ea import GAConfig, GeneticAlgorithm
+    ev = lambda pop: pop.sum(axis=1)
+    runs = []
+    for _ in range(2):
+        ga = GeneticAlgorithm(GAConfig(pop_size=64, genome_len=10, min_gen=0, max_gen=2, seed=3), ev)
+        best, fit = ga.run(25)
+        runs.append((best.copy(), fit, [r["best"] for r in ga.log]))
+    assert np.array_equal(runs[0][0], runs[1][0]) and runs[0][1] == runs[1][1]          # same seed, same run
+    bests = runs[0][2]
+    assert bests[-1] > bests[0] and all(b2 >= b1 for b1, b2 in zip(bests, bests[1:]))     # elitism: monotone
+    assert runs[0][1] > 17.0 and np.all(runs[0][0] <= 2.0) and np.all(runs[0][0] >= 0.0)
