@@ -28,6 +28,7 @@
 
 #include "r2p2_mathconsts.h"
 #include "r2p2_sincostab.h"
+#include "r2p2_tanhtab.h"
 
 #if defined(__CUDACC__)
 #define R2P2_HD __host__ __device__ __forceinline__
@@ -61,6 +62,15 @@ static __device__ __constant__ double r2p2_d_atan_lo[9] = {R2P2_ATAN_LO_VALUES};
 static const double r2p2_h_atan_hi[9] = {R2P2_ATAN_HI_VALUES};
 static const double r2p2_h_atan_lo[9] = {R2P2_ATAN_LO_VALUES};
 static const double r2p2_h_sincostab[R2P2_SINCOSTAB_LEN] = {R2P2_SINCOSTAB_VALUES};
+static const double r2p2_h_tanhtab[R2P2_TANH_NINT * R2P2_TANH_ROW] = {R2P2_TANHTAB_VALUES};
+#if defined(__CUDACC__)
+static __device__ const double r2p2_d_tanhtab[R2P2_TANH_NINT * R2P2_TANH_ROW] = {R2P2_TANHTAB_VALUES};
+#endif
+#if defined(__CUDA_ARCH__)
+#define R2P2_TANHTAB r2p2_d_tanhtab
+#else
+#define R2P2_TANHTAB r2p2_h_tanhtab
+#endif
 #if defined(__CUDA_ARCH__)
 #define R2P2_ATAN_HI(i) r2p2_d_atan_hi[(i)]
 #define R2P2_ATAN_LO(i) r2p2_d_atan_lo[(i)]
@@ -326,13 +336,46 @@ R2P2_HD double r2p2__exp_neg(double y) {     // y <= 0; results below 2^-1021 fl
     return R2P2_MUL(two_k, R2P2_ADD(1.0, p));
 }
 
-R2P2_HD double r2p2_tanh(double x) {
+// tanh, exp-based (kept for reference / accuracy cross-check): expm1 + one division, ~446 cycles on B200.
+R2P2_HD double r2p2_tanh_exp(double x) {
     const double ax = r2p2_fabs(x);
     if (x != x) return x;
     if (ax >= 22.0) return r2p2_copysign(1.0, x);
     if (ax < 0x1.0p-28) return x;
     const double t = r2p2__expm1_neg(R2P2_MUL(-2.0, ax));   // in (-1, 0)
     const double r = R2P2_DIV(r2p2_neg(t), R2P2_ADD(t, 2.0));
+    return r2p2_copysign(r, x);
+}
+
+// tanh by table: on [2^-6, 32) a degree-11 Taylor polynomial around the midpoint of the interval selected by the
+// exponent and the top four mantissa bits of |x| (tools/gen_tanhtab.py; t = |x| - mid is exact), evaluated with Estrin's
+// scheme -- no exp, no division, a 5-deep dependent chain.  Below 2^-6 the odd series at 0; from 20 on, +-1.
+R2P2_HD double r2p2_tanh(double x) {
+    const double ax = r2p2_fabs(x);
+    if (x != x) return x;
+    if (ax >= 20.0) return r2p2_copysign(1.0, x);
+    if (ax < 0x1.0p-6) {
+        if (ax < 0x1.0p-28) return x;
+        const double S[4] = {R2P2_TANH_SMALL_VALUES};
+        const double xx = R2P2_MUL(x, x);
+        double p = R2P2_FMA(xx, S[3], S[2]);
+        p = R2P2_FMA(xx, p, S[1]);
+        p = R2P2_FMA(xx, p, S[0]);
+        return R2P2_FMA(R2P2_MUL(x, xx), p, x);
+    }
+    const uint64_t top = r2p2_bits(ax) >> 48;                                   // exponent field and 4 mantissa bits
+    const int idx = (int)top - ((1023 + R2P2_TANH_E_LO) << 4);
+    const double mid = r2p2_from_bits((top << 48) | (1ULL << 47));
+    const double t = R2P2_SUB(ax, mid);
+    // row: c0 hi, c0 lo, c1..c11.  tanh = c0 + t * (c1 + c2 t + ... + c11 t^10): the bracket by Estrin, the dominant
+    // term added last so that its rounding is the only one that matters (|t| <= mid/32)
+    const double* c = R2P2_TANHTAB + idx * R2P2_TANH_ROW;
+    const double t2 = R2P2_MUL(t, t), t4 = R2P2_MUL(t2, t2), t8 = R2P2_MUL(t4, t4);
+    const double a0 = R2P2_FMA(c[3], t, c[2]), a1 = R2P2_FMA(c[5], t, c[4]), a2 = R2P2_FMA(c[7], t, c[6]);
+    const double a3 = R2P2_FMA(c[9], t, c[8]), a4 = R2P2_FMA(c[11], t, c[10]);
+    const double b0 = R2P2_FMA(a1, t2, a0), b1 = R2P2_FMA(a3, t2, a2), b2 = R2P2_FMA(c[12], t2, a4);
+    const double inner = R2P2_FMA(b2, t8, R2P2_FMA(b1, t4, b0));
+    const double r = R2P2_ADD(c[0], R2P2_FMA(t, inner, c[1]));
     return r2p2_copysign(r, x);
 }
 
