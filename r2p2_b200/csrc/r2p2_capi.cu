@@ -13,7 +13,7 @@
 #include <string>
 #include <vector>
 
-#include "r2p2_kernels.cuh"
+#include "r2p2_kernel_ws.cuh"
 
 using namespace r2p2;
 
@@ -185,9 +185,8 @@ int upload_crxy(r2p2_handle h) {
     return R2P2_OK;
 }
 
-template <int LPR, bool SMEM, class NET>
-int launch_episode(r2p2_handle h, const KParams& kp, size_t smem) {
-    auto kern = episode_kernel<LPR, SMEM, NET>;
+template <int LPR, class KERN>
+int launch_kernel(r2p2_handle h, KERN kern, const KParams& kp, size_t smem) {
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kBlock, smem));
@@ -203,6 +202,19 @@ int launch_episode(r2p2_handle h, const KParams& kp, size_t smem) {
     h->launches++;
     CK(cudaGetLastError());
     return R2P2_OK;
+}
+
+template <int LPR, bool SMEM, class NET>
+int launch_episode(r2p2_handle h, const KParams& kp, size_t smem) {
+    // 2..16 lanes per robot: the warp-synchronous kernel (r2p2_kernel_ws.cuh), same results, one instruction stream per
+    // warp.  R2P2_WS=0 in the environment selects the per-group kernel for A/B measurements.
+    if constexpr (LPR >= 2 && LPR <= 16 && !SMEM) {
+        static const bool ws = [] { const char* e = getenv("R2P2_WS"); return !(e && e[0] == '0'); }();
+        // (a sonar limit without a norm window sends whole groups through the plain loop, which the lock-step kernel
+        // cannot mix with groups that have stopped)
+        if (ws && kp.L > -1.0 && kp.L < 30000.0) return launch_kernel<LPR>(h, episode_kernel_ws<LPR, NET>, kp, smem);
+    }
+    return launch_kernel<LPR>(h, episode_kernel<LPR, SMEM, NET>, kp, smem);
 }
 
 template <class NET>

@@ -383,6 +383,21 @@ __device__ __forceinline__ Hit team_march(const StageView& s, const Team& tm, co
     return r;
 }
 
+// A ray of this limit from (x, y) that cannot reach a blocked pixel: every sample k < kB lies within k (+1 for the
+// truncation) pixels of the origin pixel, so with a distance-field value >= kB + 1 there all of them fall on unblocked
+// interior pixels and the reference loop runs exactly kB times and misses.  Only taken when the norm window is empty
+// (no knife-edge sample, which is the case unless the limit is within 2e-7 of an integer).
+__device__ __forceinline__ bool ray_is_clear(const StageView& s, double x, double y, double limit, unsigned& nsamp) {
+    int kA, kB;
+    norm_window(limit, kA, kB);
+    if ((kA != kB) | (kB > 250)) return false;
+    const int ix = dtrunc(x), iy = dtrunc(y);
+    if (!(((unsigned)ix < (unsigned)s.W) & ((unsigned)iy < (unsigned)s.H))) return false;   // also NaN / inf
+    if ((int)__ldg(s.dist + (size_t)iy * s.W + ix) < kB + 1) return false;
+    nsamp = (unsigned)kB;
+    return true;
+}
+
 // ---------------------------------------------------------------------------------------------
 // group (LPR lanes of one warp working on one robot)
 // ---------------------------------------------------------------------------------------------
@@ -870,12 +885,15 @@ __global__ void __launch_bounds__(kBlock) episode_kernel(const __grid_constant__
                 if (!csc.ok) { flags |= R2P2_F_TRIGRANGE | R2P2_F_FAULT; break; }   // NaN displacement: the reference faults two statements later
                 PT(4)
                 Hit ms;
-                if (LPR == 1) {
-                    ms = march(sv, x, y, cc_, cs_, R2P2_ADD(r2p2_norm2(dx, dy), p.radius));
+                const double climit = R2P2_ADD(r2p2_norm2(dx, dy), p.radius);
+                ms.x = -1.0; ms.y = -1.0; ms.k = -1; ms.nsamp = 0u; ms.fault = false;
+                if (ray_is_clear(sv, x, y, climit, ms.nsamp)) {
+                    // open space around the robot (group-uniform: same x, y, climit in every lane): the ray misses
+                } else if (LPR == 1) {
+                    ms = march(sv, x, y, cc_, cs_, climit);
                 } else {                                   // the whole group is one team on the collision ray
                     Team tm;
                     tm.tl = LPR; tm.j = g.sub; tm.mask = g.mask; tm.sync = g.mask;
-                    const double climit = R2P2_ADD(r2p2_norm2(dx, dy), p.radius);
                     ms = team_march(sv, tm, make_plan(climit, LPR), x, y, cc_, cs_, climit);
                 }
                 ns_coll += ms.nsamp;

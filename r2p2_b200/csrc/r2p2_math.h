@@ -225,23 +225,82 @@ R2P2_HD double r2p2_cos(double x, const double* tab, int* ok) {
     return R2P2_SUB(x, x) / R2P2_SUB(x, x);
 }
 
-// Both at once (shares the range reduction; results identical to the two calls above).
+// Both at once, results identical to the two calls above, without data-dependent branches on the common paths.
+// In every range of glibc's sin and cos the pair needs exactly ONE do_sin and ONE do_cos evaluation:
+//   |x| < 0.855469           sin = do_sin(x, 0)                  cos = do_cos(x, 0)
+//   |x| < 2.426265           sin = +-do_cos(hp0 - |x|, hp1)      cos = do_sin(a, da), a + da = (hp0 - |x|) + hp1
+//   |x| < 105414350          (a, da, n) = reduce(x): quadrant n for sin, n + 1 for cos: one is do_sin(a, da), the other do_cos(a, da)
+// so the three ranges only select the arguments and route the two results.  Lanes of a warp that hold angles of
+// different ranges (the rays of a sonar fan; robots of a population) execute one instruction stream instead of up to
+// six; inside do_sin the Taylor branch (|x| < 0.126) is evaluated next to the table branch and selected.
 R2P2_HD void r2p2_sincos(double x, const double* tab, double* s, double* c, int* ok) {
     const int32_t k = r2p2_hi32(x) & 0x7fffffff;
-    if (k >= 0x400368fd && k < 0x419921FB) {
-        double a, da;
-        const int n = r2p2__reduce_sincos(x, &a, &da);
-        // sin: quadrant n ; cos: quadrant n+1.  One of them needs do_sin, the other do_cos.
-        const double ds = r2p2__do_sin(a, da, tab);
-        const double dc = r2p2__do_cos(a, da, tab);
-        const double rs = (n & 1) ? dc : ds;
-        const double rc = (n & 1) ? ds : dc;
-        *s = (n & 2) ? r2p2_neg(rs) : rs;
-        *c = ((n + 1) & 2) ? r2p2_neg(rc) : rc;
+    if (k >= 0x419921FB) {                                  // rare: unsupported range / not finite
+        if (ok) *ok = 0;
+        *s = R2P2_SUB(x, x) / R2P2_SUB(x, x);
+        *c = *s;
         return;
     }
-    *s = r2p2_sin(x, tab, ok);
-    *c = r2p2_cos(x, tab, ok);
+    const int r1 = k < 0x3feb6000, r2 = !r1 && (k < 0x400368fd);
+    const double ax = r2p2_fabs(x);
+    // range 3: Cody-Waite reduction (always evaluated; harmless for small |x|)
+    double a3, da3;
+    const int n = r2p2__reduce_sincos(x, &a3, &da3);
+    // range 2
+    const double t2 = R2P2_SUB(R2P2_S_HP0, ax);
+    const double a2 = R2P2_ADD(t2, R2P2_S_HP1);
+    const double da2 = R2P2_ADD(R2P2_SUB(t2, a2), R2P2_S_HP1);
+    // arguments of the one do_sin and the one do_cos
+    const double sx = r1 ? x : (r2 ? a2 : a3);
+    double sdx = r1 ? 0.0 : (r2 ? da2 : da3);
+    const double cx = r1 ? x : (r2 ? t2 : a3);
+    double cdx = r1 ? 0.0 : (r2 ? R2P2_S_HP1 : da3);
+    // ---- do_sin(sx, sdx) ----
+    double ds;
+    {
+        const double tay = r2p2__taylor_sin(R2P2_MUL(sx, sx), sx, sdx);
+        const double asx = r2p2_fabs(sx);
+        if (!(sx > 0.0)) sdx = r2p2_neg(sdx);
+        const double u = R2P2_ADD(asx, R2P2_S_BIG);
+        const double xr = R2P2_SUB(asx, R2P2_SUB(u, R2P2_S_BIG));
+        const double xx = R2P2_MUL(xr, xr);
+        const double sp = R2P2_ADD(xr, R2P2_FMA(R2P2_MUL(xr, xx), R2P2_FMA(xx, R2P2_S_SN5, R2P2_S_SN3), sdx));
+        const double cp = R2P2_FMA(xr, sdx, R2P2_MUL(xx, R2P2_FMA(xx, R2P2_FMA(xx, R2P2_S_CS6, R2P2_S_CS4), R2P2_S_CS2)));
+        int ti = r2p2_lo32(u) * 4;
+        if (asx < 0.126) ti = 0;                            // the table value is not used; keep the address in range
+        const double sn = tab[ti], ssn = tab[ti + 1], cs = tab[ti + 2], ccs = tab[ti + 3];
+        const double cor = R2P2_FMA(sp, cs, R2P2_FMA(r2p2_neg(cp), sn, R2P2_FMA(sp, ccs, ssn)));
+        ds = (asx < 0.126) ? tay : r2p2_copysign(R2P2_ADD(sn, cor), sx);
+    }
+    // ---- do_cos(cx, cdx) ----
+    double dc;
+    {
+        if (cx < 0.0) cdx = r2p2_neg(cdx);
+        const double acx = r2p2_fabs(cx);
+        const double u = R2P2_ADD(acx, R2P2_S_BIG);
+        const double xr = R2P2_ADD(R2P2_SUB(acx, R2P2_SUB(u, R2P2_S_BIG)), cdx);
+        const double xx = R2P2_MUL(xr, xr);
+        const double sp = R2P2_FMA(R2P2_MUL(xr, xx), R2P2_FMA(xx, R2P2_S_SN5, R2P2_S_SN3), xr);
+        const double cp = R2P2_MUL(xx, R2P2_FMA(xx, R2P2_FMA(xx, R2P2_S_CS6, R2P2_S_CS4), R2P2_S_CS2));
+        const int ti = r2p2_lo32(u) * 4;
+        const double sn = tab[ti], ssn = tab[ti + 1], cs = tab[ti + 2], ccs = tab[ti + 3];
+        const double cor = R2P2_FMA(r2p2_neg(sp), sn, R2P2_FMA(r2p2_neg(cp), cs, R2P2_FMA(r2p2_neg(sp), ssn, ccs)));
+        dc = R2P2_ADD(cs, cor);
+    }
+    // ---- route ----
+    double rs, rc;
+    if (r1) { rs = ds; rc = dc; }
+    else if (r2) { rs = r2p2_copysign(dc, x); rc = ds; }
+    else {
+        rs = (n & 1) ? dc : ds;
+        rc = (n & 1) ? ds : dc;
+        if (n & 2) rs = r2p2_neg(rs);
+        if ((n + 1) & 2) rc = r2p2_neg(rc);
+    }
+    if (k < 0x3e500000) rs = x;
+    if (k < 0x3e400000) rc = 1.0;
+    *s = rs;
+    *c = rc;
 }
 
 // ---------------------------------------------------------------------------------------------
