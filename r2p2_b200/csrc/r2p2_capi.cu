@@ -759,4 +759,8 @@ extern "C" int r2p2_debug_phase_cycles(unsigned long long* out16, int reset) {
     }
     return 0;
 }
+extern "C" int r2p2_debug_robot_cycles(unsigned long long* out, int n_robots) {
+    cudaDeviceSynchronize();
+    return cudaMemcpyFromSymbol(out, r2p2::g_robot_cycles, (size_t)n_robots * 12 * sizeof(unsigned long long)) == cudaSuccess ? 0 : -1;
+}
 #endif

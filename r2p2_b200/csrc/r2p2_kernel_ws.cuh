@@ -38,6 +38,11 @@ struct WGroup {
         for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o, 32);
         return v;
     }
+    __device__ __forceinline__ unsigned min_u(unsigned v) const {
+#pragma unroll
+        for (int o = LPR / 2; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o, 32));
+        return v;
+    }
 };
 
 template <int LPR, class NET>
@@ -77,7 +82,8 @@ __global__ void __launch_bounds__(kBlock, (NET::kLayers > 0) ? 1 : 4) episode_ke
     const int R = p.R;
     const double delta = p.delta;
     const bool tracing = p.tr_pose != nullptr;
-    const int tl = (R >= LPR) ? 1 : LPR / R;              // lanes per sonar ray (team size)
+    int tl = 1;                                           // lanes per sonar ray: the largest power of two with R teams in the group
+    while (tl * 2 * R <= LPR && tl < kMaxSonarTeam) tl *= 2;
     const int rays_per_round = LPR / tl;
     const int team_ray = g.sub / tl, team_j = g.sub % tl;
     Team sonar_team;
@@ -139,7 +145,7 @@ __global__ void __launch_bounds__(kBlock, (NET::kLayers > 0) ? 1 : 4) episode_ke
                 const double ang = have_ray ? R2P2_ADD(p.ray_deg[i], theta) : 0.0;
                 const SinCos sc = sincos_call(R2P2_MUL(ang, kRad), s_tab);
                 if (!sc.ok && have_ray) { flags |= R2P2_F_TRIGRANGE; fault = true; }
-                const Hit h = team_march(sv, sonar_team, plan, ox, oy, sc.c, sc.s, p.L);
+                const Hit h = team_march<(LPR < kMaxSonarTeam ? LPR : kMaxSonarTeam), 4>(sv, sonar_team, plan, ox, oy, sc.c, sc.s, p.L);
                 if (h.fault && have_ray) fault = true;
                 const bool leader = have_ray && (team_j == 0);
                 double d = 0.0;
@@ -268,7 +274,7 @@ __global__ void __launch_bounds__(kBlock, (NET::kLayers > 0) ? 1 : 4) episode_ke
                 const bool teamed = must_march && windowed;
                 MarchPlan cplan = make_plan(teamed ? climit : 0.0, LPR);
                 if (!teamed) { cplan.kA = 0; cplan.kB = 0; cplan.chunk = 0; }
-                const Hit mh = team_march(sv, coll_team, cplan, x, y, csc.c, csc.s, climit);
+                const Hit mh = team_march_t<LPR, (LPR >= 8 ? 32 / LPR : 4)>(sv, coll_team, cplan, x, y, csc.c, csc.s, climit);
                 if (teamed) ms = mh;
                 else if (must_march) ms = march_plain(sv, x, y, csc.c, csc.s, climit);
             }
@@ -335,20 +341,12 @@ __global__ void __launch_bounds__(kBlock, (NET::kLayers > 0) ? 1 : 4) episode_ke
             if (__any_sync(FULL, need_ring)) {
                 // 360 probes over the lanes of the group; the reference stops at the first wall, so an IndexError only
                 // counts if it comes before the first wall probe.  Groups that do not need the ring idle through it.
-                int first_wall = 360, first_fault = 360;
-                if (need_ring) {
-                    for (int i = g.sub; i < 360; i += LPR) {
-                        bool pf = false;
-                        const bool wl = px_probe(sv.wall, sv, dtrunc(R2P2_ADD(x, s_crx[i])), dtrunc(R2P2_ADD(y, s_cry[i])), pf);
-                        if (pf) first_fault = min(first_fault, i);
-                        if (wl) first_wall = min(first_wall, i);
-                    }
-                }
-                first_wall = g.min_i(first_wall);
-                first_fault = g.min_i(first_fault);
-                if (need_ring) {
-                    if (first_fault < first_wall) { flags |= R2P2_F_FAULT; live = false; }
-                    else crash = first_wall < 360;
+                unsigned key = 0xffffffffu;
+                if (need_ring) key = ring_scan<LPR>(sv, g.sub, x, y, s_crx, s_cry);
+                key = g.min_u(key);
+                if (need_ring && key != 0xffffffffu) {
+                    if (key & 1u) crash = true;
+                    else { flags |= R2P2_F_FAULT; live = false; }
                 }
             }
             if (live) {

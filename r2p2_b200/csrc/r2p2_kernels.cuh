@@ -28,9 +28,11 @@ namespace r2p2 {
 
 #ifdef R2P2_PHASE_TIMING      // profiling build only (tools/phase_timing.py): cycles per tick phase of robot 0
 __device__ unsigned long long g_phase_cycles[16];
+__device__ unsigned long long g_robot_cycles[65536 * 12];   // per robot, per phase (last launch)
 #define PT_DECL long long pt_last = clock64(); unsigned long long pt_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 #define PT(n) { const long long pt_now = clock64(); pt_acc[n] += (unsigned long long)(pt_now - pt_last); pt_last = pt_now; }
-#define PT_FLUSH(cond) if (cond) { for (int q = 0; q < 12; ++q) atomicAdd(&g_phase_cycles[q], pt_acc[q]); }
+#define PT_FLUSH(cond) if (cond) { for (int q = 0; q < 12; ++q) atomicAdd(&g_phase_cycles[q], pt_acc[q]); } \
+    if (g.sub == 0 && rb < 65536u) { for (int q = 0; q < 12; ++q) g_robot_cycles[rb * 12 + q] = pt_acc[q]; }
 #else
 #define PT_DECL
 #define PT(n)
@@ -184,13 +186,15 @@ __device__ __noinline__ int sample_exact(const uint32_t* __restrict__ wall, int 
 }
 
 // The plain restatement: every sample goes through sample_exact (kept as the in-kernel cross-check of march).
-__device__ __forceinline__ Hit march_plain(const StageView& s, double ox, double oy, double vx, double vy, double limit) {
+// (k0, x0, y0): resume the loop at sample k0, whose position is (x0, y0); the k0 samples before it ran the loop body.
+__device__ __forceinline__ Hit march_plain(const StageView& s, double ox, double oy, double vx, double vy, double limit,
+                                           int k0, double x0, double y0) {
     Hit r;
-    r.x = -1.0; r.y = -1.0; r.k = -1; r.nsamp = 0u; r.fault = false;
+    r.x = -1.0; r.y = -1.0; r.k = -1; r.nsamp = (unsigned)k0; r.fault = false;
     int kA, kB;
     norm_window(limit, kA, kB);
-    double x = ox, y = oy;
-    for (int k = 0; k < kB; ++k) {
+    double x = x0, y = y0;
+    for (int k = k0; k < kB; ++k) {
         const int st = sample_exact(s.wall, s.W, s.H, s.wpr, x, y, ox, oy, limit, k >= kA);
         if (st == kSampleFault) { r.fault = true; return r; }
         if (st == kSampleExit) return r;
@@ -200,6 +204,10 @@ __device__ __forceinline__ Hit march_plain(const StageView& s, double ox, double
         y = R2P2_ADD(y, vy);
     }
     return r;
+}
+
+__device__ __forceinline__ Hit march_plain(const StageView& s, double ox, double oy, double vx, double vy, double limit) {
+    return march_plain(s, ox, oy, vx, vy, limit, 0, ox, oy);
 }
 
 // Distance-field march.  s.dist[iy*W + ix] is the Chebyshev distance (saturated at 255) from pixel (ix, iy) to the
@@ -288,7 +296,7 @@ __device__ __forceinline__ MarchPlan make_plan(double limit, int tl) {
     return m;
 }
 
-__device__ __forceinline__ Hit team_march(const StageView& s, const Team& tm, const MarchPlan& mp, double ox, double oy,
+__device__ __forceinline__ Hit team_march_chunked(const StageView& s, const Team& tm, const MarchPlan& mp, double ox, double oy,
                                           double vx, double vy, double limit) {
     const int kA = mp.kA, kB = mp.kB;
     if (kB == 0x7fffffff) return march_plain(s, ox, oy, vx, vy, limit);     // non-finite / huge limit: uniform in the team
@@ -383,6 +391,168 @@ __device__ __forceinline__ Hit team_march(const StageView& s, const Team& tm, co
     return r;
 }
 
+// floor(v) for 0 <= v < 2^32 without an FP64 -> int conversion (F2I.F64 issues at a quarter of the DADD rate): the low
+// word of RD(v + 2^52).  ok is false outside that range and for NaN; inside it floor == trunc, i.e. Python's int().
+__device__ __forceinline__ bool fast_floor(double v, int& idx) {
+    const double t = __dadd_rd(v, 4503599627370496.0);
+    idx = __double2loint(t);
+    return __double2hiint(t) == 0x43300000;
+}
+
+// Strided team march (the one the kernels use).  TL lanes -- a power of two, an aligned segment of the warp --
+// cooperate on ONE ray; lane j owns the samples k = j, j + TL, j + 2 TL, ...  A warp issues in order, so the code is
+// laid out as the hardware should see it: one unpredicated chain of the reference's sequential additions (a predicated
+// DADD chain runs at half speed, measured), the position recorded and the bit-plane load issued whenever the lane
+// passes one of its own samples, and all the tests after the chain, when the loads have landed; NOWN own samples
+// (TL * NOWN samples of the ray) per pass, fully unrolled.  The earliest event of the ray -- wall hit, while-condition
+// false at the knife-edge sample, or a sample off the interior of the map -- is a min-reduction over the team of
+// (k << 2 | kind); in the last case the exact loop takes over from that sample.  All collectives are issued with
+// tm.sync, one mask value shared by every lane that executes this code together.
+template <int TL, int NOWN>
+__device__ __forceinline__ Hit team_march_t(const StageView& s, const Team& tm, const MarchPlan& mp, double ox, double oy,
+                                            double vx, double vy, double limit) {
+    const int kA = mp.kA, kB = mp.kB;
+    if (kB == 0x7fffffff) return march_plain(s, ox, oy, vx, vy, limit);     // non-finite / huge limit: uniform in the team
+    Hit r;
+    r.x = -1.0; r.y = -1.0; r.k = -1; r.nsamp = 0u; r.fault = false;
+    const int j = tm.j;
+    constexpr unsigned kNone = 0xffffffffu;
+    constexpr unsigned kSampleSlow = 3u;
+    unsigned key = kNone;
+    double x = ox, y = oy, hx = -1.0, hy = -1.0;
+    const int nwalk = min(TL, kB) - 1;                     // to this lane's first sample: additions of v or of 0.0
+#pragma unroll 4
+    for (int i = 0; i < nwalk; ++i) {
+        const bool on = i < j;
+        x = R2P2_ADD(x, on ? vx : 0.0);
+        y = R2P2_ADD(y, on ? vy : 0.0);
+    }
+    const bool has_window = kB > kA;                       // uniform
+    double xw = 0.0, yw = 0.0;
+    for (int k0 = j; k0 < kB; k0 += TL * NOWN) {
+        double xs[NOWN], ys[NOWN];
+        unsigned w[NOWN];
+        int ixs[NOWN];
+        bool inter[NOWN];
+#pragma unroll
+        for (int m = 0; m < NOWN; ++m) {
+            xs[m] = x; ys[m] = y;
+            int ix, iy;
+            const bool okx = fast_floor(x, ix), oky = fast_floor(y, iy);
+            inter[m] = okx & oky & ((unsigned)(ix - 1) < (unsigned)(s.W - 2)) & ((unsigned)(iy - 1) < (unsigned)(s.H - 2));
+            w[m] = s.wall[inter[m] ? (iy * s.wpr + (ix >> 5)) : 0];              // always a valid address
+            ixs[m] = ix;
+            if (m + 1 < NOWN) {
+#pragma unroll
+                for (int u = 0; u < TL; ++u) { x = R2P2_ADD(x, vx); y = R2P2_ADD(y, vy); }
+            }
+        }
+        if (has_window) {
+#pragma unroll
+            for (int m = 0; m < NOWN; ++m)
+                if (k0 + m * TL == kA) { xw = xs[m]; yw = ys[m]; }
+        }
+#pragma unroll
+        for (int m = 0; m < NOWN; ++m) {
+            const int k = k0 + m * TL;
+            const unsigned kind = !inter[m] ? kSampleSlow : (((w[m] >> (ixs[m] & 31)) & 1u) ? (unsigned)kSampleHit : 0u);
+            if ((k < kB) && kind != 0u && key == kNone) { key = ((unsigned)k << 2) | kind; hx = xs[m]; hy = ys[m]; }
+        }
+        if (k0 + TL * NOWN < kB) {                          // another pass follows
+#pragma unroll
+            for (int u = 0; u < TL; ++u) { x = R2P2_ADD(x, vx); y = R2P2_ADD(y, vy); }
+        }
+    }
+    // the knife-edge sample (at most one, k = kA = kB - 1): the reference's limit test comes before its pixel test, and
+    // after its bounds test
+    if (has_window && ((kA & (TL - 1)) == j)) {
+        const bool in_range = r2p2_norm2sq(R2P2_SUB(xw, ox), R2P2_SUB(yw, oy)) < mp.qstar;
+        const bool earlier = (key != kNone) && ((int)(key >> 2) < kA || (key & 3u) == kSampleSlow);
+        if (!in_range && !earlier) { key = ((unsigned)kA << 2) | (unsigned)kSampleExit; hx = xw; hy = yw; }
+    }
+    unsigned best = key;
+    if (TL == 32) {
+        best = __reduce_min_sync(tm.sync, key);
+    } else {
+#pragma unroll
+        for (int o = TL >> 1; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(tm.sync, best, o));
+    }
+    if (TL > 1) {
+        const int lane = (int)(threadIdx.x & 31u);
+        const int src = (best != kNone) ? (lane - j + (int)((best >> 2) & (unsigned)(TL - 1))) : lane;   // the owner of that sample
+        hx = __shfl_sync(tm.sync, hx, src);
+        hy = __shfl_sync(tm.sync, hy, src);
+    }
+    if (best == kNone) { r.nsamp = (unsigned)kB; return r; }
+    const int k = (int)(best >> 2);
+    const unsigned kind = best & 3u;
+    if (kind == kSampleSlow) return march_plain(s, ox, oy, vx, vy, limit, k, hx, hy);   // team-uniform
+    if (kind == kSampleHit) {
+        r.x = hx; r.y = hy; r.k = k; r.nsamp = (unsigned)(k + 1);
+    } else {
+        r.nsamp = (unsigned)k;          // the while-condition failed at sample k
+    }
+    return r;
+}
+
+// Team sizes the kernels use: sonar rays 1, 2, 4 or 8 lanes (the largest that gives every ray of the fan a team within
+// the group), the collision ray the whole group.  MAXTL = lanes per robot.
+constexpr int kMaxSonarTeam = 8;
+template <int MAXTL, int MAXOWN = 8>
+__device__ __forceinline__ Hit team_march(const StageView& s, const Team& tm, const MarchPlan& mp, double ox, double oy,
+                                          double vx, double vy, double limit) {
+    constexpr int O = MAXOWN;
+    switch (tm.tl) {                                       // uniform
+        case 32: if constexpr (MAXTL >= 32) return team_march_t<32, 1>(s, tm, mp, ox, oy, vx, vy, limit);
+        case 16: if constexpr (MAXTL >= 16) return team_march_t<16, 2>(s, tm, mp, ox, oy, vx, vy, limit);
+        case 8: if constexpr (MAXTL >= 8) return team_march_t<8, 4>(s, tm, mp, ox, oy, vx, vy, limit);
+        case 4: if constexpr (MAXTL >= 4) return team_march_t<4, O>(s, tm, mp, ox, oy, vx, vy, limit);
+        case 2: if constexpr (MAXTL >= 2) return team_march_t<2, O>(s, tm, mp, ox, oy, vx, vy, limit);
+        default: return team_march_t<1, O>(s, tm, mp, ox, oy, vx, vy, limit);
+    }
+}
+
+// Robot.__crashing_radius probes (r2p2/robot.py:181-186) of one lane: i = sub, sub + LPR, ... < 360, four in flight.
+// returns the lane's earliest event as 2 i (IndexError at probe i) or 2 i + 1 (wall at probe i), 0xffffffff for none;
+// the reference stops at the first wall, so an IndexError counts only if it comes before the first wall probe: after
+// a min-reduction over the lanes, an even key is a fault, an odd key a crash.
+template <int LPR>
+__device__ __forceinline__ unsigned ring_scan(const StageView& sv, int sub, double x, double y,
+                                              const double* s_crx, const double* s_cry) {
+    unsigned key = 0xffffffffu;
+    constexpr int kPer = (360 + LPR - 1) / LPR;
+#pragma unroll 1
+    for (int m0 = 0; m0 < kPer; m0 += 4) {
+        unsigned w[4], ev[4];
+        int bx[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = sub + (m0 + u) * LPR;
+            const bool ok = i < 360;
+            const int ii = ok ? i : 0;
+            const double px = R2P2_ADD(x, s_crx[ii]), py = R2P2_ADD(y, s_cry[ii]);
+            int ix, iy;
+            if (!(fast_floor(px, ix) & fast_floor(py, iy))) {   // negative / huge / NaN: Python's int() and index wrap, exactly
+                ix = dtrunc(px); iy = dtrunc(py);
+                if (ix < 0) ix += sv.W;
+                if (iy < 0) iy += sv.H;
+            }
+            const bool f = ((unsigned)ix >= (unsigned)sv.W) | ((unsigned)iy >= (unsigned)sv.H);
+            w[u] = sv.wall[f ? 0 : (iy * sv.wpr + (ix >> 5))];
+            bx[u] = ix & 31;
+            ev[u] = !ok ? 0xffffffffu : (f ? (unsigned)(2 * i) : 0xfffffffeu);   // 0xfffffffe: decided by the bit
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = sub + (m0 + u) * LPR;
+            unsigned e = ev[u];
+            if (e == 0xfffffffeu) e = ((w[u] >> bx[u]) & 1u) ? (unsigned)(2 * i + 1) : 0xffffffffu;
+            key = min(key, e);
+        }
+    }
+    return key;
+}
+
 // A ray of this limit from (x, y) that cannot reach a blocked pixel: every sample k < kB lies within k (+1 for the
 // truncation) pixels of the origin pixel, so with a distance-field value >= kB + 1 there all of them fall on unblocked
 // interior pixels and the reference loop runs exactly kB times and misses.  Only taken when the norm window is empty
@@ -422,6 +592,12 @@ struct Group {
         for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o, 32);
         return v;
     }
+    __device__ __forceinline__ unsigned min_u(unsigned v) const {
+        if (LPR == 32) return __reduce_min_sync(0xffffffffu, v);
+#pragma unroll
+        for (int o = LPR / 2; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(mask, v, o, 32));
+        return v;
+    }
     __device__ __forceinline__ unsigned bcast_u(unsigned v) const { return (LPR == 1) ? v : __shfl_sync(mask, v, 0, LPR); }
 };
 
@@ -452,16 +628,10 @@ __device__ __forceinline__ double noise_draw(const KParams& p, unsigned rb, unsi
 template <int LPR>
 __device__ __forceinline__ int crash_ring(const StageView& sv, const Group<LPR>& g, double x, double y,
                                        const double* s_crx, const double* s_cry) {
-    int first_wall = 360, first_fault = 360;
-    for (int i = g.sub; i < 360; i += LPR) {
-        bool pf = false;
-        const bool wl = px_probe(sv.wall, sv, dtrunc(R2P2_ADD(x, s_crx[i])), dtrunc(R2P2_ADD(y, s_cry[i])), pf);
-        if (pf) first_fault = min(first_fault, i);
-        if (wl) first_wall = min(first_wall, i);
-    }
-    if (LPR > 1) { first_wall = g.min_i(first_wall); first_fault = g.min_i(first_fault); }
-    if (first_fault < first_wall) return 2;
-    return first_wall < 360 ? 1 : 0;
+    unsigned key = ring_scan<LPR>(sv, g.sub, x, y, s_crx, s_cry);
+    if (LPR > 1) key = g.min_u(key);
+    if (key == 0xffffffffu) return 0;
+    return (key & 1u) ? 1 : 2;
 }
 
 // (Measured: making sincos / tanh out-of-line calls to shrink the code footprint costs more in call overhead and
@@ -616,7 +786,7 @@ struct FixedMlp<LPR, GenericNet> {
 };
 
 template <int LPR, bool SMEM_STAGE, class NET>
-__global__ void __launch_bounds__(kBlock) episode_kernel(const __grid_constant__ KParams p) {
+__global__ void __launch_bounds__(kBlock, (NET::kLayers > 0) ? 1 : 4) episode_kernel(const __grid_constant__ KParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NR = kBlock / LPR;                      // robots in flight per CTA
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw);
@@ -668,7 +838,8 @@ __global__ void __launch_bounds__(kBlock) episode_kernel(const __grid_constant__
     const int R = p.R;
     const double delta = p.delta;
     const bool tracing = p.tr_pose != nullptr;
-    const int tl = (LPR == 1 || R >= LPR) ? 1 : LPR / R;  // lanes per sonar ray (team size)
+    int tl = 1;                                           // lanes per sonar ray: the largest power of two with R teams in the group
+    while (LPR > 1 && tl * 2 * R <= LPR && tl < kMaxSonarTeam) tl *= 2;
     const int rays_per_round = LPR / tl;
     const int team_ray = g.sub / tl, team_j = g.sub % tl; // this lane's ray slot and position inside its team
     Team sonar_team;
@@ -734,7 +905,7 @@ __global__ void __launch_bounds__(kBlock) episode_kernel(const __grid_constant__
                         if (LPR == 1) {
                             h = sc.ok ? march(sv, ox, oy, vc, vs, p.L) : Hit{-1.0, -1.0, -1, 0u, true};
                         } else {
-                            h = team_march(sv, sonar_team, sonar_plan, ox, oy, vc, vs, p.L);
+                            h = team_march<(LPR < kMaxSonarTeam ? LPR : kMaxSonarTeam)>(sv, sonar_team, sonar_plan, ox, oy, vc, vs, p.L);
                         }
                         PT(9)
                         if (h.fault && have_ray) fault = true;
@@ -894,7 +1065,7 @@ __global__ void __launch_bounds__(kBlock) episode_kernel(const __grid_constant__
                 } else {                                   // the whole group is one team on the collision ray
                     Team tm;
                     tm.tl = LPR; tm.j = g.sub; tm.mask = g.mask; tm.sync = g.mask;
-                    ms = team_march(sv, tm, make_plan(climit, LPR), x, y, cc_, cs_, climit);
+                    ms = team_march_t<LPR, (LPR >= 4 ? 32 / LPR : 8)>(sv, tm, make_plan(climit, LPR), x, y, cc_, cs_, climit);
                 }
                 ns_coll += ms.nsamp;
                 if (ms.fault) { flags |= R2P2_F_FAULT; break; }

@@ -30,3 +30,16 @@ print("kernel ms %.3f; robot 0: %d ticks" % (ev.sim.last_run_ms(), ev.sim.state(
 for i, n in enumerate(names):
     if n != "-": print("%-36s %9.0f cycles/tick  %5.1f%%" % (n, out[i] / a.ticks, 100.0 * out[i] / tot))
 print("total %.0f cycles/tick" % (tot / a.ticks))
+
+import numpy as np
+n = min(w["P"], 65536)
+rc = np.zeros((n, 12), dtype=np.uint64)
+L.r2p2_debug_robot_cycles(rc.ctypes.data_as(C.c_void_p), n)
+rc = rc.astype(np.float64) / a.ticks
+tot_r = rc.sum(1)
+st = ev.sim.state()
+order = np.argsort(tot_r)
+print("per-robot cycles/tick: min %.0f  median %.0f  p90 %.0f  max %.0f" % (tot_r.min(), np.median(tot_r), np.percentile(tot_r, 90), tot_r.max()))
+print("phase means (all robots):", " ".join("%d:%.0f" % (i, rc[:, i].mean()) for i in range(12)))
+for r in list(order[-5:]) + list(order[:2]):
+    print("robot %5d total %.0f ticks %d coll %d flags %x |" % (r, tot_r[r], st["ticks"][r], st["ncollide"][r], st["flags"][r]), " ".join("%d:%.0f" % (i, rc[r, i]) for i in range(12)))

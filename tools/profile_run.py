@@ -9,10 +9,11 @@ from r2p2_b200.evaluator import PopulationEvaluator
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--workload", default="B"); ap.add_argument("--lpr", type=int, default=0); ap.add_argument("--smem", type=int, default=-1)
-ap.add_argument("--iters", type=int, default=3); ap.add_argument("--ticks", type=int, default=0)
+ap.add_argument("--iters", type=int, default=3); ap.add_argument("--pop", type=int, default=0); ap.add_argument("--ticks", type=int, default=0)
 a = ap.parse_args()
 w = dict(bench.WORKLOADS[a.workload])
 if a.ticks: w["T"] = a.ticks
+if a.pop: w["P"] = a.pop
 rob = bench.ROBOTS[w["robot"]]
 px, py, pt = bench.start_poses(w, w["P"], 4321)
 ev = PopulationEvaluator(bench.load_stage(w["stage"]), sonar_range=rob["sonar_range"], radius=rob["radius"], max_speed=rob["max_speed"],
