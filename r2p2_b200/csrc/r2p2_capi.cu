@@ -185,11 +185,13 @@ int upload_crxy(r2p2_handle h) {
     return R2P2_OK;
 }
 
+// occ_out != NULL: only report how many CTAs of the kernel this configuration selects fit on an SM (no launch)
 template <int LPR, class KERN>
-int launch_kernel(r2p2_handle h, KERN kern, const KParams& kp, size_t smem) {
+int launch_kernel(r2p2_handle h, KERN kern, const KParams& kp, size_t smem, int* occ_out) {
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kBlock, smem));
+    if (occ_out) { *occ_out = occ; return R2P2_OK; }
     if (occ < 1) return fail(h, R2P2_E_LIMIT, "episode kernel does not fit on an SM (smem %zu bytes)", smem);
     const int robots_per_cta = kBlock / LPR;
     long long ctas = ((long long)kp.P + robots_per_cta - 1) / robots_per_cta;
@@ -205,16 +207,16 @@ int launch_kernel(r2p2_handle h, KERN kern, const KParams& kp, size_t smem) {
 }
 
 template <int LPR, bool SMEM, class NET>
-int launch_episode(r2p2_handle h, const KParams& kp, size_t smem) {
+int launch_episode(r2p2_handle h, const KParams& kp, size_t smem, int* occ_out) {
     // 2..16 lanes per robot: the warp-synchronous kernel (r2p2_kernel_ws.cuh), same results, one instruction stream per
     // warp.  R2P2_WS=0 in the environment selects the per-group kernel for A/B measurements.
     if constexpr (LPR >= 2 && LPR <= 16 && !SMEM) {
         static const bool ws = [] { const char* e = getenv("R2P2_WS"); return !(e && e[0] == '0'); }();
         // (a sonar limit without a norm window sends whole groups through the plain loop, which the lock-step kernel
         // cannot mix with groups that have stopped)
-        if (ws && kp.L > -1.0 && kp.L < 30000.0) return launch_kernel<LPR>(h, episode_kernel_ws<LPR, NET>, kp, smem);
+        if (ws && kp.L > -1.0 && kp.L < 30000.0) return launch_kernel<LPR>(h, episode_kernel_ws<LPR, NET>, kp, smem, occ_out);
     }
-    return launch_kernel<LPR>(h, episode_kernel<LPR, SMEM, NET>, kp, smem);
+    return launch_kernel<LPR>(h, episode_kernel<LPR, SMEM, NET>, kp, smem, occ_out);
 }
 
 template <class NET>
@@ -226,7 +228,7 @@ bool net_matches(const KParams& kp) {
 }
 
 template <int LPR>
-int launch_episode_s(r2p2_handle h, KParams& kp, bool smem_stage) {
+int launch_episode_s(r2p2_handle h, KParams& kp, bool smem_stage, int* occ_out) {
     // the reference's shipped network shapes have fixed-shape instances (weights in registers; chosen unless the shared-memory
     // stage copy is requested, which keeps the run-time-shaped path reachable for tests); LPR == 1 would need
     // the whole net in one thread's registers, so it stays on the generic path
@@ -236,24 +238,44 @@ int launch_episode_s(r2p2_handle h, KParams& kp, bool smem_stage) {
     if constexpr (LPR >= 16) if (!smem_stage) {
         if (net_matches<NetNeuro>(kp)) {
             kp.w_in_smem = 0;
-            return launch_episode<LPR, false, NetNeuro>(h, kp, episode_smem_bytes(LPR, false, kp.plane_bytes, kp.has50, kp.maxw, 0, kp.G));
+            return launch_episode<LPR, false, NetNeuro>(h, kp, episode_smem_bytes(LPR, false, kp.plane_bytes, kp.has50, kp.maxw, 0, kp.G), occ_out);
         }
         if (net_matches<NetSimple>(kp)) {
             kp.w_in_smem = 0;
-            return launch_episode<LPR, false, NetSimple>(h, kp, episode_smem_bytes(LPR, false, kp.plane_bytes, kp.has50, kp.maxw, 0, kp.G));
+            return launch_episode<LPR, false, NetSimple>(h, kp, episode_smem_bytes(LPR, false, kp.plane_bytes, kp.has50, kp.maxw, 0, kp.G), occ_out);
         }
     }
     const size_t smem = episode_smem_bytes(LPR, smem_stage, kp.plane_bytes, kp.has50, kp.maxw, kp.w_in_smem, kp.G);
-    return smem_stage ? launch_episode<LPR, true, GenericNet>(h, kp, smem) : launch_episode<LPR, false, GenericNet>(h, kp, smem);
+    return smem_stage ? launch_episode<LPR, true, GenericNet>(h, kp, smem, occ_out) : launch_episode<LPR, false, GenericNet>(h, kp, smem, occ_out);
 }
 
-int choose_lpr(const r2p2_handle h) {
+// genomes of the robots in flight live in shared memory when the group mapping leaves room for them
+int w_in_smem_for(int lpr, int G) { return (lpr > 1 && (size_t)(kBlock / lpr) * G * 8 <= 48 * 1024) ? 1 : 0; }
+
+int dispatch_episode(r2p2_handle h, KParams& kp, int lpr, bool smem_stage, int* occ_out) {
+    kp.w_in_smem = w_in_smem_for(lpr, kp.G);
+    switch (lpr) {
+        case 1: return launch_episode_s<1>(h, kp, smem_stage, occ_out);
+        case 2: return launch_episode_s<2>(h, kp, smem_stage, occ_out);
+        case 4: return launch_episode_s<4>(h, kp, smem_stage, occ_out);
+        case 8: return launch_episode_s<8>(h, kp, smem_stage, occ_out);
+        case 16: return launch_episode_s<16>(h, kp, smem_stage, occ_out);
+        default: return launch_episode_s<32>(h, kp, smem_stage, occ_out);
+    }
+}
+
+// Widest group whose whole population is resident at once, judged by the occupancy of the kernel instance that mapping
+// selects (the register-weight instances hold 2 CTAs per SM, the run-time-shaped ones 4).  Measured on B200:
+// P=1024 -> 32 lanes, P=2048 -> 16, P=8192 -> 8, P=65536 -> 1.
+int choose_lpr(r2p2_handle h, const KParams& kp) {
     if (h->lpr_req) return h->lpr_req;
-    // Widest group whose whole population is resident at once (the kernel holds ~128 registers per thread, so an SM
-    // keeps 512 threads in flight).  Measured on B200: P=1024 -> 32 lanes, P=8192 -> 8, P=65536 -> 1.
-    const long long resident = (long long)h->sm_count * 512;
-    for (int lpr = 32; lpr > 1; lpr >>= 1)
-        if ((long long)h->P * lpr <= resident) return lpr;
+    for (int lpr = 32; lpr > 1; lpr >>= 1) {
+        KParams k2 = kp;
+        int occ = 0;
+        if (dispatch_episode(h, k2, lpr, false, &occ) != R2P2_OK) continue;
+        const long long ctas = ((long long)h->P * lpr + kBlock - 1) / kBlock;
+        if (ctas <= (long long)occ * h->sm_count) return lpr;
+    }
     // many rays per robot (config E: 32 rays, 262144 robots): two lanes per robot split the ray fan (1.42 s vs 2.24 s)
     return h->R >= 16 ? 2 : 1;
 }
@@ -516,7 +538,6 @@ int r2p2_run(r2p2_handle h, int32_t T, double delta, double delta_ctrl, int32_t 
     if (h->trace && (T > h->trace_T)) return fail(h, R2P2_E_ARG, "trace enabled for at most %d ticks per run", h->trace_T);
     CK(cudaSetDevice(h->device));
 
-    const int lpr = choose_lpr(h);
     KParams kp;
     memset(&kp, 0, sizeof kp);
     kp.W = h->W; kp.H = h->H; kp.wpr = h->wpr; kp.has50 = h->has50;
@@ -549,7 +570,9 @@ int r2p2_run(r2p2_handle h, int32_t T, double delta, double delta_ctrl, int32_t 
     kp.noise_mode = h->noise_mode; kp.noise_len = h->noise_len; kp.noise_seed = h->noise_seed; kp.noise_stream = h->d_noise;
     if (h->noise_mode == 1 && h->noise_P != h->P) return fail(h, R2P2_E_ARG, "noise stream was uploaded for %d robots, population is %d", h->noise_P, h->P);
     kp.work_counter = h->d_work;
+    kp.genomes = h->d_genomes;
 
+    const int lpr = choose_lpr(h, kp);
     if (lpr == 1) {
         if (!h->genomes_t_valid) {
             dim3 grid((h->P + 31) / 32, (h->G + 31) / 32), block(32, 8);
@@ -576,25 +599,13 @@ int r2p2_run(r2p2_handle h, int32_t T, double delta, double delta_ctrl, int32_t 
         kp.tr_nsamp = h->tr_nsamp; kp.tr_ncoll = h->tr_ncoll;
     }
 
-    // genomes of the robots in flight live in shared memory when the group mapping leaves room for them
-    kp.w_in_smem = (lpr > 1 && (size_t)(kBlock / lpr) * h->G * 8 <= 48 * 1024) ? 1 : 0;
-    bool smem_stage;
-    const size_t with_stage = episode_smem_bytes(lpr, true, kp.plane_bytes, kp.has50, kp.maxw, kp.w_in_smem, kp.G);
-    if (h->smem_req == 1) smem_stage = true;
-    else if (h->smem_req == 0) smem_stage = false;
-    else smem_stage = false;   // measured on B200: L1-cached global reads of the planes are as fast as the shared copy
-    if (smem_stage && with_stage > h->smem_optin) {
-        if (h->smem_req == 1) return fail(h, R2P2_E_LIMIT, "stage planes (%zu bytes with tables) exceed shared memory", with_stage);
-        smem_stage = false;
+    kp.w_in_smem = w_in_smem_for(lpr, kp.G);
+    bool smem_stage = h->smem_req == 1;   // default off: measured on B200, L1-cached global reads of the planes are as fast as the shared copy
+    if (smem_stage) {
+        const size_t with_stage = episode_smem_bytes(lpr, true, kp.plane_bytes, kp.has50, kp.maxw, kp.w_in_smem, kp.G);
+        if (with_stage > h->smem_optin) return fail(h, R2P2_E_LIMIT, "stage planes (%zu bytes with tables) exceed shared memory", with_stage);
     }
-    switch (lpr) {
-        case 1: return launch_episode_s<1>(h, kp, smem_stage);
-        case 2: return launch_episode_s<2>(h, kp, smem_stage);
-        case 4: return launch_episode_s<4>(h, kp, smem_stage);
-        case 8: return launch_episode_s<8>(h, kp, smem_stage);
-        case 16: return launch_episode_s<16>(h, kp, smem_stage);
-        default: return launch_episode_s<32>(h, kp, smem_stage);
-    }
+    return dispatch_episode(h, kp, lpr, smem_stage, nullptr);
 }
 
 int r2p2_sync(r2p2_handle h) {
