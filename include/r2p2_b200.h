@@ -160,6 +160,43 @@ int r2p2_set_trace(r2p2_handle h, int32_t enable, int32_t T_max);
  * tested per ray; ncoll [T][P] collide() calls in the tick.  Any pointer may be NULL. */
 int r2p2_read_trace(r2p2_handle h, int32_t T, double* pose, double* dst, int32_t* hitk, int32_t* hitpx,
                     uint32_t* nsamp, uint32_t* ncoll);
+/* The collide() calls of each tick, for the collision lines of the robot log (Robot.collide, r2p2/robot.py:170-179,
+ * called from __update_position, r2p2/robot.py:211-253): cinfo [T][P][4] = code, wx, wy, b.
+ * code bit 0: wall collision at the proposed position (wx, wy) (robot.py:212); bits 1-4: map-border case 1..8 in
+ * the order of robot.py:222-247 -- spot (W, b), (W, H), (W, 0), (0, b), (0, H), (0, 0), (b, H), (b, 0); bit 5: the
+ * crash-radius / level-50 test fired and the robot went back to its last position, which is the spot (robot.py:249-252). */
+int r2p2_read_trace_collisions(r2p2_handle h, int32_t T, double* cinfo);
+
+/* ---- generation step of the EA on the device -------------------------------------------------- */
+/* The reference leaves the EA to the user (r2p2/evolution.py:58-68 "TODO: Implement your EA here"; ga.py.gpg is
+ * encrypted) and fixes the contract: generate_float candidates uniform in [min_gen, max_gen] (evolution.py:18-22),
+ * evaluator(candidates) -> fitness, higher is better (evolution.py:29-52).  These calls keep population, fitness
+ * and breeding (inspyred ec.GA operators: tournament selection, uniform crossover, Gaussian mutation clipped to
+ * the range, elitism) in device memory.  All randomness is Philox4x32-10 of (seed, generation, individual, gene),
+ * so every GPU of a multi-GPU run breeds the same next generation from the same fitness vector. */
+/* Allocate a population of P individuals x G genes and draw generation 0 (generate_float). */
+int r2p2_ga_create(r2p2_handle h, int32_t P, int32_t G, uint64_t seed, double min_gen, double max_gen);
+/* tournament size 1..4, rates in [0, 1], elites 0..64.  Defaults: 2, 0.9, 0.05, 0.1, 1. */
+int r2p2_ga_set_operators(r2p2_handle h, int32_t tournament, double crossover_rate, double mutation_rate,
+                          double mutation_sigma, int32_t elites);
+/* Device pointers of the current generation [P][G] and of its fitness vector [P] (target of the caller's
+ * all-gather in a multi-GPU run). */
+int r2p2_ga_population_device(r2p2_handle h, double** d_population);
+int r2p2_ga_fitness_device(r2p2_handle h, double** d_fitness);
+/* Host -> device fitness of individuals [first, first + count) (fitness computed elsewhere). */
+int r2p2_ga_write_fitness(r2p2_handle h, const double* fitness, int32_t first, int32_t count);
+/* Current generation and its fitness to the host; either pointer may be NULL. */
+int r2p2_ga_read(r2p2_handle h, double* population, double* fitness);
+/* evaluate_ann for individuals [first, first + count) of the current generation: they become this handle's
+ * population, start from the pose / time budget of the last r2p2_reset(n = 1), run T ticks (r2p2_run), and their
+ * fitness lands in the GA's fitness vector.  No host round trip. */
+int r2p2_ga_evaluate(r2p2_handle h, int32_t first, int32_t count, int32_t T, double delta, double delta_ctrl, int32_t evolve);
+/* Next generation from the current one and its fitness vector; the generation counter advances. */
+int r2p2_ga_breed(r2p2_handle h);
+/* Best individual of the generation last bred from: index, fitness, genome [G]; any pointer may be NULL
+ * (the history_*.log record of evolution.py:45-47). */
+int r2p2_ga_best(r2p2_handle h, int32_t* index, double* fitness, double* genome);
+int r2p2_ga_generation(r2p2_handle h, uint32_t* generation);
 
 /* ---- raw ray-caster (utils.search_edge_in_angle_with_limit, r2p2/utils.py:420-432) --------------- */
 /* n independent rays against the current stage; host arrays in, host arrays out.

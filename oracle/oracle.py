@@ -72,7 +72,7 @@ class Oracle:
         L.orc_ray.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_double,
                               C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_uint32)]
         L.orc_run.restype = C.c_int
-        L.orc_run.argtypes = [C.POINTER(_Cfg), C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32] + [C.c_void_p] * 6
+        L.orc_run.argtypes = [C.POINTER(_Cfg), C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32] + [C.c_void_p] * 7
 
     @staticmethod
     def _env(env):
@@ -126,13 +126,14 @@ class Oracle:
             st[f] = v
         st["time"] = cfg.time_budget
         out = {}
-        ptrs = [None] * 6
+        ptrs = [None] * 7
         if trace:
             R = len(rays)
             out["pose"] = np.zeros((T, P, 5)); out["dst"] = np.zeros((T, P, R))
             out["hitk"] = np.full((T, P, R), -1, dtype=np.int32); out["hitpx"] = np.full((T, P, R, 2), -1, dtype=np.int32)
             out["nsamp"] = np.zeros((T, P, R), dtype=np.uint32); out["ncoll"] = np.zeros((T, P), dtype=np.uint32)
-            ptrs = [out[k].ctypes.data for k in ("pose", "dst", "hitk", "hitpx", "nsamp", "ncoll")]
+            out["cinfo"] = np.zeros((T, P, 4))
+            ptrs = [out[k].ctypes.data for k in ("pose", "dst", "hitk", "hitpx", "nsamp", "ncoll", "cinfo")]
         rc = self.lib.orc_run(C.byref(cfg), st.ctypes.data, genomes.ctypes.data, P, int(T), int(threads), *ptrs)
         if rc != 0:
             raise ValueError("oracle: unsupported configuration")

@@ -160,6 +160,7 @@ typedef struct {             /* optional per-tick trace rows for one robot (all 
     int32_t* hitk;           /* [R]  hit step or -1 */
     int32_t* hitpx;          /* [R][2] hit pixel (int(x), int(y)) or -1,-1 */
     uint32_t* nsamp;         /* [R]  samples tested on the ray */
+    double* cinfo;       /* [4]: collide() calls of the tick: code, wall spot x, y, border coordinate (include/r2p2_b200.h) */
 } orc_trace_row;
 
 /* robot.py:287-318 */
@@ -263,7 +264,11 @@ static int orc_crashing(const orc_cfg* c, orc_robot* rb, const double* crx, cons
 }
 
 /* robot.py:188-255 */
-static int orc_move(const orc_cfg* c, orc_robot* rb, const double* crx, const double* cry) {
+static int orc_move(const orc_cfg* c, orc_robot* rb, const double* crx, const double* cry, double* ci) {
+    double ci_local[4];
+    if (!ci) ci = ci_local;
+    ci[0] = ci[1] = ci[2] = ci[3] = 0.0;
+    unsigned code = 0;
     const double W = (double)c->W, H = (double)c->H, rad = c->radius, delta = c->delta;
     int ok = 1;
     const double hr = rb->theta * ORC_RAD;
@@ -287,6 +292,7 @@ static int orc_move(const orc_cfg* c, orc_robot* rb, const double* crx, const do
         if (!orc_pyint(cx, &ix) || !orc_pyint(cy, &iy) || !orc_px(c, ix, iy, &v)) { rb->flags |= ORC_F_FAULT; return 0; }
         if (v == 0) {
             orc_collide(rb);
+            code |= 1u; ci[1] = rb->x; ci[2] = rb->y;
             if (ms.x - rb->x > 0) rb->x = ms.x + (rad + 1);
             else if (ms.x - rb->x < 0) rb->x = ms.x - (rad + 1);
             if (ms.y - rb->y > 0) rb->y = ms.y + (rad + 1);
@@ -294,20 +300,25 @@ static int orc_move(const orc_cfg* c, orc_robot* rb, const double* crx, const do
         }
     }
     if (rb->x + rad >= W) {
-        if (rb->y + rad < H && rb->y - rad >= 0) orc_collide(rb);
-        else if (rb->y + rad >= H) { orc_collide(rb); rb->y = H - 1 - rad; }
-        else { orc_collide(rb); rb->y = rad; }
+        ci[3] = rb->y;
+        if (rb->y + rad < H && rb->y - rad >= 0) { orc_collide(rb); code |= 1u << 1; }
+        else if (rb->y + rad >= H) { orc_collide(rb); code |= 2u << 1; rb->y = H - 1 - rad; }
+        else { orc_collide(rb); code |= 3u << 1; rb->y = rad; }
         rb->x = W - 1;
     } else if (rb->x - rad < 0) {
-        if (rb->y + rad < H && rb->y - rad >= 0) orc_collide(rb);
-        else if (rb->y + rad >= H) { orc_collide(rb); rb->y = H - 1 - rad; }
-        else { orc_collide(rb); rb->y = rad; }
+        ci[3] = rb->y;
+        if (rb->y + rad < H && rb->y - rad >= 0) { orc_collide(rb); code |= 4u << 1; }
+        else if (rb->y + rad >= H) { orc_collide(rb); code |= 5u << 1; rb->y = H - 1 - rad; }
+        else { orc_collide(rb); code |= 6u << 1; rb->y = rad; }
         rb->x = 0;
     } else if (rb->y + rad > H) {
-        orc_collide(rb); rb->y = H - 1 - rad;
+        ci[3] = rb->x;
+        orc_collide(rb); code |= 7u << 1; rb->y = H - 1 - rad;
     } else if (rb->y - rad < 0) {
-        orc_collide(rb); rb->y = rad;
+        ci[3] = rb->x;
+        orc_collide(rb); code |= 8u << 1; rb->y = rad;
     }
+    ci[0] = (double)code;
     {
         int64_t ix, iy; int32_t v;
         rb->npixel++;
@@ -317,7 +328,7 @@ static int orc_move(const orc_cfg* c, orc_robot* rb, const double* crx, const do
             crash = orc_crashing(c, rb, crx, cry);
             if (crash < 0) { rb->flags |= ORC_F_FAULT; return 0; }
         }
-        if (crash) { rb->x = rb->last_x; rb->y = rb->last_y; orc_collide(rb); }
+        if (crash) { rb->x = rb->last_x; rb->y = rb->last_y; orc_collide(rb); code |= 1u << 5; ci[0] = (double)code; }
         else { rb->last_x = rb->x; rb->last_y = rb->y; }
     }
     return 1;
@@ -333,7 +344,7 @@ static int orc_tick(const orc_cfg* c, orc_robot* rb, const double* genome, const
     if (fabs(v) > c->max_speed) v = v / fabs(v) * c->max_speed;
     rb->speed = v; rb->omega = w;
     rb->theta = rb->theta + rb->omega * c->delta;
-    if (!orc_move(c, rb, crx, cry)) return 0;
+    if (!orc_move(c, rb, crx, cry, tr ? tr->cinfo : NULL)) return 0;
     rb->ticks++;
     return 1;
 }
@@ -362,7 +373,7 @@ void orc_init_robot(orc_robot* rb, double x, double y, double theta, double time
 
 typedef struct {
     const orc_cfg* c; orc_robot* robots; const double* genomes; int32_t p0, p1, P, T;
-    double* tr_pose; double* tr_dst; int32_t* tr_hitk; int32_t* tr_hitpx; uint32_t* tr_nsamp; uint32_t* tr_ncoll;
+    double* tr_pose; double* tr_dst; int32_t* tr_hitk; int32_t* tr_hitpx; uint32_t* tr_nsamp; uint32_t* tr_ncoll; double* tr_cinfo;
 } orc_job;
 
 static void* orc_worker(void* arg) {
@@ -385,6 +396,7 @@ static void* orc_worker(void* arg) {
             tr.hitk = j->tr_hitk ? j->tr_hitk + row * R : NULL;
             tr.hitpx = j->tr_hitpx ? j->tr_hitpx + row * R * 2 : NULL;
             tr.nsamp = j->tr_nsamp ? j->tr_nsamp + row * R : NULL;
+            tr.cinfo = j->tr_cinfo ? j->tr_cinfo + row * 4 : NULL;
             const uint32_t ncoll0 = rb->ncollide;
             int alive = 0;
             if (!(rb->flags & (ORC_F_FAULT | ORC_F_DONE))) {
@@ -405,7 +417,7 @@ static void* orc_worker(void* arg) {
 
 /* Run robots[0..P) for T ticks.  Trace pointers may be NULL; layouts [T][P][...].  n_threads >= 1. */
 int orc_run(const orc_cfg* c, orc_robot* robots, const double* genomes, int32_t P, int32_t T, int32_t n_threads,
-            double* tr_pose, double* tr_dst, int32_t* tr_hitk, int32_t* tr_hitpx, uint32_t* tr_nsamp, uint32_t* tr_ncoll) {
+            double* tr_pose, double* tr_dst, int32_t* tr_hitk, int32_t* tr_hitpx, uint32_t* tr_nsamp, uint32_t* tr_ncoll, double* tr_cinfo) {
     if (c->R > ORC_MAX_RAYS || c->n_layers > ORC_MAX_LAYERS) return -1;
     for (int l = 0; l < c->n_layers; ++l) if (c->layers[l] > ORC_MAX_WIDTH) return -1;
     if (n_threads < 1) n_threads = 1;
@@ -417,7 +429,7 @@ int orc_run(const orc_cfg* c, orc_robot* robots, const double* genomes, int32_t 
         j->c = c; j->robots = robots; j->genomes = genomes; j->P = P; j->T = T;
         j->p0 = (int32_t)((int64_t)P * i / n_threads); j->p1 = (int32_t)((int64_t)P * (i + 1) / n_threads);
         j->tr_pose = tr_pose; j->tr_dst = tr_dst; j->tr_hitk = tr_hitk; j->tr_hitpx = tr_hitpx;
-        j->tr_nsamp = tr_nsamp; j->tr_ncoll = tr_ncoll;
+        j->tr_nsamp = tr_nsamp; j->tr_ncoll = tr_ncoll; j->tr_cinfo = tr_cinfo;
         if (n_threads == 1) orc_worker(j); else pthread_create(&th[i], NULL, orc_worker, j);
     }
     if (n_threads > 1) for (int i = 0; i < n_threads; ++i) pthread_join(th[i], NULL);

@@ -62,6 +62,17 @@ _SIGS = {
     "r2p2_launch_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "r2p2_set_trace": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32]),
     "r2p2_read_trace": (C.c_int, [C.c_void_p, C.c_int32] + [C.c_void_p] * 6),
+    "r2p2_read_trace_collisions": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
+    "r2p2_ga_create": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_uint64, C.c_double, C.c_double]),
+    "r2p2_ga_set_operators": (C.c_int, [C.c_void_p, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_int32]),
+    "r2p2_ga_population_device": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "r2p2_ga_fitness_device": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "r2p2_ga_write_fitness": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
+    "r2p2_ga_read": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "r2p2_ga_evaluate": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_int32]),
+    "r2p2_ga_breed": (C.c_int, [C.c_void_p]),
+    "r2p2_ga_best": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_double), C.c_void_p]),
+    "r2p2_ga_generation": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint32)]),
     "r2p2_cast_rays": (C.c_int, [C.c_void_p, C.c_int32] + [C.c_void_p] * 9),
     "r2p2_cast_rays_plain": (C.c_int, [C.c_void_p, C.c_int32] + [C.c_void_p] * 9),
 }

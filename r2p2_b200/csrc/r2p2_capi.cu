@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "r2p2_kernel_ws.cuh"
+#include "r2p2_ga.cuh"
 
 using namespace r2p2;
 
@@ -73,9 +74,20 @@ struct r2p2_sim {
     // trace
     bool trace = false;
     int trace_T = 0, trace_P = 0, trace_R = 0;
-    double *tr_pose = nullptr, *tr_dst = nullptr;
+    double *tr_pose = nullptr, *tr_dst = nullptr, *tr_cinfo = nullptr;
     int32_t *tr_hitk = nullptr, *tr_hitpx = nullptr;
     uint32_t *tr_nsamp = nullptr, *tr_ncoll = nullptr;
+    // start pose / time budget of the last r2p2_reset with n == 1 (re-applied by r2p2_ga_evaluate)
+    bool have_pose1 = false;
+    double rx0 = 0, ry0 = 0, rt0 = 0, rbudget = 0;
+    // on-device GA (r2p2_ga.cuh)
+    int ga_P = 0, ga_G = 0, ga_cur = 0, ga_tournament = 2, ga_elites = 1;
+    double ga_cx = 0.9, ga_mut = 0.05, ga_sigma = 0.1, ga_min = -1.0, ga_max = 1.0;
+    unsigned long long ga_seed = 0;
+    uint32_t ga_generation = 0;
+    double* d_ga_pop[2] = {nullptr, nullptr};
+    double* d_ga_fit = nullptr;
+    int* d_ga_elite = nullptr;
     // scheduling / counters
     unsigned int* d_work = nullptr;
     unsigned long long* d_cnt3 = nullptr;
@@ -133,8 +145,8 @@ int ensure_genomes(r2p2_handle h, int P, int G) {
 }
 
 void free_trace(r2p2_handle h) {
-    cudaFree(h->tr_pose); cudaFree(h->tr_dst); cudaFree(h->tr_hitk); cudaFree(h->tr_hitpx); cudaFree(h->tr_nsamp); cudaFree(h->tr_ncoll);
-    h->tr_pose = h->tr_dst = nullptr; h->tr_hitk = h->tr_hitpx = nullptr; h->tr_nsamp = h->tr_ncoll = nullptr;
+    cudaFree(h->tr_pose); cudaFree(h->tr_dst); cudaFree(h->tr_hitk); cudaFree(h->tr_hitpx); cudaFree(h->tr_nsamp); cudaFree(h->tr_ncoll); cudaFree(h->tr_cinfo);
+    h->tr_pose = h->tr_dst = h->tr_cinfo = nullptr; h->tr_hitk = h->tr_hitpx = nullptr; h->tr_nsamp = h->tr_ncoll = nullptr;
     h->trace_T = h->trace_P = h->trace_R = 0;
 }
 
@@ -332,7 +344,8 @@ int r2p2_destroy(r2p2_handle h) {
     StateArrays& s = h->st;
     void* ptrs[] = {s.x, s.y, s.theta, s.speed, s.omega, s.last_x, s.last_y, s.dist, s.odom_x, s.odom_y, s.origin_x, s.origin_y,
                     s.time, s.fitness, s.flags, s.ncollide, s.ticks, s.ndraws, s.nsamp_sonar, s.nsamp_coll, h->d_noise, h->d_x0, h->d_y0, h->d_t0,
-                    h->d_wall, h->d_l50, h->d_dist, h->d_crxy, h->d_sincostab, h->d_genomes, h->d_genomes_t, h->d_work, h->d_cnt3};
+                    h->d_wall, h->d_l50, h->d_dist, h->d_crxy, h->d_sincostab, h->d_genomes, h->d_genomes_t, h->d_work, h->d_cnt3,
+                    h->d_ga_pop[0], h->d_ga_pop[1], h->d_ga_fit, h->d_ga_elite};
     for (void* p : ptrs) cudaFree(p);
     free_trace(h);
     cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
@@ -514,6 +527,7 @@ int r2p2_reset(r2p2_handle h, const double* x0, const double* y0, const double* 
     CK(cudaGetLastError());
     if (n > 1) CK(cudaStreamSynchronize(h->stream));   // host arrays may be pageable and reused by the caller
     h->have_reset = true;
+    if (n == 1) { h->have_pose1 = true; h->rx0 = x0[0]; h->ry0 = y0[0]; h->rt0 = theta0[0]; h->rbudget = time_budget; }
     return R2P2_OK;
 }
 
@@ -595,8 +609,9 @@ int r2p2_run(r2p2_handle h, int32_t T, double delta, double delta_ctrl, int32_t 
         CK(cudaMemsetAsync(h->tr_hitpx, 0xff, rows * h->R * 2 * sizeof(int32_t), h->stream));
         CK(cudaMemsetAsync(h->tr_nsamp, 0, rows * h->R * sizeof(uint32_t), h->stream));
         CK(cudaMemsetAsync(h->tr_ncoll, 0, rows * sizeof(uint32_t), h->stream));
+        CK(cudaMemsetAsync(h->tr_cinfo, 0, rows * 4 * sizeof(double), h->stream));
         kp.tr_pose = h->tr_pose; kp.tr_dst = h->tr_dst; kp.tr_hitk = h->tr_hitk; kp.tr_hitpx = h->tr_hitpx;
-        kp.tr_nsamp = h->tr_nsamp; kp.tr_ncoll = h->tr_ncoll;
+        kp.tr_nsamp = h->tr_nsamp; kp.tr_ncoll = h->tr_ncoll; kp.tr_cinfo = h->tr_cinfo;
     }
 
     kp.w_in_smem = w_in_smem_for(lpr, kp.G);
@@ -695,7 +710,7 @@ int r2p2_set_trace(r2p2_handle h, int32_t enable, int32_t T_max) {
     const size_t rows = (size_t)T_max * h->P;
     CK(dalloc(&h->tr_pose, rows * 5)); CK(dalloc(&h->tr_dst, rows * h->R));
     CK(dalloc(&h->tr_hitk, rows * h->R)); CK(dalloc(&h->tr_hitpx, rows * h->R * 2));
-    CK(dalloc(&h->tr_nsamp, rows * h->R)); CK(dalloc(&h->tr_ncoll, rows));
+    CK(dalloc(&h->tr_nsamp, rows * h->R)); CK(dalloc(&h->tr_ncoll, rows)); CK(dalloc(&h->tr_cinfo, rows * 4));
     h->trace = true; h->trace_T = T_max; h->trace_P = h->P; h->trace_R = h->R;
     return R2P2_OK;
 }
@@ -713,6 +728,139 @@ int r2p2_read_trace(r2p2_handle h, int32_t T, double* pose, double* dst, int32_t
     if (nsamp) CK(cudaMemcpyAsync(nsamp, h->tr_nsamp, rows * R * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
     if (ncoll) CK(cudaMemcpyAsync(ncoll, h->tr_ncoll, rows * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    return R2P2_OK;
+}
+
+int r2p2_read_trace_collisions(r2p2_handle h, int32_t T, double* cinfo) {
+    if (!h) return R2P2_E_ARG;
+    if (!h->trace) return fail(h, R2P2_E_ARG, "trace not enabled");
+    if (T < 0 || T > h->trace_T) return fail(h, R2P2_E_ARG, "T out of range");
+    if (!cinfo) return fail(h, R2P2_E_ARG, "cinfo is NULL");
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync(cinfo, h->tr_cinfo, (size_t)T * h->trace_P * 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return R2P2_OK;
+}
+
+/* ---- on-device GA (r2p2_ga.cuh) --------------------------------------------------------------- */
+static int ga_ready(r2p2_handle h) {
+    if (!h) return R2P2_E_ARG;
+    if (!h->d_ga_pop[0]) return fail(h, R2P2_E_ARG, "no GA population (call r2p2_ga_create)");
+    return R2P2_OK;
+}
+
+int r2p2_ga_create(r2p2_handle h, int32_t P, int32_t G, uint64_t seed, double min_gen, double max_gen) {
+    if (!h) return R2P2_E_ARG;
+    if (P < 2 || G < 1) return fail(h, R2P2_E_ARG, "GA: need P >= 2, G >= 1");
+    if (!(min_gen < max_gen)) return fail(h, R2P2_E_ARG, "GA: need min_gen < max_gen");
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < 2; ++i) CK(dalloc(&h->d_ga_pop[i], (size_t)P * G));
+    CK(dalloc(&h->d_ga_fit, (size_t)P));
+    CK(dalloc(&h->d_ga_elite, (size_t)kGaMaxElites));
+    CK(cudaMemsetAsync(h->d_ga_fit, 0, (size_t)P * sizeof(double), h->stream));
+    h->ga_P = P; h->ga_G = G; h->ga_seed = seed; h->ga_min = min_gen; h->ga_max = max_gen; h->ga_cur = 0; h->ga_generation = 0;
+    const size_t n = (size_t)P * G;
+    const int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)h->sm_count * 8);
+    ga_init_kernel<<<blocks, 256, 0, h->stream>>>(h->d_ga_pop[0], P, G, min_gen, max_gen, seed);
+    h->launches++;
+    CK(cudaGetLastError());
+    return R2P2_OK;
+}
+
+int r2p2_ga_set_operators(r2p2_handle h, int32_t tournament, double crossover_rate, double mutation_rate, double mutation_sigma, int32_t elites) {
+    if (!h) return R2P2_E_ARG;
+    if (tournament < 1 || tournament > 4) return fail(h, R2P2_E_ARG, "GA: tournament size must be 1..4");
+    if (elites < 0 || elites > kGaMaxElites) return fail(h, R2P2_E_ARG, "GA: elites must be 0..%d", kGaMaxElites);
+    if (!(crossover_rate >= 0.0 && crossover_rate <= 1.0 && mutation_rate >= 0.0 && mutation_rate <= 1.0 && mutation_sigma >= 0.0))
+        return fail(h, R2P2_E_ARG, "GA: rates must be in [0, 1], sigma >= 0");
+    h->ga_tournament = tournament; h->ga_cx = crossover_rate; h->ga_mut = mutation_rate; h->ga_sigma = mutation_sigma; h->ga_elites = elites;
+    return R2P2_OK;
+}
+
+int r2p2_ga_population_device(r2p2_handle h, double** d_pop) {
+    int rc = ga_ready(h); if (rc) return rc;
+    if (!d_pop) return fail(h, R2P2_E_ARG, "d_pop is NULL");
+    *d_pop = h->d_ga_pop[h->ga_cur];
+    return R2P2_OK;
+}
+
+int r2p2_ga_fitness_device(r2p2_handle h, double** d_fit) {
+    int rc = ga_ready(h); if (rc) return rc;
+    if (!d_fit) return fail(h, R2P2_E_ARG, "d_fit is NULL");
+    *d_fit = h->d_ga_fit;
+    return R2P2_OK;
+}
+
+int r2p2_ga_write_fitness(r2p2_handle h, const double* fitness, int32_t first, int32_t count) {
+    int rc = ga_ready(h); if (rc) return rc;
+    if (!fitness || first < 0 || count < 0 || first + count > h->ga_P) return fail(h, R2P2_E_ARG, "GA: fitness range out of bounds");
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync(h->d_ga_fit + first, fitness, (size_t)count * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return R2P2_OK;
+}
+
+int r2p2_ga_read(r2p2_handle h, double* population, double* fitness) {
+    int rc = ga_ready(h); if (rc) return rc;
+    CK(cudaSetDevice(h->device));
+    if (population) CK(cudaMemcpyAsync(population, h->d_ga_pop[h->ga_cur], (size_t)h->ga_P * h->ga_G * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (fitness) CK(cudaMemcpyAsync(fitness, h->d_ga_fit, (size_t)h->ga_P * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return R2P2_OK;
+}
+
+int r2p2_ga_evaluate(r2p2_handle h, int32_t first, int32_t count, int32_t T, double delta, double delta_ctrl, int32_t evolve) {
+    int rc = ga_ready(h); if (rc) return rc;
+    if (first < 0 || count < 1 || first + count > h->ga_P) return fail(h, R2P2_E_ARG, "GA: individual range out of bounds");
+    if (!h->have_pose1) return fail(h, R2P2_E_ARG, "GA: no start pose (call r2p2_reset with n == 1 once)");
+    rc = r2p2_set_genomes_device(h, h->d_ga_pop[h->ga_cur] + (size_t)first * h->ga_G, count, h->ga_G);
+    if (rc) return rc;
+    rc = r2p2_reset(h, &h->rx0, &h->ry0, &h->rt0, 1, h->rbudget);
+    if (rc) return rc;
+    rc = r2p2_run(h, T, delta, delta_ctrl, evolve);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(h->d_ga_fit + first, h->st.fitness, (size_t)count * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    return R2P2_OK;
+}
+
+int r2p2_ga_breed(r2p2_handle h) {
+    int rc = ga_ready(h); if (rc) return rc;
+    CK(cudaSetDevice(h->device));
+    GaParams g;
+    g.P = h->ga_P; g.G = h->ga_G; g.tournament = h->ga_tournament; g.elites = std::min(h->ga_elites, h->ga_P);
+    g.crossover_rate = h->ga_cx; g.mutation_rate = h->ga_mut; g.mutation_sigma = h->ga_sigma; g.min_gen = h->ga_min; g.max_gen = h->ga_max;
+    g.seed = h->ga_seed; g.generation = h->ga_generation;
+    g.pop = h->d_ga_pop[h->ga_cur]; g.fit = h->d_ga_fit; g.next = h->d_ga_pop[h->ga_cur ^ 1]; g.elite_idx = h->d_ga_elite;
+    ga_elites_kernel<<<1, 1024, 0, h->stream>>>(h->d_ga_fit, h->ga_P, std::max(g.elites, 1), h->d_ga_elite);
+    const long long threads = (long long)h->ga_P * 32;
+    ga_breed_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, h->stream>>>(g);
+    h->launches += 2;
+    CK(cudaGetLastError());
+    h->ga_cur ^= 1;
+    h->ga_generation++;
+    return R2P2_OK;
+}
+
+/* Best individual of the generation that was bred from last (index, fitness, genome [G]); any pointer may be NULL. */
+int r2p2_ga_best(r2p2_handle h, int32_t* index, double* fitness, double* genome) {
+    int rc = ga_ready(h); if (rc) return rc;
+    if (h->ga_generation == 0) return fail(h, R2P2_E_ARG, "GA: no generation bred yet");
+    CK(cudaSetDevice(h->device));
+    int idx = -1;
+    CK(cudaMemcpyAsync(&idx, h->d_ga_elite, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (idx < 0 || idx >= h->ga_P) return fail(h, R2P2_E_CUDA, "GA: elite index out of range");
+    if (index) *index = idx;
+    if (fitness) CK(cudaMemcpyAsync(fitness, h->d_ga_fit + idx, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (genome) CK(cudaMemcpyAsync(genome, h->d_ga_pop[h->ga_cur ^ 1] + (size_t)idx * h->ga_G, (size_t)h->ga_G * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return R2P2_OK;
+}
+
+int r2p2_ga_generation(r2p2_handle h, uint32_t* generation) {
+    if (!h || !generation) return R2P2_E_ARG;
+    *generation = h->ga_generation;
     return R2P2_OK;
 }
 

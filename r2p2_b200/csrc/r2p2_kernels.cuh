@@ -82,6 +82,7 @@ struct KParams {
     uint32_t* ndraws;                  // [P] draws consumed so far
     // trace (optional)
     double* tr_pose; double* tr_dst; int32_t* tr_hitk; int32_t* tr_hitpx; uint32_t* tr_nsamp; uint32_t* tr_ncoll;
+    double* tr_cinfo;           // [T][P][4]: collide() calls of the tick (code, wall spot x, y, border coordinate), see r2p2_read_trace_collisions
     // scheduling
     unsigned int* work_counter;
 };
@@ -882,6 +883,8 @@ __global__ void __launch_bounds__(kBlock, (NET::kLayers > 0) ? 1 : 4) episode_ke
             if (flags & (R2P2_F_FAULT | R2P2_F_DONE)) break;
             ncollide0 = ncollide;
             const size_t trow = (size_t)t * (size_t)p.P + rb;
+            unsigned ccode = 0u;                          // collide() calls of this tick, for the trace
+            double ccx = 0.0, ccy = 0.0, cbv = 0.0;
 
             PT(11)
             // ---- sense: Robot.check_sensors (robot.py:287-318) --------------------------------
@@ -1078,29 +1081,31 @@ __global__ void __launch_bounds__(kBlock, (NET::kLayers > 0) ? 1 : 4) episode_ke
                     if (f) { flags |= R2P2_F_FAULT; break; }
                     if (inwall) {
                         ncollide++; tmr = 0.0;
+                        ccode |= 1u; ccx = x; ccy = y;
                         const double ex = R2P2_SUB(ms.x, x), ey = R2P2_SUB(ms.y, y);
                         if (ex > 0.0) x = R2P2_ADD(ms.x, p.rad_p1); else if (ex < 0.0) x = R2P2_SUB(ms.x, p.rad_p1);
                         if (ey > 0.0) y = R2P2_ADD(ms.y, p.rad_p1); else if (ey < 0.0) y = R2P2_SUB(ms.y, p.rad_p1);
                     }
                 }
                 const double dW = (double)p.W, dH = (double)p.H, rad = p.radius;
+                // (border cases 1..8 of robot.py:222-247, recorded for the collision log: the spot mixes map sizes and this coordinate)
                 if (R2P2_ADD(x, rad) >= dW) {
-                    ncollide++; tmr = 0.0;
-                    if (R2P2_ADD(y, rad) < dH && R2P2_SUB(y, rad) >= 0.0) { }
-                    else if (R2P2_ADD(y, rad) >= dH) y = R2P2_SUB(R2P2_SUB(dH, 1.0), rad);
-                    else y = rad;
+                    ncollide++; tmr = 0.0; cbv = y;
+                    if (R2P2_ADD(y, rad) < dH && R2P2_SUB(y, rad) >= 0.0) { ccode |= 1u << 1; }
+                    else if (R2P2_ADD(y, rad) >= dH) { ccode |= 2u << 1; y = R2P2_SUB(R2P2_SUB(dH, 1.0), rad); }
+                    else { ccode |= 3u << 1; y = rad; }
                     x = R2P2_SUB(dW, 1.0);
                 } else if (R2P2_SUB(x, rad) < 0.0) {
-                    ncollide++; tmr = 0.0;
-                    if (R2P2_ADD(y, rad) < dH && R2P2_SUB(y, rad) >= 0.0) { }
-                    else if (R2P2_ADD(y, rad) >= dH) y = R2P2_SUB(R2P2_SUB(dH, 1.0), rad);
-                    else y = rad;
+                    ncollide++; tmr = 0.0; cbv = y;
+                    if (R2P2_ADD(y, rad) < dH && R2P2_SUB(y, rad) >= 0.0) { ccode |= 4u << 1; }
+                    else if (R2P2_ADD(y, rad) >= dH) { ccode |= 5u << 1; y = R2P2_SUB(R2P2_SUB(dH, 1.0), rad); }
+                    else { ccode |= 6u << 1; y = rad; }
                     x = 0.0;
                 } else if (R2P2_ADD(y, rad) > dH) {
-                    ncollide++; tmr = 0.0;
+                    ncollide++; tmr = 0.0; cbv = x; ccode |= 7u << 1;
                     y = R2P2_SUB(R2P2_SUB(dH, 1.0), rad);
                 } else if (R2P2_SUB(y, rad) < 0.0) {
-                    ncollide++; tmr = 0.0;
+                    ncollide++; tmr = 0.0; cbv = x; ccode |= 8u << 1;
                     y = rad;
                 }
                 PT(6)
@@ -1126,7 +1131,7 @@ __global__ void __launch_bounds__(kBlock, (NET::kLayers > 0) ? 1 : 4) episode_ke
                     if (cr == 2) { flags |= R2P2_F_FAULT; break; }
                     crash = cr == 1;
                 }
-                if (crash) { x = last_x; y = last_y; ncollide++; tmr = 0.0; }
+                if (crash) { x = last_x; y = last_y; ncollide++; tmr = 0.0; ccode |= 1u << 5; }
                 else { last_x = x; last_y = y; }
             }
             PT(7)
@@ -1136,6 +1141,8 @@ __global__ void __launch_bounds__(kBlock, (NET::kLayers > 0) ? 1 : 4) episode_ke
                 double* q = p.tr_pose + trow * 5;
                 q[0] = x; q[1] = y; q[2] = theta; q[3] = speed; q[4] = omega;
                 p.tr_ncoll[trow] = ncollide - ncollide0;
+                double* ci = p.tr_cinfo + trow * 4;
+                ci[0] = (double)ccode; ci[1] = ccx; ci[2] = ccy; ci[3] = cbv;
             }
         }
         PT_FLUSH(rb == 0 && g.sub == 0)

@@ -15,7 +15,7 @@ from .sim import BatchSim
 
 class Robot:
     def __init__(self, identifier=-1, x=0, y=0, orientation=0, speed=0, max_speed=2, acceleration=0, sensors=8,
-                 vision_range=(0, 10000), radius=1, color=None, controller=None, name=None, lock=None, device=0):
+                 vision_range=(0, 10000), radius=1, color=None, controller=None, name=None, lock=None, device=0, log_dir=None):
         self.identifier = identifier
         self.x, self.y = x, y
         self.last_pos = (x, y)
@@ -38,6 +38,11 @@ class Robot:
         self._env_id = None
         self._mirror = None
         self._dirty = True
+        # the reference always writes ../logs/robot_<id>.log and ..._sensors.log (robot.py:84-93); here only on request
+        self._logs = None
+        if log_dir is not None:
+            from .logs import RobotLogs
+            self._logs = RobotLogs(log_dir, identifier, name)
         self.controller.register_robot(self)
 
     # ---- reference API -----------------------------------------------------------------------
@@ -93,11 +98,16 @@ class Robot:
             sim.set_noise("off")
             sim.run(1, delta=delta, delta_ctrl=getattr(ctrl, "delta_ctrl", delta), evolve=evolve)
         self._pull(sim)
+        if write_stats and self._logs is not None:
+            self._logs.stats(self)                          # write_stats_to_log (robot.py:158-168)
 
     # ---- plumbing --------------------------------------------------------------------------------
     def _ray_angles(self, sim):
-        from .sim import expand_sonars
-        return expand_sonars(self.sensors)
+        """Ray angles with the reference's own Python types (JSON list entries / range() ints, utils.py:465-466)."""
+        import math
+        if isinstance(self.sensors, (list, tuple)):
+            return list(self.sensors)
+        return list(range(0, 360, math.floor(365 / int(self.sensors))))
 
     def _genome_changed(self):
         self._dirty = True
@@ -136,6 +146,7 @@ class Robot:
         s = sim.state()
         tr = sim.trace(1)
         theta_before = self.orientation
+        last_before = self.last_pos
         self.x, self.y, self.orientation = float(s["x"][0]), float(s["y"][0]), float(s["theta"][0])
         self.speed, self.angular_velocity = float(s["speed"][0]), float(s["omega"][0])
         self.flags = int(s["flags"][0])
@@ -146,6 +157,11 @@ class Robot:
         ctrl.set_ang([a + theta_before for a in self._ray_angles(sim)])
         ctrl.update_sensor_angles(ctrl.ang, list(dst))
         ctrl._fitness = float(sim.fitness()[0])
+        if self._logs is not None:
+            from .logs import python_dst, collision_spots, format_collision
+            self._logs.sensor_data(self.identifier, ctrl.ang, theta_before, python_dst(dst, self.vision_range[1] + self.radius))
+            for spot in collision_spots(tr["cinfo"][0, 0], (sim.W, sim.H), last_before):
+                self._logs.log.write(format_collision(self.identifier, spot))
         ncoll = int(tr["ncoll"][0, 0])
         for _ in range(ncoll):
             self.collide((self.x, self.y))

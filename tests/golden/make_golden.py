@@ -314,9 +314,56 @@ def gen_noisy_episodes(E):
     np.savez_compressed(os.path.join(OUT, "episodes_noise.npz"), meta=meta(), specs=json.dumps(specs), **out)
 
 
+def gen_logs(E):
+    """Log files the reference writes (robot.py:158-168, 337-352) for two short episodes -> tests/golden/logs.json."""
+    Scripted = make_scripted(E)
+    out = {}
+
+    def run(name, stage, robot_json, ctrl, T, genome, kind, layers=(), delta=0.1):
+        env = E.load_env(stage)
+        with contextlib.redirect_stdout(io.StringIO()):
+            r = E.make_robot(robot_json, ctrl)
+        cfg = json.load(open(os.path.join("..", "conf", robot_json)))
+        done = 0
+        try:
+            for t in range(T):
+                r.update(env, delta, True)
+                done += 1
+        except (IndexError, ValueError) as ex:      # the reference leaves the map: the tick is cut short
+            print("  ", name, "raised", type(ex).__name__, "in tick", done)
+        T = done
+        r.log.flush(); r.sensors_output.flush()
+        stem = os.path.join("..", "logs", "robot_" + str(r.identifier))
+        out[name] = {"log": open(stem + ".log").read(), "sensors": open(stem + "_sensors.log").read(),
+                     "identifier": r.identifier, "robot_json": cfg, "stage": stage, "T": T, "kind": kind, "layers": list(layers),
+                     "delta": delta, "genome": [float(g) for g in genome], "acceleration": r.acceleration,
+                     "final": [r.x, r.y, r.orientation], "shape": [int(env.shape[0]), int(env.shape[1])]}
+        print("logs", name, len(out[name]["log"]), "bytes")
+
+    c = np.random.RandomState(7).uniform(-1, 1, 18) * 0.05
+    run("linear_omni", "track_2.png", "robot_omni.json", E.linear_controller(c), 40, c, "linear")
+    sc = Scripted(); sc.cmd = (30.0, 2.0)
+    run("const_wall", "track_2.png", "robot-neuro.json", sc, 70, [30.0, 2.0], "const")
+    sc = Scripted(); sc.cmd = (-12.5, -7.0)
+    run("const_stage", "stage.png", "robot.json", sc, 30, [-12.5, -7.0], "const")
+    # long ticks: the robot jumps into walls (collide at the proposed position, robot.py:212)
+    sc = Scripted(); sc.cmd = (50.0, 7.0)
+    run("fast_walls", "stage.png", "robot.json", sc, 60, [50.0, 7.0], "const", delta=1.0)
+    # an empty 400 x 300 stage written into the scratch tree: the robot reaches the left / top map border (robot.py:232-247)
+    from PIL import Image
+    Image.new("L", (400, 300), 255).save(os.path.join("..", "res", "blank.png"))
+    sc = Scripted(); sc.cmd = (-45.0, 3.0)
+    run("blank_border", "blank.png", "robot.json", sc, 40, [-45.0, 3.0], "const", delta=1.0)
+    with open(os.path.join(OUT, "logs.json"), "w") as fp:
+        json.dump(out, fp, indent=1)
+
+
 def main():
     E = ref_harness.RefEnv()
     try:
+        if "--logs-only" in sys.argv:
+            gen_logs(E)
+            return
         if "--noise-only" in sys.argv:
             gen_noisy_episodes(E)
             return
@@ -324,6 +371,7 @@ def main():
         gen_ticks(E)
         gen_episodes(E)
         gen_noisy_episodes(E)
+        gen_logs(E)
         # stage bitmaps as the reference loads them (env[x, y], int32) -- fixtures for the GPU box
         for stage in STAGES:
             env = np.ascontiguousarray(E.load_env(stage)).astype(np.uint8)
