@@ -66,3 +66,39 @@ class ShardedEvaluator:
         local = np.asarray(self.local_eval(genomes[lo:hi]), dtype=np.float64)
         t = torch.from_numpy(local).to(self.device)
         return gather_fitness(t, P, self.group).cpu().numpy()
+
+
+def device_view(dev_ptr, n, device):
+    """Zero-copy float64 torch view of n doubles at a device pointer owned by the library."""
+    class _Holder:
+        pass
+    h = _Holder()
+    h.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f8", "data": (int(dev_ptr), False), "version": 3}
+    return torch.as_tensor(h, device=device)
+
+
+class ShardedDeviceGA:
+    """The on-device EA (ea.DeviceGA) over the GPUs of one box.
+
+    Every rank holds the whole population and the whole fitness vector in its own HBM and the same seed.  Per
+    generation: rank r evaluates its block of individuals (one episode-kernel launch), the fitness blocks are
+    all-gathered over NCCL straight into the GA's device fitness vector, and every rank breeds the identical next
+    generation (Philox draws depend only on seed / generation / individual / gene).  No genome ever crosses a link."""
+
+    def __init__(self, ga, device, group=None):
+        self.ga, self.device, self.group = ga, torch.device(device), group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.lo, self.hi = shard_bounds(ga.P, self.world, self.rank)
+
+    def step(self, ticks, delta=0.1, delta_ctrl=None, evolve=False):
+        ga = self.ga
+        ga.evaluate(ticks, delta, delta_ctrl, evolve, first=self.lo, count=self.hi - self.lo)
+        full = device_view(ga.fitness_device_ptr(), ga.P, self.device)
+        ga.sim.sync()                                       # the library's stream -> torch's stream
+        gathered = gather_fitness(full[self.lo:self.hi].clone(), ga.P, self.group)
+        full.copy_(gathered)
+        if self.device.type == "cuda":
+            torch.cuda.current_stream(self.device).synchronize()
+        ga.breed()
+        i, f, _ = ga.best(genome=False)
+        return {"generation": ga.generation - 1, "best": f, "best_index": i}
