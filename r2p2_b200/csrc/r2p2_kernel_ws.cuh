@@ -346,7 +346,7 @@ __global__ void __launch_bounds__(kBlock, (NET::kLayers > 0) ? 1 : 4) episode_ke
                 // 360 probes over the lanes of the group; the reference stops at the first wall, so an IndexError only
                 // counts if it comes before the first wall probe.  Groups that do not need the ring idle through it.
                 unsigned key = 0xffffffffu;
-                if (need_ring) key = ring_scan<LPR>(sv, g.sub, x, y, s_crx, s_cry);
+                if (need_ring) key = ring_scan<LPR>(sv, g.sub, x, y, p.radius, s_crx, s_cry);
                 key = g.min_u(key);
                 if (need_ring && key != 0xffffffffu) {
                     if (key & 1u) crash = true;

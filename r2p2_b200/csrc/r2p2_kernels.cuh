@@ -518,10 +518,38 @@ __device__ __forceinline__ Hit team_march(const StageView& s, const Team& tm, co
 // the reference stops at the first wall, so an IndexError counts only if it comes before the first wall probe: after
 // a min-reduction over the lanes, an even key is a fault, an odd key a crash.
 template <int LPR>
-__device__ __forceinline__ unsigned ring_scan(const StageView& sv, int sub, double x, double y,
+__device__ __forceinline__ unsigned ring_scan(const StageView& sv, int sub, double x, double y, double radius,
                                               const double* s_crx, const double* s_cry) {
     unsigned key = 0xffffffffu;
     constexpr int kPer = (360 + LPR - 1) / LPR;
+    // The whole ring strictly inside the map (the usual case: |offset| <= |radius|): every probe index is in range and
+    // non-negative, so neither Python's index wrap nor an IndexError can occur and only the wall bit is read.
+    const double ar = r2p2_fabs(radius);
+    const bool inside = (R2P2_SUB(x, ar) >= 1.0) & (R2P2_ADD(x, ar) < (double)(sv.W - 1)) & (R2P2_SUB(y, ar) >= 1.0) & (R2P2_ADD(y, ar) < (double)(sv.H - 1));
+    if (inside) {                                          // uniform in the group
+#pragma unroll 1
+        for (int m0 = 0; m0 < kPer; m0 += 4) {
+            unsigned w[4];
+            int bx[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = sub + (m0 + u) * LPR;
+                const int ii = (i < 360) ? i : 0;
+                int ix, iy;
+                fast_floor(R2P2_ADD(x, s_crx[ii]), ix);
+                fast_floor(R2P2_ADD(y, s_cry[ii]), iy);
+                w[u] = sv.wall[iy * sv.wpr + (ix >> 5)];
+                bx[u] = ix & 31;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = sub + (m0 + u) * LPR;
+                const bool hit = (i < 360) & (((w[u] >> bx[u]) & 1u) != 0u);
+                key = min(key, hit ? (unsigned)(2 * i + 1) : 0xffffffffu);
+            }
+        }
+        return key;
+    }
 #pragma unroll 1
     for (int m0 = 0; m0 < kPer; m0 += 4) {
         unsigned w[4], ev[4];
@@ -627,9 +655,9 @@ __device__ __forceinline__ double noise_draw(const KParams& p, unsigned rb, unsi
 // Robot.__crashing_radius (r2p2/robot.py:181-186), only reached when the centre pixel is within ceil(radius)+1 of a
 // blocked pixel.  returns 0 clear, 1 crashing, 2 the reference raises (IndexError before the first wall probe).
 template <int LPR>
-__device__ __forceinline__ int crash_ring(const StageView& sv, const Group<LPR>& g, double x, double y,
+__device__ __forceinline__ int crash_ring(const StageView& sv, const Group<LPR>& g, double x, double y, double radius,
                                        const double* s_crx, const double* s_cry) {
-    unsigned key = ring_scan<LPR>(sv, g.sub, x, y, s_crx, s_cry);
+    unsigned key = ring_scan<LPR>(sv, g.sub, x, y, radius, s_crx, s_cry);
     if (LPR > 1) key = g.min_u(key);
     if (key == 0xffffffffu) return 0;
     return (key & 1u) ? 1 : 2;
@@ -1127,7 +1155,7 @@ __global__ void __launch_bounds__(kBlock, (NET::kLayers > 0) ? 1 : 4) episode_ke
                 if (!crash && !ring_clear) {
                     // 360 probes spread over the group; the reference stops at the first wall, so an
                     // IndexError only counts if it comes before the first wall probe
-                    const int cr = crash_ring<LPR>(sv, g, x, y, s_crx, s_cry);
+                    const int cr = crash_ring<LPR>(sv, g, x, y, p.radius, s_crx, s_cry);
                     if (cr == 2) { flags |= R2P2_F_FAULT; break; }
                     crash = cr == 1;
                 }
