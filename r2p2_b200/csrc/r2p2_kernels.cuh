@@ -126,6 +126,14 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ int dtrunc(double v) { return __double2int_rz(v); }   // int(v); saturates, NaN -> 0
 
+// floor(v) for 0 <= v < 2^32 without an FP64 -> int conversion (F2I.F64 issues at a quarter of the DADD rate): the low
+// word of RD(v + 2^52).  ok is false outside that range and for NaN; inside it floor == trunc, i.e. Python's int().
+__device__ __forceinline__ bool fast_floor(double v, int& idx) {
+    const double t = __dadd_rd(v, 4503599627370496.0);
+    idx = __double2loint(t);
+    return __double2hiint(t) == 0x43300000;
+}
+
 __device__ __forceinline__ bool plane_bit(const uint32_t* __restrict__ plane, int wpr, int ix, int iy) {
     return (plane[iy * wpr + (ix >> 5)] >> (ix & 31)) & 1u;
 }
@@ -227,9 +235,18 @@ __device__ __forceinline__ Hit march(const StageView& s, double ox, double oy, d
     int k = 0;
     while (k < kB) {
         unsigned d = 0u;
+        bool wall_here = false;
         if (k < kA) {
-            const int ix = dtrunc(x), iy = dtrunc(y);
-            if (((unsigned)ix < (unsigned)s.W) & ((unsigned)iy < (unsigned)s.H)) d = __ldg(s.dist + (size_t)iy * s.W + ix);
+            int ix, iy;
+            const bool inmap = fast_floor(x, ix) & fast_floor(y, iy) & ((unsigned)ix < (unsigned)s.W) & ((unsigned)iy < (unsigned)s.H);
+            if (inmap) d = __ldg(s.dist + (size_t)iy * s.W + ix);
+            // distance 0 on an interior pixel is a wall (the only other blocked pixels are the outer ring): a hit
+            wall_here = inmap & (d == 0u) & ((unsigned)(ix - 1) < (unsigned)(s.W - 2)) & ((unsigned)(iy - 1) < (unsigned)(s.H - 2));
+        }
+        if (wall_here) {
+            r.nsamp++;
+            r.x = x; r.y = y; r.k = k;
+            return r;
         }
         if (d == 0u) {
             const int st = sample_exact(s.wall, s.W, s.H, s.wpr, x, y, ox, oy, limit, k >= kA);
@@ -390,14 +407,6 @@ __device__ __forceinline__ Hit team_march_chunked(const StageView& s, const Team
         r.nsamp = (unsigned)k;          // the while-condition failed at sample k
     }
     return r;
-}
-
-// floor(v) for 0 <= v < 2^32 without an FP64 -> int conversion (F2I.F64 issues at a quarter of the DADD rate): the low
-// word of RD(v + 2^52).  ok is false outside that range and for NaN; inside it floor == trunc, i.e. Python's int().
-__device__ __forceinline__ bool fast_floor(double v, int& idx) {
-    const double t = __dadd_rd(v, 4503599627370496.0);
-    idx = __double2loint(t);
-    return __double2hiint(t) == 0x43300000;
 }
 
 // Strided team march (the one the kernels use).  TL lanes -- a power of two, an aligned segment of the warp --
