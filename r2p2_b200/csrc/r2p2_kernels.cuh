@@ -468,6 +468,7 @@ __device__ __forceinline__ Hit team_march_t(const StageView& s, const Team& tm, 
             const unsigned kind = !inter[m] ? kSampleSlow : (((w[m] >> (ixs[m] & 31)) & 1u) ? (unsigned)kSampleHit : 0u);
             if ((k < kB) && kind != 0u && key == kNone) { key = ((unsigned)k << 2) | kind; hx = xs[m]; hy = ys[m]; }
         }
+        if (key != kNone) break;                            // this lane's later samples cannot come before its first event
         if (k0 + TL * NOWN < kB) {                          // another pass follows
 #pragma unroll
             for (int u = 0; u < TL; ++u) { x = R2P2_ADD(x, vx); y = R2P2_ADD(y, vy); }
@@ -943,7 +944,9 @@ __global__ void __launch_bounds__(kBlock, (NET::kLayers > 0) ? 1 : 4) episode_ke
                         if (!sc.ok && have_ray) { flags |= R2P2_F_TRIGRANGE; fault = true; }
                         Hit h;
                         if (LPR == 1) {
-                            h = sc.ok ? march(sv, ox, oy, vc, vs, p.L) : Hit{-1.0, -1.0, -1, 0u, true};
+                            // one thread walks the whole ray: every sample's bit-plane load is independent of the others
+                            // (the distance-field march chains each load to the one before it and diverges between robots)
+                            h = sc.ok ? team_march_t<1, 8>(sv, sonar_team, sonar_plan, ox, oy, vc, vs, p.L) : Hit{-1.0, -1.0, -1, 0u, true};
                         } else {
                             h = team_march<(LPR < kMaxSonarTeam ? LPR : kMaxSonarTeam)>(sv, sonar_team, sonar_plan, ox, oy, vc, vs, p.L);
                         }
