@@ -18,7 +18,7 @@ __global__ void march_lat(double* out, StageView sv, long long* cyc, int mode) {
 #pragma unroll 1
     for (int i = 0; i < N; ++i) {
         {
-            const Hit h = team_march(sv, tm, mp, ox, oy, vx, vy, limit);
+            const Hit h = team_march_chunked(sv, tm, mp, ox, oy, vx, vy, limit);
             acc += h.nsamp;
             ox = 230.0 + (double)(h.nsamp & 1u);
         }

@@ -21,21 +21,21 @@ __global__ void lat(double* out, StageView sv, long long* cyc, int mode, const d
     for (int i = 0; i < N; ++i) {
         if (mode == 0) {            // miss, plan hoisted
             const MarchPlan mp = make_plan(7.3, 32);
-            const Hit h = team_march(sv, tm, mp, ox, oy, vx, vy, 7.3);
+            const Hit h = team_march_t<32, 1>(sv, tm, mp, ox, oy, vx, vy, 7.3);
             acc += h.nsamp; ox = 230.0 + (double)(h.nsamp & 1u);
         } else if (mode == 1) {     // make_plan in the chain
             const MarchPlan mp = make_plan(limit, 32);
-            const Hit h = team_march(sv, tm, mp, ox, oy, vx, vy, limit);
+            const Hit h = team_march_t<32, 1>(sv, tm, mp, ox, oy, vx, vy, limit);
             acc += h.nsamp; ox = 230.0 + (double)(h.nsamp & 1u); limit = 7.3 + 1e-9 * (double)(h.nsamp & 3u);
         } else if (mode == 2) {     // hit at k = 3 (wall column at x = 303)
             const MarchPlan mp = make_plan(limit, 32);
-            const Hit h = team_march(sv, tm, mp, ox + 70.0, oy, vx, vy, limit);
+            const Hit h = team_march_t<32, 1>(sv, tm, mp, ox + 70.0, oy, vx, vy, limit);
             acc += h.nsamp; ox = 230.0 + (double)(h.k & 1); limit = 7.3 + 1e-9 * (double)(h.nsamp & 3u);
         } else if (mode == 3) {     // crash ring, clear
-            const int c = crash_ring<32>(sv, g, ox, oy, s_crx, s_cry);
+            const int c = crash_ring<32>(sv, g, ox, oy, 6.0, s_crx, s_cry);
             acc += c; ox = 230.0 + (double)(c & 1);
         } else if (mode == 4) {     // crash ring touching the wall
-            const int c = crash_ring<32>(sv, g, ox + 67.5, oy, s_crx, s_cry);
+            const int c = crash_ring<32>(sv, g, ox + 67.5, oy, 6.0, s_crx, s_cry);
             acc += c; ox = 230.0 + (double)(c & 2);
         } else if (mode == 5) {     // ray_is_clear + norm2
             unsigned ns = 0;

@@ -6,7 +6,7 @@ using namespace r2p2;
 #define N 512
 
 template <int TL, int NOWN>
-__device__ __forceinline__ Hit team_march_t(const StageView& s, const Team& tm, const MarchPlan& mp, double ox, double oy,
+__device__ __forceinline__ Hit team_march_x(const StageView& s, const Team& tm, const MarchPlan& mp, double ox, double oy,
                                             double vx, double vy, double limit) {
     const int kA = mp.kA, kB = mp.kB;
     if (kB == 0x7fffffff) return march_plain(s, ox, oy, vx, vy, limit);
@@ -70,7 +70,7 @@ __device__ __forceinline__ Hit team_march_t(const StageView& s, const Team& tm, 
 }
 
 // floor(v) for 0 <= v < 2^32 without F2I: the low word of RD(v + 2^52); ok is false outside that range (and for NaN)
-__device__ __forceinline__ bool fast_floor(double v, int& idx) {
+__device__ __forceinline__ bool fast_floor_x(double v, int& idx) {
     const double t = __dadd_rd(v, 4503599627370496.0);
     idx = __double2loint(t);
     return __double2hiint(t) == 0x43300000;
@@ -105,7 +105,7 @@ __device__ __forceinline__ Hit team_march_f(const StageView& s, const Team& tm, 
         for (int m = 0; m < NOWN; ++m) {
             xs[m] = x; ys[m] = y;
             int ix, iy;
-            const bool okx = fast_floor(x, ix), oky = fast_floor(y, iy);
+            const bool okx = fast_floor_x(x, ix), oky = fast_floor_x(y, iy);
             inter[m] = okx & oky & ((unsigned)(ix - 1) < (unsigned)(s.W - 2)) & ((unsigned)(iy - 1) < (unsigned)(s.H - 2));
             w[m] = __ldg(s.wall + (inter[m] ? (iy * s.wpr + (ix >> 5)) : 0));
             ixs[m] = ix;
@@ -172,11 +172,11 @@ __global__ void lat(double* out, StageView sv, long long* cyc, int mode, double 
     for (int i = 0; i < N; ++i) {
         Hit h;
         if (mode == 0) h = team_march_chunked(sv, tm, mp, ox, oy, vx, vy, limit);
-        else if (mode == 1) h = team_march(sv, tm, mp, ox, oy, vx, vy, limit);
-        else if (mode == 2) h = team_march_t<4, 8>(sv, tm, mp, ox, oy, vx, vy, limit);
+        else if (mode == 1) h = team_march_x<4, 8>(sv, tm, mp, ox, oy, vx, vy, limit);
+        else if (mode == 2) h = team_march_x<4, 8>(sv, tm, mp, ox, oy, vx, vy, limit);
         else if (mode == 3) h = team_march_f<4, 8>(sv, tm, mp, ox, oy, vx, vy, limit);
         else if (mode == 4) h = team_march_f<32, 1>(sv, tm, mp, ox, oy, vx, vy, limit);
-        else h = team_march_t<32, 1>(sv, tm, mp, ox, oy, vx, vy, limit);
+        else h = team_march_x<32, 1>(sv, tm, mp, ox, oy, vx, vy, limit);
         acc += h.nsamp + (unsigned)h.k;
         ox = ox0 + (double)(h.nsamp & 1u);
         __syncwarp();
