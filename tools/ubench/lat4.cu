@@ -1,7 +1,7 @@
 // Latency of team_march (5 sonar rays x 6 lanes, limit 30) and of the 32-lane collision-ray march, single warp.
 #include <cstdio>
 #include <cuda_runtime.h>
-#include "../../r2p2_b200/csrc/r2p2_kernels.cuh"
+#include "chunked_march.cuh"
 using namespace r2p2;
 #define N 512
 __global__ void march_lat(double* out, StageView sv, long long* cyc, int mode) {

@@ -1,7 +1,7 @@
 // Sonar-fan march variants, single warp, 5 rays from one origin (limit 31: kA = 31, kB = 32), runtime plan.
 #include <cstdio>
 #include <cuda_runtime.h>
-#include "../../r2p2_b200/csrc/r2p2_kernels.cuh"
+#include "chunked_march.cuh"
 using namespace r2p2;
 #define N 512
 
