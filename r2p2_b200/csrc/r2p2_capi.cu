@@ -10,6 +10,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -65,8 +66,10 @@ struct r2p2_sim {
     StateArrays st;
     int state_cap = 0;
     double *d_x0 = nullptr, *d_y0 = nullptr, *d_t0 = nullptr;
-    // mapping
+    // mapping (the choice is cached until the configuration changes: the per-tick API calls r2p2_run once per frame)
     int lpr_req = 0, smem_req = -1;
+    uint64_t cfg_epoch = 1, lpr_epoch = 0;
+    int lpr_cached = 0;
     // sensor noise
     int noise_mode = 0, noise_len = 0, noise_P = 0;
     unsigned long long noise_seed = 0;
@@ -139,6 +142,7 @@ int ensure_genomes(r2p2_handle h, int P, int G) {
         h->genomes_cap = need;
     }
     if (P != h->P) h->have_reset = false;
+    if (P != h->P || G != h->G) h->cfg_epoch++;
     h->P = P; h->G = G;
     h->genomes_t_valid = false;
     return ensure_state(h, P);
@@ -179,6 +183,7 @@ int pack_stage(r2p2_handle h, const uint8_t* d_levels, int W, int H) {
     cudaFree(d_has);
     cudaFree(d_hrow);
     h->W = W; h->H = H; h->wpr = wpr; h->has50 = has; h->plane_bytes = (uint32_t)bytes;
+    h->cfg_epoch++;
     return R2P2_OK;
 }
 
@@ -198,11 +203,23 @@ int upload_crxy(r2p2_handle h) {
 }
 
 // occ_out != NULL: only report how many CTAs of the kernel this configuration selects fit on an SM (no launch)
+struct OccEntry { const void* fn; int device; size_t smem; int occ; };
+std::vector<OccEntry> g_occ_cache;      // per kernel instance: dynamic shared memory it was sized for, CTAs per SM
+std::mutex g_occ_mutex;                 // handles of different host threads share the cache
+
 template <int LPR, class KERN>
 int launch_kernel(r2p2_handle h, KERN kern, const KParams& kp, size_t smem, int* occ_out) {
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int occ = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kBlock, smem));
+    int occ = -1;
+    std::lock_guard<std::mutex> lock(g_occ_mutex);
+    for (const OccEntry& e : g_occ_cache)
+        if (e.fn == (const void*)kern && e.device == h->device && e.smem == smem) { occ = e.occ; break; }
+    if (occ < 0) {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kBlock, smem));
+        // one entry per (kernel, device): a new size replaces the old one, the attribute is the last one set
+        g_occ_cache.erase(std::remove_if(g_occ_cache.begin(), g_occ_cache.end(), [&](const OccEntry& e) { return e.fn == (const void*)kern && e.device == h->device; }), g_occ_cache.end());
+        g_occ_cache.push_back({(const void*)kern, h->device, smem, occ});
+    }
     if (occ_out) { *occ_out = occ; return R2P2_OK; }
     if (occ < 1) return fail(h, R2P2_E_LIMIT, "episode kernel does not fit on an SM (smem %zu bytes)", smem);
     const int robots_per_cta = kBlock / LPR;
@@ -426,6 +443,7 @@ int r2p2_set_robot(r2p2_handle h, double vr0, double vr1, double radius, double 
     h->vr0 = vr0; h->vr1 = vr1; h->radius = radius; h->max_speed = max_speed; h->R = n_rays;
     memcpy(h->ray_deg, ray_deg, sizeof(double) * (size_t)n_rays);
     h->have_robot = true;
+    h->cfg_epoch++;
     return upload_crxy(h);
 }
 
@@ -447,6 +465,7 @@ int r2p2_set_controller(r2p2_handle h, int32_t kind, const int32_t* layers, int3
         h->n_layers = 0;
     }
     h->kind = kind; h->activation = activation; h->have_ctrl = true;
+    h->cfg_epoch++;
     return R2P2_OK;
 }
 
@@ -482,6 +501,7 @@ int r2p2_set_mapping(r2p2_handle h, int32_t lanes_per_robot, int32_t stage_in_sm
     if (!(l == 0 || l == 1 || l == 2 || l == 4 || l == 8 || l == 16 || l == 32)) return fail(h, R2P2_E_ARG, "lanes_per_robot must be 0,1,2,4,8,16,32");
     if (stage_in_smem < -1 || stage_in_smem > 1) return fail(h, R2P2_E_ARG, "stage_in_smem must be -1, 0 or 1");
     h->lpr_req = l; h->smem_req = stage_in_smem;
+    h->cfg_epoch++;
     return R2P2_OK;
 }
 
@@ -586,7 +606,8 @@ int r2p2_run(r2p2_handle h, int32_t T, double delta, double delta_ctrl, int32_t 
     kp.work_counter = h->d_work;
     kp.genomes = h->d_genomes;
 
-    const int lpr = choose_lpr(h, kp);
+    if (h->lpr_epoch != h->cfg_epoch) { h->lpr_cached = choose_lpr(h, kp); h->lpr_epoch = h->cfg_epoch; }
+    const int lpr = h->lpr_cached;
     if (lpr == 1) {
         if (!h->genomes_t_valid) {
             dim3 grid((h->P + 31) / 32, (h->G + 31) / 32), block(32, 8);
