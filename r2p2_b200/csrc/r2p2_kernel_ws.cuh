@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(kBlock, (NET::kLayers > 0) ? 1 : 4) episode_ke
                 const double ang = have_ray ? R2P2_ADD(p.ray_deg[i], theta) : 0.0;
                 const SinCos sc = sincos_call(R2P2_MUL(ang, kRad), s_tab);
                 if (!sc.ok && have_ray) { flags |= R2P2_F_TRIGRANGE; fault = true; }
-                const Hit h = team_march<(LPR < kMaxSonarTeam ? LPR : kMaxSonarTeam), 4>(sv, sonar_team, plan, ox, oy, sc.c, sc.s, p.L);
+                const Hit h = team_march<(LPR < kMaxSonarTeam ? LPR : kMaxSonarTeam), (LPR <= 2 ? 8 : 4)>(sv, sonar_team, plan, ox, oy, sc.c, sc.s, p.L);
                 if (h.fault && have_ray) fault = true;
                 const bool leader = have_ray && (team_j == 0);
                 double d = 0.0;
