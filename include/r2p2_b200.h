@@ -167,6 +167,19 @@ int r2p2_read_trace(r2p2_handle h, int32_t T, double* pose, double* dst, int32_t
  * crash-radius / level-50 test fired and the robot went back to its last position, which is the spot (robot.py:249-252). */
 int r2p2_read_trace_collisions(r2p2_handle h, int32_t T, double* cinfo);
 
+/* ---- controllers that run on the host (any reference Controller subclass: PID, PDDL, teleop ...) ---------- */
+/* Robot.update is control() then the move (r2p2/robot.py:389-402); control() is check_sensors, the controller's
+ * control(dst), the speed clamp (robot.py:373-387).  For a controller without a device form the tick is split at the
+ * controller call:
+ *   r2p2_sense  = Robot.check_sensors (robot.py:287-318) for every robot at its current pose: dst [P][R] distances
+ *                 as the controller receives them (clamped, with noise if enabled), hitpx [P][R][2] hit pixel or -1
+ *                 (may be NULL).  Poses are not touched.
+ *   r2p2_move   = the rest of the tick with the controller's answer: commands [P][2] = (speed, angular_velocity) per
+ *                 robot -> speed clamp, __update_angle, __update_position (robot.py:386-387, 257-267, 188-255).
+ * Both are synchronous (host arrays).  The population is sized by r2p2_upload_genomes (any G) and r2p2_reset. */
+int r2p2_sense(r2p2_handle h, double* dst, int32_t* hitpx);
+int r2p2_move(r2p2_handle h, const double* commands, double delta);
+
 /* ---- generation step of the EA on the device -------------------------------------------------- */
 /* The reference leaves the EA to the user (r2p2/evolution.py:58-68 "TODO: Implement your EA here"; ga.py.gpg is
  * encrypted) and fixes the contract: generate_float candidates uniform in [min_gen, max_gen] (evolution.py:18-22),

@@ -83,6 +83,11 @@ struct r2p2_sim {
     // start pose / time budget of the last r2p2_reset with n == 1 (re-applied by r2p2_ga_evaluate)
     bool have_pose1 = false;
     double rx0 = 0, ry0 = 0, rt0 = 0, rbudget = 0;
+    // host-controller bridge (r2p2_sense / r2p2_move)
+    double* d_sense_dst = nullptr;      // [P][R]
+    int32_t* d_sense_px = nullptr;      // [P][R][2]
+    double* d_cmd = nullptr;            // [P][2]
+    int bridge_cap = 0, bridge_R = 0;
     // on-device GA (r2p2_ga.cuh)
     int ga_P = 0, ga_G = 0, ga_cur = 0, ga_tournament = 2, ga_elites = 1;
     double ga_cx = 0.9, ga_mut = 0.05, ga_sigma = 0.1, ga_min = -1.0, ga_max = 1.0;
@@ -243,7 +248,7 @@ int launch_episode(r2p2_handle h, const KParams& kp, size_t smem, int* occ_out) 
         static const bool ws = [] { const char* e = getenv("R2P2_WS"); return !(e && e[0] == '0'); }();
         // (a sonar limit without a norm window sends whole groups through the plain loop, which the lock-step kernel
         // cannot mix with groups that have stopped)
-        if (ws && kp.L > -1.0 && kp.L < 30000.0) return launch_kernel<LPR>(h, episode_kernel_ws<LPR, NET>, kp, smem, occ_out);
+        if (ws && !kp.skip_sense && kp.L > -1.0 && kp.L < 30000.0) return launch_kernel<LPR>(h, episode_kernel_ws<LPR, NET>, kp, smem, occ_out);
     }
     return launch_kernel<LPR>(h, episode_kernel<LPR, SMEM, NET>, kp, smem, occ_out);
 }
@@ -362,7 +367,7 @@ int r2p2_destroy(r2p2_handle h) {
     void* ptrs[] = {s.x, s.y, s.theta, s.speed, s.omega, s.last_x, s.last_y, s.dist, s.odom_x, s.odom_y, s.origin_x, s.origin_y,
                     s.time, s.fitness, s.flags, s.ncollide, s.ticks, s.ndraws, s.nsamp_sonar, s.nsamp_coll, h->d_noise, h->d_x0, h->d_y0, h->d_t0,
                     h->d_wall, h->d_l50, h->d_dist, h->d_crxy, h->d_sincostab, h->d_genomes, h->d_genomes_t, h->d_work, h->d_cnt3,
-                    h->d_ga_pop[0], h->d_ga_pop[1], h->d_ga_fit, h->d_ga_elite};
+                    h->d_ga_pop[0], h->d_ga_pop[1], h->d_ga_fit, h->d_ga_elite, h->d_sense_dst, h->d_sense_px, h->d_cmd};
     for (void* p : ptrs) cudaFree(p);
     free_trace(h);
     cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
@@ -551,28 +556,7 @@ int r2p2_reset(r2p2_handle h, const double* x0, const double* y0, const double* 
     return R2P2_OK;
 }
 
-int r2p2_run(r2p2_handle h, int32_t T, double delta, double delta_ctrl, int32_t evolve) {
-    if (!h) return R2P2_E_ARG;
-    if (!h->d_wall) return fail(h, R2P2_E_ARG, "r2p2_run: no stage (call r2p2_set_stage)");
-    if (!h->have_robot) return fail(h, R2P2_E_ARG, "r2p2_run: no robot (call r2p2_set_robot)");
-    if (!h->have_ctrl) return fail(h, R2P2_E_ARG, "r2p2_run: no controller (call r2p2_set_controller)");
-    if (!h->have_genomes) return fail(h, R2P2_E_ARG, "r2p2_run: no genomes (call r2p2_upload_genomes)");
-    if (!h->have_reset) return fail(h, R2P2_E_ARG, "r2p2_run: population not initialised (call r2p2_reset)");
-    if (T < 0) return fail(h, R2P2_E_ARG, "T must be >= 0");
-    if (h->kind == R2P2_CTRL_NEURO) {
-        if (h->layers[0] != h->R) return fail(h, R2P2_E_ARG, "MLP input width %d != number of sonar rays %d", h->layers[0], h->R);
-        int g = 0;
-        for (int l = 0; l + 1 < h->n_layers; ++l) g += h->layers[l] * h->layers[l + 1];
-        if (g != h->G) return fail(h, R2P2_E_ARG, "genome length %d != MLP weight count %d", h->G, g);
-    } else if (h->kind == R2P2_CTRL_LINEAR) {
-        if (h->G < 4 || (h->G & 1)) return fail(h, R2P2_E_ARG, "linear chromosome length must be even and >= 4 (got %d)", h->G);
-    } else if (h->G != 2) {
-        return fail(h, R2P2_E_ARG, "constant-command genome must be [speed, angular_velocity]");
-    }
-    if (h->trace && (T > h->trace_T)) return fail(h, R2P2_E_ARG, "trace enabled for at most %d ticks per run", h->trace_T);
-    CK(cudaSetDevice(h->device));
-
-    KParams kp;
+static int fill_params(r2p2_handle h, KParams& kp, int32_t T, double delta, double delta_ctrl, int32_t evolve) {
     memset(&kp, 0, sizeof kp);
     kp.W = h->W; kp.H = h->H; kp.wpr = h->wpr; kp.has50 = h->has50;
     kp.g_wall = h->d_wall; kp.g_lvl50 = h->d_l50; kp.plane_bytes = h->plane_bytes;
@@ -605,6 +589,34 @@ int r2p2_run(r2p2_handle h, int32_t T, double delta, double delta_ctrl, int32_t 
     if (h->noise_mode == 1 && h->noise_P != h->P) return fail(h, R2P2_E_ARG, "noise stream was uploaded for %d robots, population is %d", h->noise_P, h->P);
     kp.work_counter = h->d_work;
     kp.genomes = h->d_genomes;
+
+    return R2P2_OK;
+}
+
+int r2p2_run(r2p2_handle h, int32_t T, double delta, double delta_ctrl, int32_t evolve) {
+    if (!h) return R2P2_E_ARG;
+    if (!h->d_wall) return fail(h, R2P2_E_ARG, "r2p2_run: no stage (call r2p2_set_stage)");
+    if (!h->have_robot) return fail(h, R2P2_E_ARG, "r2p2_run: no robot (call r2p2_set_robot)");
+    if (!h->have_ctrl) return fail(h, R2P2_E_ARG, "r2p2_run: no controller (call r2p2_set_controller)");
+    if (!h->have_genomes) return fail(h, R2P2_E_ARG, "r2p2_run: no genomes (call r2p2_upload_genomes)");
+    if (!h->have_reset) return fail(h, R2P2_E_ARG, "r2p2_run: population not initialised (call r2p2_reset)");
+    if (T < 0) return fail(h, R2P2_E_ARG, "T must be >= 0");
+    if (h->kind == R2P2_CTRL_NEURO) {
+        if (h->layers[0] != h->R) return fail(h, R2P2_E_ARG, "MLP input width %d != number of sonar rays %d", h->layers[0], h->R);
+        int g = 0;
+        for (int l = 0; l + 1 < h->n_layers; ++l) g += h->layers[l] * h->layers[l + 1];
+        if (g != h->G) return fail(h, R2P2_E_ARG, "genome length %d != MLP weight count %d", h->G, g);
+    } else if (h->kind == R2P2_CTRL_LINEAR) {
+        if (h->G < 4 || (h->G & 1)) return fail(h, R2P2_E_ARG, "linear chromosome length must be even and >= 4 (got %d)", h->G);
+    } else if (h->G != 2) {
+        return fail(h, R2P2_E_ARG, "constant-command genome must be [speed, angular_velocity]");
+    }
+    if (h->trace && (T > h->trace_T)) return fail(h, R2P2_E_ARG, "trace enabled for at most %d ticks per run", h->trace_T);
+    CK(cudaSetDevice(h->device));
+
+    KParams kp;
+    int rc0 = fill_params(h, kp, T, delta, delta_ctrl, evolve);
+    if (rc0) return rc0;
 
     if (h->lpr_epoch != h->cfg_epoch) { h->lpr_cached = choose_lpr(h, kp); h->lpr_epoch = h->cfg_epoch; }
     const int lpr = h->lpr_cached;
@@ -642,6 +654,70 @@ int r2p2_run(r2p2_handle h, int32_t T, double delta, double delta_ctrl, int32_t 
         if (with_stage > h->smem_optin) return fail(h, R2P2_E_LIMIT, "stage planes (%zu bytes with tables) exceed shared memory", with_stage);
     }
     return dispatch_episode(h, kp, lpr, smem_stage, nullptr);
+}
+
+/* ---- controllers that run on the host: the tick in two halves --------------------------------- */
+static int bridge_ready(r2p2_handle h, const char* who) {
+    if (!h) return R2P2_E_ARG;
+    if (!h->d_wall) return fail(h, R2P2_E_ARG, "%s: no stage (call r2p2_set_stage)", who);
+    if (!h->have_robot) return fail(h, R2P2_E_ARG, "%s: no robot (call r2p2_set_robot)", who);
+    if (h->P < 1 || !h->have_reset) return fail(h, R2P2_E_ARG, "%s: population not initialised (upload genomes to size it, then r2p2_reset)", who);
+    if (h->P > h->bridge_cap || h->R != h->bridge_R) {
+        CK(cudaSetDevice(h->device));
+        CK(cudaStreamSynchronize(h->stream));
+        CK(dalloc(&h->d_sense_dst, (size_t)h->P * h->R));
+        CK(dalloc(&h->d_sense_px, (size_t)h->P * h->R * 2));
+        CK(dalloc(&h->d_cmd, (size_t)h->P * 2));
+        h->bridge_cap = h->P; h->bridge_R = h->R;
+    }
+    return R2P2_OK;
+}
+
+int r2p2_sense(r2p2_handle h, double* dst, int32_t* hitpx) {
+    int rc = bridge_ready(h, "r2p2_sense"); if (rc) return rc;
+    if (!dst) return fail(h, R2P2_E_ARG, "dst is NULL");
+    CK(cudaSetDevice(h->device));
+    SenseParams sp;
+    rc = fill_params(h, sp.k, 1, 0.0, 0.0, 0);
+    if (rc) return rc;
+    sp.dst = h->d_sense_dst; sp.hitpx = h->d_sense_px;
+    CK(cudaMemsetAsync(h->d_sense_dst, 0, (size_t)h->P * h->R * sizeof(double), h->stream));
+    CK(cudaMemsetAsync(h->d_sense_px, 0xff, (size_t)h->P * h->R * 2 * sizeof(int32_t), h->stream));
+    sense_kernel<<<(h->P + 127) / 128, 128, 0, h->stream>>>(sp);
+    h->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(dst, h->d_sense_dst, (size_t)h->P * h->R * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (hitpx) CK(cudaMemcpyAsync(hitpx, h->d_sense_px, (size_t)h->P * h->R * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return R2P2_OK;
+}
+
+int r2p2_move(r2p2_handle h, const double* commands, double delta) {
+    int rc = bridge_ready(h, "r2p2_move"); if (rc) return rc;
+    if (!commands) return fail(h, R2P2_E_ARG, "commands is NULL");
+    if (h->trace && h->trace_T < 1) return fail(h, R2P2_E_ARG, "trace enabled for 0 ticks");
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync(h->d_cmd, commands, (size_t)h->P * 2 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    KParams kp;
+    rc = fill_params(h, kp, 1, delta, 0.0, 0);
+    if (rc) return rc;
+    kp.ctrl_kind = R2P2_CTRL_CONST; kp.n_layers = 0; kp.G = 2; kp.genomes = h->d_cmd; kp.skip_sense = 1;
+    kp.maxw = std::max(1, h->R);
+    if (h->trace) {
+        if (h->trace_P != h->P || h->trace_R != h->R) return fail(h, R2P2_E_ARG, "trace buffers were sized for another population; call r2p2_set_trace again");
+        const size_t rows = (size_t)h->P;
+        CK(cudaMemsetAsync(h->tr_pose, 0, rows * 5 * sizeof(double), h->stream));
+        CK(cudaMemsetAsync(h->tr_ncoll, 0, rows * sizeof(uint32_t), h->stream));
+        CK(cudaMemsetAsync(h->tr_cinfo, 0, rows * 4 * sizeof(double), h->stream));
+        kp.tr_pose = h->tr_pose; kp.tr_dst = h->tr_dst; kp.tr_hitk = h->tr_hitk; kp.tr_hitpx = h->tr_hitpx;
+        kp.tr_nsamp = h->tr_nsamp; kp.tr_ncoll = h->tr_ncoll; kp.tr_cinfo = h->tr_cinfo;
+    }
+    // the whole warp / a pair of lanes per robot: the command is read as genome[0], genome[1] of a [P][2] array
+    const int lpr = ((long long)h->P * 32 <= (long long)h->sm_count * 512) ? 32 : 2;
+    rc = dispatch_episode(h, kp, lpr, false, nullptr);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(h->stream));     // `commands` may be pageable and reused by the caller
+    return R2P2_OK;
 }
 
 int r2p2_sync(r2p2_handle h) {

@@ -82,6 +82,7 @@ struct KParams {
     uint32_t* ndraws;                  // [P] draws consumed so far
     // trace (optional)
     double* tr_pose; double* tr_dst; int32_t* tr_hitk; int32_t* tr_hitpx; uint32_t* tr_nsamp; uint32_t* tr_ncoll;
+    int skip_sense;             // r2p2_move: the tick starts at the controller output (command in `genomes`), no sensor sweep
     double* tr_cinfo;           // [T][P][4]: collide() calls of the tick (code, wall spot x, y, border coordinate), see r2p2_read_trace_collisions
     // scheduling
     unsigned int* work_counter;
@@ -827,9 +828,9 @@ __global__ void __launch_bounds__(kBlock, (NET::kLayers > 0) ? 1 : 4) episode_ke
 
             PT(11)
             // ---- sense: Robot.check_sensors (robot.py:287-318) --------------------------------
-            bool fault = !(isfinite(x) && isfinite(y));   // round(nan) / round(inf) raise
+            bool fault = !p.skip_sense && !(isfinite(x) && isfinite(y));   // round(nan) / round(inf) raise
             const double ox = rint(x), oy = rint(y);      // Python round(): half to even
-            if (!fault) {                                 // (uniform in the group)
+            if (!fault && !p.skip_sense) {                // (uniform in the group)
                 // Rays are spread over the group: `tl` lanes per ray (team march) when the group has lanes to spare.
                 // Every lane of the group walks through the same code (lanes without a ray march a dummy one), so that
                 // the warp-level collectives inside team_march see one member mask.
@@ -1251,6 +1252,49 @@ __global__ void cast_rays_kernel(StageView sv, int plain, const double* __restri
     const Hit h = plain ? march_plain(sv, ox[i], oy[i], vc, vs, limit[i]) : march(sv, ox[i], oy[i], vc, vs, limit[i]);
     status[i] = h.fault ? -1 : (h.k >= 0 ? 1 : 0);
     hx[i] = h.x; hy[i] = h.y; kk[i] = h.k; nsamp[i] = h.nsamp;
+}
+
+// Robot.check_sensors (r2p2/robot.py:287-318) alone, for controllers that run on the host (r2p2_sense): one thread per
+// robot walks its fan in ray order -- the noise draw index of a ray is the number of unclamped rays before it -- and
+// writes the distances the controller gets.  Poses are not touched; a robot the reference would raise for gets the
+// fault flag, as in the episode kernel.
+struct SenseParams {
+    KParams k;
+    double* dst;          // [P][R]
+    int32_t* hitpx;       // [P][R][2] hit pixel or -1 (the `col` list of check_sensors), may be NULL
+};
+__global__ void sense_kernel(const __grid_constant__ SenseParams sp) {
+    const KParams& p = sp.k;
+    const unsigned rb = blockIdx.x * blockDim.x + threadIdx.x;
+    if (rb >= (unsigned)p.P) return;
+    unsigned flags = p.flags[rb];
+    if (flags & (R2P2_F_FAULT | R2P2_F_DONE)) return;
+    StageView sv;
+    sv.wall = p.g_wall; sv.lvl50 = p.g_lvl50; sv.dist = p.g_dist; sv.W = p.W; sv.H = p.H; sv.wpr = p.wpr;
+    const double x = p.x[rb], y = p.y[rb], theta = p.theta[rb];
+    bool fault = !(isfinite(x) && isfinite(y));
+    const double ox = rint(x), oy = rint(y);
+    unsigned ndraws = p.noise_mode ? p.ndraws[rb] : 0u;
+    unsigned long long ns = 0;
+    for (int i = 0; i < p.R && !fault; ++i) {
+        const SinCos sc = sincos_call(R2P2_MUL(R2P2_ADD(p.ray_deg[i], theta), kRad), p.g_sincostab);
+        if (!sc.ok) { flags |= R2P2_F_TRIGRANGE; fault = true; break; }
+        const Hit h = march(sv, ox, oy, sc.c, sc.s, p.L);
+        if (h.fault) { fault = true; break; }
+        ns += h.nsamp;
+        double d = (h.k >= 0) ? r2p2_norm2(R2P2_SUB(h.x, ox), R2P2_SUB(h.y, oy)) : r2p2_from_bits(0x7ff0000000000000ULL);
+        if ((d < p.db_hi && d > p.db_lo) || d > p.L) d = p.L;
+        else if (p.noise_mode) d = R2P2_ADD(d, noise_draw(p, rb, ndraws++));
+        sp.dst[(size_t)rb * p.R + i] = d;
+        if (sp.hitpx) {
+            sp.hitpx[((size_t)rb * p.R + i) * 2] = (h.k >= 0) ? dtrunc(h.x) : -1;
+            sp.hitpx[((size_t)rb * p.R + i) * 2 + 1] = (h.k >= 0) ? dtrunc(h.y) : -1;
+        }
+    }
+    if (fault) flags |= R2P2_F_FAULT;
+    p.flags[rb] = flags;
+    p.nsamp_sonar[rb] += ns;
+    if (p.noise_mode) p.ndraws[rb] = ndraws;
 }
 
 }  // namespace r2p2

@@ -79,6 +79,8 @@ class Robot:
     def update(self, env, delta, write_stats=False):
         """Robot.update (robot.py:389-402): sense, control, turn, move -- one fused kernel launch."""
         sim = self._ensure(env)
+        if self.controller.device_spec(sim.R) is None:
+            return self._update_host_controller(sim, delta, write_stats)
         self._push(sim)
         ctrl = self.controller
         evolve = bool(getattr(ctrl, "evolve", False))
@@ -101,6 +103,63 @@ class Robot:
         if write_stats and self._logs is not None:
             self._logs.stats(self)                          # write_stats_to_log (robot.py:158-168)
 
+    def _update_host_controller(self, sim, delta, write_stats):
+        """A controller without a device form (PID, PDDL, teleop, user classes): sensors and motion on the device,
+        ``controller.control(dst)`` on the host in between -- Robot.control / update of the reference (robot.py:373-402)
+        with the two physics halves as launches (r2p2_sense, r2p2_move)."""
+        cur = (self.x, self.y, self.orientation)
+        if self._dirty or self._mirror != cur or not getattr(self, "_host_mode", False):
+            sim.set_controller("const")
+            sim.upload_genomes(np.zeros((1, 2)))
+            sim.reset(float(self.x), float(self.y), float(self.orientation))
+            sim.set_trace(True, 1)
+            self._dirty, self._host_mode = False, True
+        if self.has_noise:
+            state = np.random.get_state()
+            draws = np.random.normal(0, 0.5, size=sim.R)
+            sim.set_noise("replay", stream=draws[None, :])
+        else:
+            sim.set_noise("off")
+        dst_row, px = sim.sense(hit_pixels=True)
+        if self.has_noise:                                  # advance numpy's global stream by what the sweep consumed
+            used = int(sim.noise_draws()[0])
+            np.random.set_state(state)
+            if used:
+                np.random.normal(0, 0.5, size=used)
+        theta_before = self.orientation
+        clamp = self.vision_range[1] + self.radius
+        dst = [clamp if float(d) == float(clamp) else float(d) for d in dst_row[0]]
+        ang = [a + theta_before for a in self._ray_angles(sim)]
+        col = [(float(p[0]), float(p[1])) for p in px[0] if p[0] >= 0]
+        ctrl = self.controller
+        if self._logs is not None:
+            self._logs.sensor_data(self.identifier, ang, theta_before, dst)
+        ctrl.handle_collision(col) if hasattr(ctrl, "handle_collision") else None
+        ctrl.set_dst(dst)
+        ctrl.set_ang(ang)
+        speed, angular_velocity = ctrl.control(dst)         # robot.py:385
+        sim.move(np.asarray([[float(speed), float(angular_velocity)]]), delta)
+        s = sim.state()
+        tr = sim.trace(1)
+        last_before = self.last_pos
+        self.x, self.y, self.orientation = float(s["x"][0]), float(s["y"][0]), float(s["theta"][0])
+        self.speed, self.angular_velocity = float(s["speed"][0]), float(s["omega"][0])
+        self.flags = int(s["flags"][0])
+        self._mirror = (self.x, self.y, self.orientation)
+        if self._logs is not None:
+            from .logs import collision_spots, format_collision
+            for spot in collision_spots(tr["cinfo"][0, 0], (sim.W, sim.H), last_before):
+                self._logs.log.write(format_collision(self.identifier, spot))
+        ncoll = int(tr["ncoll"][0, 0])
+        for _ in range(ncoll):
+            self.collide((self.x, self.y))
+        if not ncoll:
+            self.last_pos = (self.x, self.y)
+        if write_stats and self._logs is not None:
+            self._logs.stats(self)
+        if self.flags & 2:
+            raise IndexError("robot %s left the map or has a non-finite pose (the reference raises here too)" % self.identifier)
+
     # ---- plumbing --------------------------------------------------------------------------------
     def _ray_angles(self, sim):
         """Ray angles with the reference's own Python types (JSON list entries / range() ints, utils.py:465-466)."""
@@ -115,9 +174,7 @@ class Robot:
 
     def _configure_controller(self, sim):
         spec = self.controller.device_spec(sim.R)
-        if spec is None:
-            raise NotImplementedError("controller %s has no device form (supported: Neuro_controller, Inspyred_controller, "
-                                      "Naive_controller)" % type(self.controller).__name__)
+        self._host_mode = False
         sim.set_controller(spec["kind"], hidden_layer=spec["hidden_layer"], activation=spec["activation"])
         sim.upload_genomes(np.asarray([spec["genome"]], dtype=np.float64))
         self._genome_dirty = False

@@ -200,6 +200,19 @@ class BatchSim:
         self._ck(self._L.r2p2_read_trace_collisions(self._h, int(T), out["cinfo"].ctypes.data))
         return out
 
+    # ---- controllers that run on the host: the tick in two halves ----------------------------------
+    def sense(self, hit_pixels=False):
+        """Robot.check_sensors for every robot at its current pose: dst [P, R] (and the hit pixels [P, R, 2] or -1)."""
+        dst = np.empty((self.P, self.R))
+        px = np.empty((self.P, self.R, 2), dtype=np.int32) if hit_pixels else None
+        self._ck(self._L.r2p2_sense(self._h, dst.ctypes.data, px.ctypes.data if hit_pixels else None))
+        return (dst, px) if hit_pixels else dst
+
+    def move(self, commands, delta=0.1):
+        """The rest of the tick with the controllers' answers: commands [P, 2] = (speed, angular_velocity)."""
+        c = _f64(commands).reshape(self.P, 2)
+        self._ck(self._L.r2p2_move(self._h, c.ctypes.data, float(delta)))
+
     # ---- raw rays ----------------------------------------------------------------------------------
     def cast_rays(self, ox, oy, angle_rad, limit, plain=False):
         ox, oy, ang, lim = (_f64(a) for a in (ox, oy, angle_rad, limit))

@@ -96,3 +96,82 @@ def test_scenario_files_and_evolution_callback(tmp_path, oracle_port):
     assert evolution.evaluate_ann(genomes[7].tolist(), {}) == fit[7]
     assert evolution.evaluator([[0.0] * 3], {}) == [0]            # evolution.py:49-52: a failing candidate scores 0
     ev.close()
+
+
+from r2p2_b200.controller import Controller as _Controller  # noqa: E402
+
+
+class _HostLinear(_Controller):
+    """A controller the library knows nothing about (no device form): the arithmetic of the reference's
+    Inspyred_controller.control (controllers/inspyred.py:60-100) in plain Python."""
+
+    def __init__(self, chromosome):
+        super().__init__("HOST", None)
+        n = len(chromosome) // 2 - 1
+        self.lin, self.angc = list(chromosome[:n]), list(chromosome[n:2 * n])
+        self.calls = 0
+
+    def control(self, dst):
+        self.calls += 1
+        v = 0
+        w = 0
+        for coef, d in zip(self.lin, dst):
+            v += coef * d
+        for coef, d in zip(self.angc, dst):
+            w += coef * d
+        return v, w
+
+
+@pytest.mark.gpu
+def test_host_controller_bridge_reproduces_reference_episode():
+    """Robot.update with a controller that has no device form: r2p2_sense -> controller.control on the host ->
+    r2p2_move.  Same poses as the unmodified reference's run of the same linear controller (golden kat3_linear), bit
+    for bit on every tick, and the same robot logs."""
+    import json, os, tempfile
+    from r2p2_b200.robot import Robot
+    e, specs = common.episode_specs()
+    sp = next(s for s in specs if s["name"] == "kat3_linear")
+    rj = common.ROBOTS[sp["robot"]]
+    ctrl = _HostLinear([float(c) for c in e["kat3_linear/genome"]])
+    tmp = tempfile.mkdtemp()
+    r = Robot(identifier=0, x=rj["x"], y=rj["y"], orientation=rj["orientation"], max_speed=rj["max_speed"], sensors=rj["sonars"],
+              vision_range=rj["sonar_range"], radius=rj["radius"], controller=ctrl, log_dir=tmp)
+    r.has_noise = False
+    env = common.load_stage(sp["stage"])
+    T = 120
+    for t in range(T):
+        r.update(env, sp["delta"], True)
+        gp = e["kat3_linear/pose"][t]
+        assert (r.x, r.y, r.orientation, r.speed, r.angular_velocity) == tuple(gp), t
+        assert [float(d) for d in ctrl.dst] == list(e["kat3_linear/dst"][t]), t
+    assert ctrl.calls == T
+    r._logs.close()
+    with open(os.path.join(common.GOLDEN, "logs.json")) as fp:
+        g = json.load(fp)["linear_omni"]                # same robot, same chromosome, 40 ticks with write_stats
+    assert open(os.path.join(tmp, "robot_0_sensors.log")).read().startswith(g["sensors"])
+    assert open(os.path.join(tmp, "robot_0.log")).read().startswith(g["log"])
+
+
+@pytest.mark.gpu
+def test_sense_move_equal_device_controller(oracle_port):
+    """Population level: r2p2_sense + host linear algebra + r2p2_move per tick == the device's own linear controller."""
+    rj = "robot_omni.json"
+    rob = common.ROBOTS[rj]
+    P, T = 200, 60
+    genomes = np.random.RandomState(11).uniform(-1, 1, (P, 18)) * 0.06
+    ref = common.make_sim("track_2.png", rj, "linear")
+    ref.upload_genomes(genomes); ref.reset(rob["x"], rob["y"], 0.0); ref.run(T)
+    sim = common.make_sim("track_2.png", rj, "const")
+    sim.upload_genomes(np.zeros((P, 2))); sim.reset(rob["x"], rob["y"], 0.0)
+    n = 18 // 2 - 1
+    for _ in range(T):
+        dst = sim.sense()
+        v = np.zeros(P); w = np.zeros(P)
+        for i in range(n):                              # the reference's accumulation order (inspyred.py:88-93)
+            v = v + genomes[:, i] * dst[:, i]
+            w = w + genomes[:, n + i] * dst[:, i]
+        sim.move(np.stack([v, w], axis=1), 0.1)
+    a, b = sim.state(), ref.state()
+    for k in ("x", "y", "theta", "speed", "omega", "ncollide", "flags", "ticks"):
+        assert np.array_equal(a[k], b[k]), k
+    sim.close(); ref.close()
