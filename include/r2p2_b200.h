@@ -61,6 +61,7 @@ typedef struct r2p2_sim* r2p2_handle;
 #define R2P2_F_COLLIDED 1u   /* Robot.collide() was called at least once                               */
 #define R2P2_F_FAULT 2u      /* the reference would have raised (IndexError off-map, ValueError on NaN) */
 #define R2P2_F_DONE 4u       /* evolve mode: the episode ended (timer ran out or collision)             */
+#define R2P2_F_GOAL 16u      /* r2p2_set_goal: the goal predicate held after some tick                    */
 #define R2P2_F_TRIGRANGE 8u  /* heading beyond the supported sin/cos range (|radians| >= 105414350)     */
 
 /* limits */
@@ -166,6 +167,15 @@ int r2p2_read_trace(r2p2_handle h, int32_t T, double* pose, double* dst, int32_t
  * the order of robot.py:222-247 -- spot (W, b), (W, H), (W, 0), (0, b), (0, H), (0, 0), (b, H), (b, 0); bit 5: the
  * crash-radius / level-50 test fired and the robot went back to its last position, which is the spot (robot.py:249-252). */
 int r2p2_read_trace_collisions(r2p2_handle h, int32_t T, double* cinfo);
+
+/* ---- goal flagging ---------------------------------------------------------------------------- */
+/* Sequential_PID_Controller.is_at_goal (r2p2/controllers/pid_controller.py:207-213) as a per-run predicate for any
+ * controller: after every completed tick, `env[int(gx), int(gy)] is 0 or norm(goal - pos) <= radius * 1.85`.  It
+ * only sets R2P2_F_GOAL and records the tick; the dynamics never see it.  The goal pixel must be on the map
+ * (Python index rules: -W <= int(gx) < W).  enable = 0 switches it off. */
+int r2p2_set_goal(r2p2_handle h, int32_t enable, double gx, double gy);
+/* goal_tick [P]: ticks completed when the predicate first held, 0xffffffff if it never did. */
+int r2p2_read_goal(r2p2_handle h, uint32_t* goal_tick);
 
 /* ---- controllers that run on the host (any reference Controller subclass: PID, PDDL, teleop ...) ---------- */
 /* Robot.update is control() then the move (r2p2/robot.py:389-402); control() is check_sensors, the controller's

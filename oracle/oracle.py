@@ -25,7 +25,7 @@ class _Cfg(C.Structure):
                 ("ctrl_kind", C.c_int32), ("n_layers", C.c_int32), ("layers", C.c_int32 * MAX_LAYERS),
                 ("activation", C.c_int32), ("G", C.c_int32), ("evolve", C.c_int32),
                 ("delta", C.c_double), ("delta_ctrl", C.c_double), ("time_budget", C.c_double),
-                ("noise", C.c_void_p), ("noise_len", C.c_int32)]
+                ("noise", C.c_void_p), ("noise_len", C.c_int32), ("goal_on", C.c_int32), ("goal_x", C.c_double), ("goal_y", C.c_double)]
 
 
 class _Robot(C.Structure):
@@ -33,13 +33,13 @@ class _Robot(C.Structure):
                                           "odom_x", "odom_y", "origin_x", "origin_y", "time", "fitness")] + \
                [("flags", C.c_uint32), ("ncollide", C.c_uint32), ("ticks", C.c_uint32),
                 ("nsamp_sonar", C.c_uint64), ("nsamp_coll", C.c_uint64), ("npixel", C.c_uint64),
-                ("ndraws", C.c_uint32), ("pad_", C.c_uint32)]
+                ("ndraws", C.c_uint32), ("goal_tick", C.c_uint32)]
 
 
 ROBOT_DTYPE = np.dtype([(n, "<f8") for n in ("x", "y", "theta", "speed", "omega", "last_x", "last_y", "dist",
                                              "odom_x", "odom_y", "origin_x", "origin_y", "time", "fitness")] +
                        [("flags", "<u4"), ("ncollide", "<u4"), ("ticks", "<u4"), ("_pad", "<u4"),
-                        ("nsamp_sonar", "<u8"), ("nsamp_coll", "<u8"), ("npixel", "<u8"), ("ndraws", "<u4"), ("pad_", "<u4")])
+                        ("nsamp_sonar", "<u8"), ("nsamp_coll", "<u8"), ("npixel", "<u8"), ("ndraws", "<u4"), ("goal_tick", "<u4")])
 
 
 def build(force=False):
@@ -90,7 +90,7 @@ class Oracle:
 
     def run(self, env, *, rays, vr, radius, max_speed, ctrl, genomes, x0, y0, theta0, T, delta=0.1,
             layers=None, activation="tanh", evolve=False, delta_ctrl=None, time_budget=20000.0,
-            noise=None, trace=False, threads=1):
+            noise=None, trace=False, threads=1, goal=None):
         """Run P robots for T ticks.  Returns dict(state=structured array [P], plus traces [T,P,...])."""
         env = self._env(env)
         genomes = np.ascontiguousarray(genomes, dtype=np.float64)
@@ -112,6 +112,8 @@ class Oracle:
         cfg.delta = float(delta)
         cfg.delta_ctrl = float(delta if delta_ctrl is None else delta_ctrl)
         cfg.time_budget = float(time_budget)
+        if goal is not None:
+            cfg.goal_on, cfg.goal_x, cfg.goal_y = 1, float(goal[0]), float(goal[1])
         if noise is not None:
             noise = np.ascontiguousarray(noise, dtype=np.float64)
             assert noise.ndim == 2 and noise.shape[0] == P      # per-robot stream of N(0, 0.5) draws, consumed sequentially
@@ -125,6 +127,7 @@ class Oracle:
                      ("y", y0), ("last_y", y0), ("odom_y", y0), ("origin_y", y0), ("theta", th0)):
             st[f] = v
         st["time"] = cfg.time_budget
+        st["goal_tick"] = 0xFFFFFFFF
         out = {}
         ptrs = [None] * 7
         if trace:

@@ -66,6 +66,7 @@ enum { ORC_ACT_IDENTITY = 0, ORC_ACT_TANH = 1, ORC_ACT_RELU = 2, ORC_ACT_LOGISTI
 #define ORC_F_COLLIDED 1u   /* collide() was called at least once            */
 #define ORC_F_FAULT 2u      /* the reference would have raised (IndexError / ValueError / OverflowError) */
 #define ORC_F_DONE 4u       /* evolve: the episode ended (timer or collision) */
+#define ORC_F_GOAL 16u      /* the goal predicate held after some tick */
 #define ORC_F_TRIGRANGE 8u  /* |angle| beyond the supported sin/cos range (port mode only) */
 
 typedef struct {
@@ -86,6 +87,8 @@ typedef struct {
     const double* noise;       /* has_noise (robot.py:96,308-310): per-robot stream [P][noise_len] of N(0, 0.5) draws, consumed
                                   one per unclamped ray in ray order exactly as np.random.normal is called; NULL = noise off */
     int32_t noise_len;
+    int32_t goal_on;           /* goal flagging: Sequential_PID_Controller.is_at_goal (controllers/pid_controller.py:207-213) as a */
+    double goal_x, goal_y;     /* per-run predicate on the pose after each tick; a flag only, the dynamics never see it          */
 } orc_cfg;
 
 typedef struct {
@@ -98,7 +101,7 @@ typedef struct {
     uint64_t nsamp_sonar, nsamp_coll;
     uint64_t npixel;           /* every env.item() the reference would have executed */
     uint32_t ndraws;           /* noise draws consumed so far */
-    uint32_t pad_;
+    uint32_t goal_tick;        /* ticks completed when the goal predicate first held (0xffffffff: never) */
 } orc_robot;
 
 static const double ORC_RAD = 3.14159265358979323846 / 180.0;  /* CPython degToRad */
@@ -346,6 +349,14 @@ static int orc_tick(const orc_cfg* c, orc_robot* rb, const double* genome, const
     rb->theta = rb->theta + rb->omega * c->delta;
     if (!orc_move(c, rb, crx, cry, tr ? tr->cinfo : NULL)) return 0;
     rb->ticks++;
+    if (c->goal_on && !(rb->flags & ORC_F_GOAL)) {
+        /* pid_controller.py:210-213: `npdata.item((int(gx), int(gy))) is 0` or norm(goal - pos) <= radius * 1.85 */
+        int64_t gx, gy; int32_t v = 1;
+        int at = 0;
+        if (orc_pyint(c->goal_x, &gx) && orc_pyint(c->goal_y, &gy) && orc_px(c, gx, gy, &v) && v == 0) at = 1;
+        if (!at) at = orc_norm2(c->goal_x - rb->x, c->goal_y - rb->y) <= c->radius * 1.85;
+        if (at) { rb->flags |= ORC_F_GOAL; rb->goal_tick = rb->ticks; }
+    }
     return 1;
 }
 
@@ -369,6 +380,7 @@ void orc_init_robot(orc_robot* rb, double x, double y, double theta, double time
     rb->last_x = x; rb->last_y = y;
     rb->odom_x = rb->origin_x = x; rb->odom_y = rb->origin_y = y;
     rb->time = time_budget;
+    rb->goal_tick = 0xffffffffu;
 }
 
 typedef struct {

@@ -63,6 +63,8 @@ _SIGS = {
     "r2p2_set_trace": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32]),
     "r2p2_read_trace": (C.c_int, [C.c_void_p, C.c_int32] + [C.c_void_p] * 6),
     "r2p2_read_trace_collisions": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
+    "r2p2_set_goal": (C.c_int, [C.c_void_p, C.c_int32, C.c_double, C.c_double]),
+    "r2p2_read_goal": (C.c_int, [C.c_void_p, C.c_void_p]),
     "r2p2_sense": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "r2p2_move": (C.c_int, [C.c_void_p, C.c_void_p, C.c_double]),
     "r2p2_ga_create": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_uint64, C.c_double, C.c_double]),

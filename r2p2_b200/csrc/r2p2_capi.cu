@@ -26,7 +26,7 @@ struct StateArrays {
     double *x = nullptr, *y = nullptr, *theta = nullptr, *speed = nullptr, *omega = nullptr, *last_x = nullptr, *last_y = nullptr,
            *dist = nullptr, *odom_x = nullptr, *odom_y = nullptr, *origin_x = nullptr, *origin_y = nullptr, *time = nullptr,
            *fitness = nullptr;
-    uint32_t *flags = nullptr, *ncollide = nullptr, *ticks = nullptr, *ndraws = nullptr;
+    uint32_t *flags = nullptr, *ncollide = nullptr, *ticks = nullptr, *ndraws = nullptr, *goal_tick = nullptr;
     unsigned long long *nsamp_sonar = nullptr, *nsamp_coll = nullptr;
 };
 }  // namespace
@@ -83,6 +83,9 @@ struct r2p2_sim {
     // start pose / time budget of the last r2p2_reset with n == 1 (re-applied by r2p2_ga_evaluate)
     bool have_pose1 = false;
     double rx0 = 0, ry0 = 0, rt0 = 0, rbudget = 0;
+    // goal flagging
+    int goal_on = 0, goal_is_wall = 0;
+    double goal_x = 0, goal_y = 0;
     // host-controller bridge (r2p2_sense / r2p2_move)
     double* d_sense_dst = nullptr;      // [P][R]
     int32_t* d_sense_px = nullptr;      // [P][R][2]
@@ -133,7 +136,7 @@ int ensure_state(r2p2_handle h, int P) {
                       &s.origin_x, &s.origin_y, &s.time, &s.fitness, &h->d_x0, &h->d_y0, &h->d_t0};
     for (double** p : dbl) CK(dalloc(p, (size_t)P));
     CK(dalloc(&s.flags, (size_t)P)); CK(dalloc(&s.ncollide, (size_t)P)); CK(dalloc(&s.ticks, (size_t)P));
-    CK(dalloc(&s.nsamp_sonar, (size_t)P)); CK(dalloc(&s.nsamp_coll, (size_t)P)); CK(dalloc(&s.ndraws, (size_t)P));
+    CK(dalloc(&s.nsamp_sonar, (size_t)P)); CK(dalloc(&s.nsamp_coll, (size_t)P)); CK(dalloc(&s.ndraws, (size_t)P)); CK(dalloc(&s.goal_tick, (size_t)P));
     h->state_cap = P;
     h->have_reset = false;
     return R2P2_OK;
@@ -189,6 +192,7 @@ int pack_stage(r2p2_handle h, const uint8_t* d_levels, int W, int H) {
     cudaFree(d_hrow);
     h->W = W; h->H = H; h->wpr = wpr; h->has50 = has; h->plane_bytes = (uint32_t)bytes;
     h->cfg_epoch++;
+    h->goal_on = 0;                     // the goal is judged against the stage it was set on
     return R2P2_OK;
 }
 
@@ -244,13 +248,17 @@ template <int LPR, bool SMEM, class NET>
 int launch_episode(r2p2_handle h, const KParams& kp, size_t smem, int* occ_out) {
     // 2..16 lanes per robot: the warp-synchronous kernel (r2p2_kernel_ws.cuh), same results, one instruction stream per
     // warp.  R2P2_WS=0 in the environment selects the per-group kernel for A/B measurements.
+    const bool extra = kp.goal_on || kp.skip_sense;     // rarely used switches live in their own instances
     if constexpr (LPR >= 2 && LPR <= 16 && !SMEM) {
         static const bool ws = [] { const char* e = getenv("R2P2_WS"); return !(e && e[0] == '0'); }();
         // (a sonar limit without a norm window sends whole groups through the plain loop, which the lock-step kernel
         // cannot mix with groups that have stopped)
-        if (ws && !kp.skip_sense && kp.L > -1.0 && kp.L < 30000.0) return launch_kernel<LPR>(h, episode_kernel_ws<LPR, NET>, kp, smem, occ_out);
+        if (ws && !kp.skip_sense && kp.L > -1.0 && kp.L < 30000.0)
+            return extra ? launch_kernel<LPR>(h, episode_kernel_ws<LPR, NET, true>, kp, smem, occ_out)
+                         : launch_kernel<LPR>(h, episode_kernel_ws<LPR, NET, false>, kp, smem, occ_out);
     }
-    return launch_kernel<LPR>(h, episode_kernel<LPR, SMEM, NET>, kp, smem, occ_out);
+    return extra ? launch_kernel<LPR>(h, episode_kernel<LPR, SMEM, NET, true>, kp, smem, occ_out)
+                 : launch_kernel<LPR>(h, episode_kernel<LPR, SMEM, NET, false>, kp, smem, occ_out);
 }
 
 template <class NET>
@@ -365,7 +373,7 @@ int r2p2_destroy(r2p2_handle h) {
     cudaStreamSynchronize(h->stream);
     StateArrays& s = h->st;
     void* ptrs[] = {s.x, s.y, s.theta, s.speed, s.omega, s.last_x, s.last_y, s.dist, s.odom_x, s.odom_y, s.origin_x, s.origin_y,
-                    s.time, s.fitness, s.flags, s.ncollide, s.ticks, s.ndraws, s.nsamp_sonar, s.nsamp_coll, h->d_noise, h->d_x0, h->d_y0, h->d_t0,
+                    s.time, s.fitness, s.flags, s.ncollide, s.ticks, s.ndraws, s.goal_tick, s.nsamp_sonar, s.nsamp_coll, h->d_noise, h->d_x0, h->d_y0, h->d_t0,
                     h->d_wall, h->d_l50, h->d_dist, h->d_crxy, h->d_sincostab, h->d_genomes, h->d_genomes_t, h->d_work, h->d_cnt3,
                     h->d_ga_pop[0], h->d_ga_pop[1], h->d_ga_fit, h->d_ga_elite, h->d_sense_dst, h->d_sense_px, h->d_cmd};
     for (void* p : ptrs) cudaFree(p);
@@ -546,7 +554,7 @@ int r2p2_reset(r2p2_handle h, const double* x0, const double* y0, const double* 
     r.x = s.x; r.y = s.y; r.theta = s.theta; r.speed = s.speed; r.omega = s.omega; r.last_x = s.last_x; r.last_y = s.last_y;
     r.dist = s.dist; r.odom_x = s.odom_x; r.odom_y = s.odom_y; r.origin_x = s.origin_x; r.origin_y = s.origin_y;
     r.time = s.time; r.fitness = s.fitness; r.flags = s.flags; r.ncollide = s.ncollide; r.ticks = s.ticks;
-    r.nsamp_sonar = s.nsamp_sonar; r.nsamp_coll = s.nsamp_coll; r.ndraws = s.ndraws;
+    r.nsamp_sonar = s.nsamp_sonar; r.nsamp_coll = s.nsamp_coll; r.ndraws = s.ndraws; r.goal_tick = s.goal_tick;
     reset_kernel<<<(h->P + 255) / 256, 256, 0, h->stream>>>(r);
     h->launches++;
     CK(cudaGetLastError());
@@ -589,6 +597,9 @@ static int fill_params(r2p2_handle h, KParams& kp, int32_t T, double delta, doub
     if (h->noise_mode == 1 && h->noise_P != h->P) return fail(h, R2P2_E_ARG, "noise stream was uploaded for %d robots, population is %d", h->noise_P, h->P);
     kp.work_counter = h->d_work;
     kp.genomes = h->d_genomes;
+    kp.goal_on = h->goal_on; kp.goal_is_wall = h->goal_is_wall; kp.goal_x = h->goal_x; kp.goal_y = h->goal_y;
+    kp.goal_r = h->radius * 1.85;                  // pid_controller.py:213
+    kp.goal_tick = s.goal_tick;
 
     return R2P2_OK;
 }
@@ -654,6 +665,33 @@ int r2p2_run(r2p2_handle h, int32_t T, double delta, double delta_ctrl, int32_t 
         if (with_stage > h->smem_optin) return fail(h, R2P2_E_LIMIT, "stage planes (%zu bytes with tables) exceed shared memory", with_stage);
     }
     return dispatch_episode(h, kp, lpr, smem_stage, nullptr);
+}
+
+/* ---- goal flagging ---- */
+int r2p2_set_goal(r2p2_handle h, int32_t enable, double gx, double gy) {
+    if (!h) return R2P2_E_ARG;
+    if (!enable) { h->goal_on = 0; return R2P2_OK; }
+    if (!h->d_wall) return fail(h, R2P2_E_ARG, "r2p2_set_goal: no stage (call r2p2_set_stage)");
+    if (!(std::isfinite(gx) && std::isfinite(gy))) return fail(h, R2P2_E_ARG, "goal must be finite");
+    long long ix = (long long)gx, iy = (long long)gy;          // Python int(): truncation
+    if (ix < 0) ix += h->W;
+    if (iy < 0) iy += h->H;
+    if (ix < 0 || ix >= h->W || iy < 0 || iy >= h->H) return fail(h, R2P2_E_ARG, "goal pixel off the map (the reference raises IndexError)");
+    CK(cudaSetDevice(h->device));
+    uint32_t word = 0;
+    CK(cudaMemcpyAsync(&word, h->d_wall + (size_t)iy * h->wpr + (size_t)(ix >> 5), sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->goal_on = 1; h->goal_x = gx; h->goal_y = gy; h->goal_is_wall = (int)((word >> (ix & 31)) & 1u);
+    return R2P2_OK;
+}
+
+int r2p2_read_goal(r2p2_handle h, uint32_t* goal_tick) {
+    if (!h || !goal_tick) return R2P2_E_ARG;
+    if (h->P < 1) return fail(h, R2P2_E_ARG, "no population");
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync(goal_tick, h->st.goal_tick, (size_t)h->P * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return R2P2_OK;
 }
 
 /* ---- controllers that run on the host: the tick in two halves --------------------------------- */

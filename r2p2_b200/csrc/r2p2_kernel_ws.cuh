@@ -45,7 +45,7 @@ struct WGroup {
     }
 };
 
-template <int LPR, class NET>
+template <int LPR, class NET, bool EXTRA = false>
 __global__ void __launch_bounds__(kBlock, (NET::kLayers > 0) ? 1 : 4) episode_kernel_ws(const __grid_constant__ KParams p) {
     static_assert(LPR >= 2 && LPR <= 16, "warp-synchronous kernel: 2..16 lanes per robot");
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -124,6 +124,7 @@ __global__ void __launch_bounds__(kBlock, (NET::kLayers > 0) ? 1 : 4) episode_ke
             gen = dst_g;
         }
 
+        unsigned goal_tick = (EXTRA && p.goal_on) ? p.goal_tick[rb] : 0xffffffffu;
         bool alive = valid && !(flags & (R2P2_F_FAULT | R2P2_F_DONE));
         int tdone = 0;                                    // ticks completed in this launch
         unsigned ncollide0 = ncollide;
@@ -358,6 +359,9 @@ __global__ void __launch_bounds__(kBlock, (NET::kLayers > 0) ? 1 : 4) episode_ke
                 else { last_x = x; last_y = y; }
                 ticks++; tdone++;
                 if (ncollide != ncollide0) flags |= R2P2_F_COLLIDED;
+                if ((EXTRA && p.goal_on) && !(flags & R2P2_F_GOAL)) {   // Sequential_PID_Controller.is_at_goal (pid_controller.py:207-213), flag only
+                    if (p.goal_is_wall || r2p2_norm2(R2P2_SUB(p.goal_x, x), R2P2_SUB(p.goal_y, y)) <= p.goal_r) { flags |= R2P2_F_GOAL; goal_tick = ticks; }
+                }
                 if (tracing && g.sub == 0) {
                     double* q = p.tr_pose + trow * 5;
                     q[0] = x; q[1] = y; q[2] = theta; q[3] = speed; q[4] = omega;
@@ -390,6 +394,7 @@ __global__ void __launch_bounds__(kBlock, (NET::kLayers > 0) ? 1 : 4) episode_ke
             p.flags[rb] = flags; p.ncollide[rb] = ncollide; p.ticks[rb] = ticks;
             p.nsamp_sonar[rb] += ns_sonar; p.nsamp_coll[rb] += ns_coll;
             if (p.noise_mode) p.ndraws[rb] = ndraws;
+            if ((EXTRA && p.goal_on)) p.goal_tick[rb] = goal_tick;
         }
         __syncwarp();
     }

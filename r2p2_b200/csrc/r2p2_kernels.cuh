@@ -82,6 +82,10 @@ struct KParams {
     uint32_t* ndraws;                  // [P] draws consumed so far
     // trace (optional)
     double* tr_pose; double* tr_dst; int32_t* tr_hitk; int32_t* tr_hitpx; uint32_t* tr_nsamp; uint32_t* tr_ncoll;
+    int goal_on;                // goal flagging (r2p2_set_goal): predicate on the pose after each tick, a flag only
+    int goal_is_wall;           //   the goal pixel itself is a wall: the predicate always holds (pid_controller.py:210-211)
+    double goal_x, goal_y, goal_r;
+    uint32_t* goal_tick;        //   [P] ticks completed when the predicate first held, 0xffffffff = never
     int skip_sense;             // r2p2_move: the tick starts at the controller output (command in `genomes`), no sensor sweep
     double* tr_cinfo;           // [T][P][4]: collide() calls of the tick (code, wall spot x, y, border coordinate), see r2p2_read_trace_collisions
     // scheduling
@@ -726,7 +730,9 @@ struct FixedMlp<LPR, GenericNet> {
     static constexpr int kSlots = 1;
 };
 
-template <int LPR, bool SMEM_STAGE, class NET>
+// EXTRA: goal flagging / r2p2_move's skip_sense compiled in.  The plain instance is what evaluations run; keeping the
+// rarely used switches out of it is worth 2-3 % on config B (register allocation of the latency-bound chain).
+template <int LPR, bool SMEM_STAGE, class NET, bool EXTRA = false>
 __global__ void __launch_bounds__(kBlock, (NET::kLayers > 0) ? 1 : 4) episode_kernel(const __grid_constant__ KParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NR = kBlock / LPR;                      // robots in flight per CTA
@@ -816,6 +822,7 @@ __global__ void __launch_bounds__(kBlock, (NET::kLayers > 0) ? 1 : 4) episode_ke
             gen = dst_g;
         }
 
+        unsigned goal_tick = (EXTRA && p.goal_on) ? p.goal_tick[rb] : 0xffffffffu;
         PT_DECL
         int t = 0;
         unsigned ncollide0 = ncollide;
@@ -828,9 +835,9 @@ __global__ void __launch_bounds__(kBlock, (NET::kLayers > 0) ? 1 : 4) episode_ke
 
             PT(11)
             // ---- sense: Robot.check_sensors (robot.py:287-318) --------------------------------
-            bool fault = !p.skip_sense && !(isfinite(x) && isfinite(y));   // round(nan) / round(inf) raise
+            bool fault = !(EXTRA && p.skip_sense) && !(isfinite(x) && isfinite(y));   // round(nan) / round(inf) raise
             const double ox = rint(x), oy = rint(y);      // Python round(): half to even
-            if (!fault && !p.skip_sense) {                // (uniform in the group)
+            if (!fault && !(EXTRA && p.skip_sense)) {                // (uniform in the group)
                 // Rays are spread over the group: `tl` lanes per ray (team march) when the group has lanes to spare.
                 // Every lane of the group walks through the same code (lanes without a ray march a dummy one), so that
                 // the warp-level collectives inside team_march see one member mask.
@@ -1079,6 +1086,9 @@ __global__ void __launch_bounds__(kBlock, (NET::kLayers > 0) ? 1 : 4) episode_ke
             PT(7)
             ticks++;
             if (ncollide != ncollide0) flags |= R2P2_F_COLLIDED;
+            if ((EXTRA && p.goal_on) && !(flags & R2P2_F_GOAL)) {   // Sequential_PID_Controller.is_at_goal (pid_controller.py:207-213), flag only
+                if (p.goal_is_wall || r2p2_norm2(R2P2_SUB(p.goal_x, x), R2P2_SUB(p.goal_y, y)) <= p.goal_r) { flags |= R2P2_F_GOAL; goal_tick = ticks; }
+            }
             if (tracing && g.sub == 0) {
                 double* q = p.tr_pose + trow * 5;
                 q[0] = x; q[1] = y; q[2] = theta; q[3] = speed; q[4] = omega;
@@ -1108,6 +1118,7 @@ __global__ void __launch_bounds__(kBlock, (NET::kLayers > 0) ? 1 : 4) episode_ke
             p.flags[rb] = flags; p.ncollide[rb] = ncollide; p.ticks[rb] = ticks;
             p.nsamp_sonar[rb] += ns_sonar; p.nsamp_coll[rb] += ns_coll;
             if (p.noise_mode) p.ndraws[rb] = ndraws;
+            if ((EXTRA && p.goal_on)) p.goal_tick[rb] = goal_tick;
         }
         g.sync();
     }
@@ -1193,6 +1204,7 @@ __global__ void transpose_genomes_kernel(const double* __restrict__ in, double* 
 }
 
 struct ResetParams {
+    uint32_t* goal_tick;
     int P, n;
     const double *x0, *y0, *theta0;
     double time_budget;
@@ -1213,6 +1225,7 @@ __global__ void reset_kernel(const ResetParams r) {
     r.flags[i] = 0u; r.ncollide[i] = 0u; r.ticks[i] = 0u;
     r.nsamp_sonar[i] = 0ull; r.nsamp_coll[i] = 0ull;
     r.ndraws[i] = 0u;
+    r.goal_tick[i] = 0xffffffffu;
 }
 
 __global__ void sum_counters_kernel(const unsigned long long* __restrict__ a, const unsigned long long* __restrict__ b,

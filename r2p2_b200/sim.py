@@ -200,6 +200,20 @@ class BatchSim:
         self._ck(self._L.r2p2_read_trace_collisions(self._h, int(T), out["cinfo"].ctypes.data))
         return out
 
+    # ---- goal flagging ---------------------------------------------------------------------------------
+    def set_goal(self, goal=None):
+        """Per-run goal point (x, y) for the is_at_goal predicate (pid_controller.py:207-213); None switches it off."""
+        if goal is None:
+            self._ck(self._L.r2p2_set_goal(self._h, 0, 0.0, 0.0))
+        else:
+            self._ck(self._L.r2p2_set_goal(self._h, 1, float(goal[0]), float(goal[1])))
+
+    def goal_ticks(self):
+        """[P] ticks completed when each robot first satisfied the goal predicate (0xffffffff: never)."""
+        g = np.empty(self.P, dtype=np.uint32)
+        self._ck(self._L.r2p2_read_goal(self._h, g.ctypes.data))
+        return g
+
     # ---- controllers that run on the host: the tick in two halves ----------------------------------
     def sense(self, hit_pixels=False):
         """Robot.check_sensors for every robot at its current pose: dst [P, R] (and the hit pixels [P, R, 2] or -1)."""

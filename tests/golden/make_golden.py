@@ -358,9 +358,45 @@ def gen_logs(E):
         json.dump(out, fp, indent=1)
 
 
+def gen_goal(E):
+    """is_at_goal of the reference's Sequential_PID_Controller (controllers/pid_controller.py:207-213) evaluated on the pose
+    after every tick of two reference episodes, for several goal points -> tests/golden/goal.json."""
+    Scripted = make_scripted(E)
+    pid = E._import_controller("pid_controller")
+    out = {}
+
+    def run(name, stage, robot_json, ctrl, T, genome, kind, goals):
+        env = E.load_env(stage)
+        with contextlib.redirect_stdout(io.StringIO()):
+            r = E.make_robot(robot_json, ctrl)
+            probe = pid.Sequential_PID_Controller({})      # only its is_at_goal is used, on the episode's robot
+        probe.robot = r
+        E.u.npdata = env
+        hits = {str(i): [] for i in range(len(goals))}
+        for t in range(T):
+            r.update(env, 0.1, False)
+            for i, gpt in enumerate(goals):
+                probe.goal = [gpt]
+                hits[str(i)].append(bool(probe.is_at_goal()))
+        out[name] = {"stage": stage, "robot": robot_json, "kind": kind, "T": T, "genome": [float(g) for g in genome], "goals": [list(g) for g in goals],
+                     "at_goal": hits}
+        print("goal", name, {k: (v.index(True) if True in v else None) for k, v in hits.items()})
+
+    c = np.random.RandomState(7).uniform(-1, 1, 18) * 0.05
+    run("kat3_linear", "track_2.png", "robot_omni.json", E.linear_controller(c), 300, c, "linear",
+        [(200, 248), (215.5, 244.25), (230, 236), (100, 100), (193, 249), (10, 10), (229.0, 239.9)])
+    sc = Scripted(); sc.cmd = (30.0, 2.0)
+    run("kat4_const", "track_2.png", "robot-neuro.json", sc, 100, [30.0, 2.0], "const", [(300, 255), (396, 266), (405.5, 268), (0, 0)])
+    with open(os.path.join(OUT, "goal.json"), "w") as fp:
+        json.dump(out, fp)
+
+
 def main():
     E = ref_harness.RefEnv()
     try:
+        if "--goal-only" in sys.argv:
+            gen_goal(E)
+            return
         if "--logs-only" in sys.argv:
             gen_logs(E)
             return
@@ -372,6 +408,7 @@ def main():
         gen_episodes(E)
         gen_noisy_episodes(E)
         gen_logs(E)
+        gen_goal(E)
         # stage bitmaps as the reference loads them (env[x, y], int32) -- fixtures for the GPU box
         for stage in STAGES:
             env = np.ascontiguousarray(E.load_env(stage)).astype(np.uint8)

@@ -64,7 +64,8 @@ def random_case(seed):
                 activation=str(rs.choice(["tanh", "tanh", "relu", "logistic", "identity"])), genomes=genomes, x0=x0, y0=y0, th0=th0,
                 T=int(rs.choice([40, 90])), delta=float(rs.choice([0.1, 0.1, 0.5, 1.0, 2.0])), evolve=bool(rs.rand() < 0.4),
                 lprs=[int(v) for v in rs.choice([1, 2, 4, 8, 16, 32], 3, replace=False)],
-                noise=(rs.normal(0, 0.5, (P, R * int(rs.choice([40, 90])))) if rs.rand() < 0.3 else None))
+                noise=(rs.normal(0, 0.5, (P, R * int(rs.choice([40, 90])))) if rs.rand() < 0.3 else None),
+                goal=((float(rs.uniform(0, W - 1)), float(rs.uniform(0, H - 1))) if rs.rand() < 0.5 else None))
 
 
 @pytest.mark.parametrize("seed", range(160))
@@ -73,7 +74,7 @@ def test_fuzz_vs_port_oracle(seed, oracle_port):
     layers = ([len(c["rays"])] + c["hidden"] + [2]) if c["hidden"] else []
     ref = oracle_port.run(c["env"], rays=c["rays"], vr=c["vr"], radius=c["radius"], max_speed=c["max_speed"], ctrl=c["kind"], genomes=c["genomes"],
                           x0=c["x0"], y0=c["y0"], theta0=c["th0"], T=c["T"], delta=c["delta"], layers=layers, activation=c["activation"],
-                          evolve=c["evolve"], delta_ctrl=40.0, time_budget=2000.0, threads=4, noise=c["noise"])
+                          evolve=c["evolve"], delta_ctrl=40.0, time_budget=2000.0, threads=4, noise=c["noise"], goal=c["goal"])
     st = ref["state"]
     for lpr in c["lprs"] + [0]:
         sim = r2p2_b200.BatchSim(0)
@@ -84,11 +85,13 @@ def test_fuzz_vs_port_oracle(seed, oracle_port):
         sim.upload_genomes(c["genomes"])
         if c["noise"] is not None:
             sim.set_noise("replay", stream=c["noise"])     # has_noise: the reference's own draws, replayed (robot.py:308-310)
+        sim.set_goal(c["goal"])
         sim.reset(c["x0"], c["y0"], c["th0"], time_budget=2000.0)
         sim.run(c["T"], delta=c["delta"], delta_ctrl=40.0, evolve=c["evolve"])
         s, f, cnt = sim.state(), sim.fitness(), sim.counters()
         tag = (seed, lpr, c["kind"], c["hidden"], len(c["rays"]))
-        assert np.array_equal(s["flags"] & 7, st["flags"] & 7), tag
+        assert np.array_equal(s["flags"] & 23, st["flags"] & 23), tag      # collided, fault, done, goal
+        assert np.array_equal(sim.goal_ticks(), st["goal_tick"]), tag
         ok = (st["flags"] & 2) == 0                       # robots the reference keeps alive: everything bit for bit
         for k in ("x", "y", "theta", "speed", "omega", "ncollide", "ticks"):
             assert np.array_equal(s[k][ok], st[k][ok]), (k,) + tag
