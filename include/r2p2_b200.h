@@ -168,6 +168,12 @@ int r2p2_read_trace(r2p2_handle h, int32_t T, double* pose, double* dst, int32_t
  * crash-radius / level-50 test fired and the robot went back to its last position, which is the spot (robot.py:249-252). */
 int r2p2_read_trace_collisions(r2p2_handle h, int32_t T, double* cinfo);
 
+/* ---- path planner's cost grid ------------------------------------------------------------------- */
+/* path_planning.generate_grid (r2p2/path_planning.py:71-110) + Node.value (r2p2/node.py:64): the stage rasterised
+ * into div_x x div_y cells.  values [div_y][div_x]: grey level at the cell centre, 0 if the cell's block contains a
+ * wall pixel; costs: int(9 - value / 255 * 8), 1 (white) .. 9 (wall).  Either pointer may be NULL. */
+int r2p2_cost_grid(r2p2_handle h, int32_t div_x, int32_t div_y, int32_t* values, int32_t* costs);
+
 /* ---- goal flagging ---------------------------------------------------------------------------- */
 /* Sequential_PID_Controller.is_at_goal (r2p2/controllers/pid_controller.py:207-213) as a per-run predicate for any
  * controller: after every completed tick, `env[int(gx), int(gy)] is 0 or norm(goal - pos) <= radius * 1.85`.  It

@@ -143,3 +143,24 @@ class Oracle:
         out["state"] = st
         out["fitness"] = st["fitness"].copy()
         return out
+
+
+def cost_grid(env, divider):
+    """path_planning.generate_grid (r2p2/path_planning.py:71-110) + Node.value (r2p2/node.py:64), restated: returns
+    (values, costs) int32 [div_y, div_x].  The reference writes each cell's value back into its copy of the map; the
+    write-back never reaches a pixel a later cell reads (cells are visited in increasing x, y and read at or beyond their
+    own int(j*cw), int(i*ch)), so the original map decides every cell."""
+    env = np.asarray(env)
+    W, H = env.shape
+    dx, dy = (divider, divider) if np.isscalar(divider) else divider
+    cw, ch = W / dx, H / dy
+    values = np.zeros((dy, dx), dtype=np.int32)
+    for i in range(dy):
+        for j in range(dx):
+            value = int(env[int(j * cw + cw / 2), int(i * ch + ch / 2)])
+            x0, y0 = int(j * cw), int(i * ch)
+            if (env[x0:x0 + int(cw), y0:y0 + int(ch)] == 0).any():     # int(j*cw + l) == int(j*cw) + l for integer l
+                value = 0
+            values[i, j] = value
+    costs = (9 - values / 255 * 8).astype(np.int32)                    # int(): truncation, values are >= 1
+    return values, costs

@@ -45,6 +45,7 @@ struct r2p2_sim {
     uint32_t plane_bytes = 0;
     uint32_t *d_wall = nullptr, *d_l50 = nullptr;
     uint8_t* d_dist = nullptr;       // Chebyshev distance field [H][W]
+    uint8_t* d_levels = nullptr;     // grey levels env[x][y] as uploaded (path planner's cost grid)
     // robot
     bool have_robot = false;
     int R = 0;
@@ -177,6 +178,8 @@ int pack_stage(r2p2_handle h, const uint8_t* d_levels, int W, int H) {
     pack_stage_kernel<<<grid, 128, 0, h->stream>>>(d_levels, W, H, wpr, h->d_wall, h->d_l50, d_has);
     h->launches++;
     CK(cudaGetLastError());
+    CK(dalloc(&h->d_levels, (size_t)W * H));
+    CK(cudaMemcpyAsync(h->d_levels, d_levels, (size_t)W * H, cudaMemcpyDeviceToDevice, h->stream));
     // distance field (Chebyshev distance to the nearest wall / outer-ring pixel, saturated at 255)
     uint8_t* d_hrow = nullptr;
     CK(cudaMalloc(&d_hrow, (size_t)W * H));
@@ -375,7 +378,7 @@ int r2p2_destroy(r2p2_handle h) {
     void* ptrs[] = {s.x, s.y, s.theta, s.speed, s.omega, s.last_x, s.last_y, s.dist, s.odom_x, s.odom_y, s.origin_x, s.origin_y,
                     s.time, s.fitness, s.flags, s.ncollide, s.ticks, s.ndraws, s.goal_tick, s.nsamp_sonar, s.nsamp_coll, h->d_noise, h->d_x0, h->d_y0, h->d_t0,
                     h->d_wall, h->d_l50, h->d_dist, h->d_crxy, h->d_sincostab, h->d_genomes, h->d_genomes_t, h->d_work, h->d_cnt3,
-                    h->d_ga_pop[0], h->d_ga_pop[1], h->d_ga_fit, h->d_ga_elite, h->d_sense_dst, h->d_sense_px, h->d_cmd};
+                    h->d_ga_pop[0], h->d_ga_pop[1], h->d_ga_fit, h->d_ga_elite, h->d_sense_dst, h->d_sense_px, h->d_cmd, h->d_levels};
     for (void* p : ptrs) cudaFree(p);
     free_trace(h);
     cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
@@ -665,6 +668,27 @@ int r2p2_run(r2p2_handle h, int32_t T, double delta, double delta_ctrl, int32_t 
         if (with_stage > h->smem_optin) return fail(h, R2P2_E_LIMIT, "stage planes (%zu bytes with tables) exceed shared memory", with_stage);
     }
     return dispatch_episode(h, kp, lpr, smem_stage, nullptr);
+}
+
+/* ---- path planner's cost grid ---- */
+int r2p2_cost_grid(r2p2_handle h, int32_t div_x, int32_t div_y, int32_t* values, int32_t* costs) {
+    if (!h) return R2P2_E_ARG;
+    if (!h->d_levels) return fail(h, R2P2_E_ARG, "r2p2_cost_grid: no stage (call r2p2_set_stage)");
+    if (div_x < 1 || div_y < 1 || div_x > h->W || div_y > h->H) return fail(h, R2P2_E_ARG, "grid divisions must be in 1..W x 1..H");
+    if (!values && !costs) return fail(h, R2P2_E_ARG, "values and costs are both NULL");
+    CK(cudaSetDevice(h->device));
+    const size_t n = (size_t)div_x * div_y;
+    int32_t *d_v = nullptr, *d_c = nullptr;
+    CK(cudaMalloc(&d_v, n * sizeof(int32_t))); CK(cudaMalloc(&d_c, n * sizeof(int32_t)));
+    cost_grid_kernel<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(h->d_levels, h->W, h->H, div_x, div_y, d_v, d_c);
+    h->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && values) e = cudaMemcpyAsync(values, d_v, n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess && costs) e = cudaMemcpyAsync(costs, d_c, n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(d_v); cudaFree(d_c);
+    if (e != cudaSuccess) return fail(h, R2P2_E_CUDA, "r2p2_cost_grid: %s", cudaGetErrorString(e));
+    return R2P2_OK;
 }
 
 /* ---- goal flagging ---- */

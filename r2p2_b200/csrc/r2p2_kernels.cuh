@@ -243,7 +243,8 @@ __device__ __forceinline__ Hit march(const StageView& s, double ox, double oy, d
         bool wall_here = false;
         if (k < kA) {
             int ix, iy;
-            const bool inmap = fast_floor(x, ix) & fast_floor(y, iy) & ((unsigned)ix < (unsigned)s.W) & ((unsigned)iy < (unsigned)s.H);
+            const bool okx = fast_floor(x, ix), oky = fast_floor(y, iy);
+            const bool inmap = okx & oky & ((unsigned)ix < (unsigned)s.W) & ((unsigned)iy < (unsigned)s.H);
             if (inmap) d = __ldg(s.dist + (size_t)iy * s.W + ix);
             // distance 0 on an interior pixel is a wall (the only other blocked pixels are the outer ring): a hit
             wall_here = inmap & (d == 0u) & ((unsigned)(ix - 1) < (unsigned)(s.W - 2)) & ((unsigned)(iy - 1) < (unsigned)(s.H - 2));
@@ -538,10 +539,13 @@ struct Group {
         return v;
     }
     __device__ __forceinline__ unsigned min_u(unsigned v) const {
-        if (LPR == 32) return __reduce_min_sync(0xffffffffu, v);
+        if constexpr (LPR == 32) {
+            return __reduce_min_sync(0xffffffffu, v);
+        } else {
 #pragma unroll
-        for (int o = LPR / 2; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(mask, v, o, 32));
-        return v;
+            for (int o = LPR / 2; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(mask, v, o, 32));
+            return v;
+        }
     }
     __device__ __forceinline__ unsigned bcast_u(unsigned v) const { return (LPR == 1) ? v : __shfl_sync(mask, v, 0, LPR); }
 };
@@ -1265,6 +1269,31 @@ __global__ void cast_rays_kernel(StageView sv, int plain, const double* __restri
     const Hit h = plain ? march_plain(sv, ox[i], oy[i], vc, vs, limit[i]) : march(sv, ox[i], oy[i], vc, vs, limit[i]);
     status[i] = h.fault ? -1 : (h.k >= 0 ? 1 : 0);
     hx[i] = h.x; hy[i] = h.y; kk[i] = h.k; nsamp[i] = h.nsamp;
+}
+
+// Grid-cost rasterisation for the path planner: path_planning.generate_grid (r2p2/path_planning.py:71-110) + Node.value
+// (r2p2/node.py:64).  Cell (j, i) of a div_x x div_y grid takes the grey level at its centre pixel, or 0 if any pixel
+// of its int(chunk_h) x int(chunk_w) block is a wall; cost = int(9 - value / 255 * 8), the only place the reference
+// uses "darker = more expensive".  One thread per cell, same double arithmetic and truncations as the Python.
+__global__ void cost_grid_kernel(const uint8_t* __restrict__ levels, int W, int H, int div_x, int div_y,
+                                 int32_t* __restrict__ values, int32_t* __restrict__ costs) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= div_x * div_y) return;
+    const int j = c % div_x, i = c / div_x;
+    const double cw = __ddiv_rn((double)W, (double)div_x), ch = __ddiv_rn((double)H, (double)div_y);
+    const double x0 = __dmul_rn((double)j, cw), y0 = __dmul_rn((double)i, ch);
+    const int cx = __double2int_rz(__dadd_rn(x0, __ddiv_rn(cw, 2.0))), cy = __double2int_rz(__dadd_rn(y0, __ddiv_rn(ch, 2.0)));
+    int value = levels[(size_t)cx * H + cy];
+    const int nk = __double2int_rz(ch), nl = __double2int_rz(cw);
+    for (int k = 0; k < nk && value != 0; ++k) {
+        const int y = __double2int_rz(__dadd_rn(y0, (double)k));
+        for (int l = 0; l < nl; ++l) {
+            const int x = __double2int_rz(__dadd_rn(x0, (double)l));
+            if (levels[(size_t)x * H + y] == 0) { value = 0; break; }
+        }
+    }
+    values[c] = value;
+    costs[c] = __double2int_rz(__dsub_rn(9.0, __dmul_rn(__ddiv_rn((double)value, 255.0), 8.0)));
 }
 
 // Robot.check_sensors (r2p2/robot.py:287-318) alone, for controllers that run on the host (r2p2_sense): one thread per

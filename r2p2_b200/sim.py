@@ -200,6 +200,15 @@ class BatchSim:
         self._ck(self._L.r2p2_read_trace_collisions(self._h, int(T), out["cinfo"].ctypes.data))
         return out
 
+    # ---- path planner's cost grid --------------------------------------------------------------------
+    def cost_grid(self, divider):
+        """path_planning.generate_grid + Node.value for `divider` (int or [div_x, div_y]): (values, costs), both
+        int32 [div_y, div_x] (grid[i][j] of the reference)."""
+        dx, dy = (divider, divider) if np.isscalar(divider) else divider
+        v = np.empty((int(dy), int(dx)), dtype=np.int32); c = np.empty_like(v)
+        self._ck(self._L.r2p2_cost_grid(self._h, int(dx), int(dy), v.ctypes.data, c.ctypes.data))
+        return v, c
+
     # ---- goal flagging ---------------------------------------------------------------------------------
     def set_goal(self, goal=None):
         """Per-run goal point (x, y) for the is_at_goal predicate (pid_controller.py:207-213); None switches it off."""

@@ -391,9 +391,39 @@ def gen_goal(E):
         json.dump(out, fp)
 
 
+def gen_grids(E):
+    """path_planning.generate_grid + node.Node values of the reference for the shipped stages -> tests/golden/grids.npz."""
+    import importlib
+    pp = importlib.import_module("path_planning")
+    node = importlib.import_module("node")
+    out = {}
+    specs = []
+    rs = np.random.RandomState(77)                   # a stage with intermediate grey levels (the shipped ones are 0 / 255 only)
+    grey = np.full((300, 200), 255, dtype=np.int64)
+    for _ in range(60):
+        x, y = rs.randint(0, 290), rs.randint(0, 190)
+        grey[x:x + rs.randint(2, 40), y:y + rs.randint(2, 40)] = int(rs.choice([0, 30, 50, 100, 128, 200, 254]))
+    out["grey/env"] = grey.astype(np.uint8)
+    for stage in STAGES + ["grey"]:
+        env = grey if stage == "grey" else E.load_env(stage)
+        for div in (10, 25, 64, [20, 13], [7, 40]):
+            with contextlib.redirect_stdout(io.StringIO()):
+                grid, cw, ch = pp.generate_grid(env, div)
+            vals = np.asarray(grid, dtype=np.int32)
+            costs = np.asarray([[node.Node(v, (0, 0), (0, 0)).value for v in row] for row in grid], dtype=np.int32)
+            key = "%s/%s" % (stage, "x".join(map(str, div)) if isinstance(div, list) else str(div))
+            out[key + "/values"] = vals; out[key + "/costs"] = costs
+            specs.append({"key": key, "stage": stage, "divider": div})
+            print("grid", key, vals.shape, "walls", int((vals == 0).sum()), "cost levels", sorted(set(costs.ravel().tolist())))
+    np.savez_compressed(os.path.join(OUT, "grids.npz"), specs=json.dumps(specs), **out)
+
+
 def main():
     E = ref_harness.RefEnv()
     try:
+        if "--grids-only" in sys.argv:
+            gen_grids(E)
+            return
         if "--goal-only" in sys.argv:
             gen_goal(E)
             return
@@ -409,6 +439,7 @@ def main():
         gen_noisy_episodes(E)
         gen_logs(E)
         gen_goal(E)
+        gen_grids(E)
         # stage bitmaps as the reference loads them (env[x, y], int32) -- fixtures for the GPU box
         for stage in STAGES:
             env = np.ascontiguousarray(E.load_env(stage)).astype(np.uint8)
