@@ -247,21 +247,31 @@ int launch_kernel(r2p2_handle h, KERN kern, const KParams& kp, size_t smem, int*
     return R2P2_OK;
 }
 
+// 2..16 lanes per robot run the warp-synchronous kernel (r2p2_kernel_ws.cuh): same results, one instruction stream per
+// warp.  R2P2_WS=0 in the environment selects the per-group kernel for A/B measurements.  A sonar limit without a norm
+// window sends whole groups through the plain loop, which the lock-step kernel cannot mix with groups that have
+// stopped; r2p2_move's skip_sense lives in the per-group kernel only.
+bool ws_allowed(const KParams& kp) {
+    static const bool ws = [] { const char* e = getenv("R2P2_WS"); return !(e && e[0] == '0'); }();
+    return ws && !kp.skip_sense && kp.L > -1.0 && kp.L < 30000.0;
+}
+
 template <int LPR, bool SMEM, class NET>
 int launch_episode(r2p2_handle h, const KParams& kp, size_t smem, int* occ_out) {
     // 2..16 lanes per robot: the warp-synchronous kernel (r2p2_kernel_ws.cuh), same results, one instruction stream per
     // warp.  R2P2_WS=0 in the environment selects the per-group kernel for A/B measurements.
     const bool extra = kp.goal_on || kp.skip_sense;     // rarely used switches live in their own instances
     if constexpr (LPR >= 2 && LPR <= 16 && !SMEM) {
-        static const bool ws = [] { const char* e = getenv("R2P2_WS"); return !(e && e[0] == '0'); }();
-        // (a sonar limit without a norm window sends whole groups through the plain loop, which the lock-step kernel
-        // cannot mix with groups that have stopped)
-        if (ws && !kp.skip_sense && kp.L > -1.0 && kp.L < 30000.0)
+        if (ws_allowed(kp))
             return extra ? launch_kernel<LPR>(h, episode_kernel_ws<LPR, NET, true>, kp, smem, occ_out)
                          : launch_kernel<LPR>(h, episode_kernel_ws<LPR, NET, false>, kp, smem, occ_out);
     }
-    return extra ? launch_kernel<LPR>(h, episode_kernel<LPR, SMEM, NET, true>, kp, smem, occ_out)
-                 : launch_kernel<LPR>(h, episode_kernel<LPR, SMEM, NET, false>, kp, smem, occ_out);
+    if constexpr (!NET::kSmemWeights) {
+        return extra ? launch_kernel<LPR>(h, episode_kernel<LPR, SMEM, NET, true>, kp, smem, occ_out)
+                     : launch_kernel<LPR>(h, episode_kernel<LPR, SMEM, NET, false>, kp, smem, occ_out);
+    } else {
+        return fail(h, R2P2_E_ARG, "internal: shared-memory-weight instance outside the warp-synchronous kernel");
+    }
 }
 
 template <class NET>
@@ -289,6 +299,12 @@ int launch_episode_s(r2p2_handle h, KParams& kp, bool smem_stage, int* occ_out) 
             kp.w_in_smem = 0;
             return launch_episode<LPR, false, NetSimple>(h, kp, episode_smem_bytes(LPR, false, kp.plane_bytes, kp.has50, kp.maxw, 0, kp.G), occ_out);
         }
+    }
+    // 2..8 lanes with the genomes of the robots in flight in shared memory: compile-time shape, weights read from there
+    if constexpr (LPR >= 2 && LPR <= 8) if (!smem_stage && kp.w_in_smem && ws_allowed(kp)) {
+        const size_t sm = episode_smem_bytes(LPR, false, kp.plane_bytes, kp.has50, kp.maxw, 1, kp.G);
+        if (net_matches<NetNeuro>(kp)) return launch_episode<LPR, false, SmemNet<NetNeuro>>(h, kp, sm, occ_out);
+        if (net_matches<NetSimple>(kp)) return launch_episode<LPR, false, SmemNet<NetSimple>>(h, kp, sm, occ_out);
     }
     const size_t smem = episode_smem_bytes(LPR, smem_stage, kp.plane_bytes, kp.has50, kp.maxw, kp.w_in_smem, kp.G);
     return smem_stage ? launch_episode<LPR, true, GenericNet>(h, kp, smem, occ_out) : launch_episode<LPR, false, GenericNet>(h, kp, smem, occ_out);

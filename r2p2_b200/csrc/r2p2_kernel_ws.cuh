@@ -46,7 +46,7 @@ struct WGroup {
 };
 
 template <int LPR, class NET, bool EXTRA = false>
-__global__ void __launch_bounds__(kBlock, (NET::kLayers > 0) ? 1 : 4) episode_kernel_ws(const __grid_constant__ KParams p) {
+__global__ void __launch_bounds__(kBlock, (NET::kLayers > 0 && !NET::kSmemWeights) ? 1 : 4) episode_kernel_ws(const __grid_constant__ KParams p) {
     static_assert(LPR >= 2 && LPR <= 16, "warp-synchronous kernel: 2..16 lanes per robot");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NR = kBlock / LPR;                      // robots in flight per CTA
@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(kBlock, (NET::kLayers > 0) ? 1 : 4) episode_ke
         unsigned my_ns_sonar = 0u, ns_coll = 0u;
         const double* gen = p.genomes + (size_t)rb * (size_t)p.G;
         FixedMlp<LPR, NET> mlp;
-        if constexpr (NET::kLayers > 0) {
+        if constexpr (NET::kLayers > 0 && !NET::kSmemWeights) {
             mlp.load(gen, g.sub);
         } else if (p.w_in_smem) {
             double* dst_g = s_gen + (size_t)slot * p.G;
@@ -202,7 +202,8 @@ __global__ void __launch_bounds__(kBlock, (NET::kLayers > 0) ? 1 : 4) episode_ke
                     const int i = g.sub + s * LPR;
                     h[s] = (i < NET::sz(0)) ? R2P2_DIV(p.vr1, bufA[i * NR]) : 0.0;
                 }
-                mlp.forward(FULL, g.sub, h, p.activation, v, w);
+                if constexpr (NET::kSmemWeights) mlp.forward_smem(gen, FULL, g.sub, h, p.activation, v, w);
+                else mlp.forward(FULL, g.sub, h, p.activation, v, w);
                 if (v > 180.0) v = R2P2_SUB(v, 360.0);
                 __syncwarp();
             } else if (p.ctrl_kind == R2P2_CTRL_NEURO) {

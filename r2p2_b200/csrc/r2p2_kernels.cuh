@@ -636,6 +636,7 @@ __host__ __device__ inline size_t episode_smem_bytes(int lpr, bool smem_stage, u
 // The arithmetic is the generic path's (ordered FMA chain per neuron), so results are bit-identical to it.
 template <int N0, int N1, int N2, int N3, int N4>
 struct NetShape {
+    static constexpr bool kSmemWeights = false;
     static constexpr int kLayers = (N4 > 0) ? 5 : (N3 > 0) ? 4 : (N2 > 0) ? 3 : 2;       // layer sizes incl. input/output
     __host__ __device__ static constexpr int sz(int l) { return l == 0 ? N0 : l == 1 ? N1 : l == 2 ? N2 : l == 3 ? N3 : N4; }
     __host__ __device__ static constexpr int woff(int l) {       // offset of layer l's weights in the flat genome
@@ -656,6 +657,13 @@ struct NetShape {
 };
 struct GenericNet {
     static constexpr int kLayers = 0;
+    static constexpr bool kSmemWeights = false;
+};
+// Compile-time shape, weights read from the shared-memory copy of the genome instead of registers: for the mappings
+// with few lanes per robot, where register-resident weight columns would cost the occupancy the run lives on.
+template <class SHAPE>
+struct SmemNet : SHAPE {
+    static constexpr bool kSmemWeights = true;
 };
 using NetNeuro = NetShape<5, 10, 7, 4, 2>;     // conf/controller-neuro.json on robot-neuro.json (5 rays)
 using NetSimple = NetShape<5, 1, 2, 0, 0>;     // conf/controller-neuro-simple.json
@@ -697,6 +705,31 @@ struct FixedMlp {
                     const double hi = (LPR == 1) ? h[i] : __shfl_sync(mask, h[i / LPR], i % LPR, LPR);
                     if (s * LPR < NET::sz(l + 1)) acc = R2P2_FMA(hi, w[q], acc);
                     ++q;
+                }
+                hn[s] = (s * LPR < NET::sz(l + 1)) ? ((l + 2 < NET::kLayers) ? activate(activation, acc) : acc) : 0.0;
+            }
+#pragma unroll
+            for (int s = 0; s < kSlots; ++s) h[s] = hn[s];
+        }
+        out0 = (LPR == 1) ? h[0] : __shfl_sync(mask, h[0], 0, LPR);
+        out1 = (LPR == 1) ? h[1] : __shfl_sync(mask, h[(1 / LPR)], 1 % LPR, LPR);
+    }
+    // Same chains with the weights in shared memory (gs = this robot's genome copy): W_l[i][j] at gs[woff(l) + i*sz(l+1) + j],
+    // compile-time i, lane-dependent j.
+    __device__ __forceinline__ void forward_smem(const double* gs, unsigned mask, int sub, double (&h)[kSlots], int activation,
+                                                 double& out0, double& out1) const {
+#pragma unroll
+        for (int l = 0; l + 1 < NET::kLayers; ++l) {
+            double hn[kSlots];
+#pragma unroll
+            for (int s = 0; s < kSlots; ++s) {
+                const int j = sub + s * LPR;
+                const int jc = (j < NET::sz(l + 1)) ? j : 0;          // lanes without a neuron read a valid column
+                double acc = 0.0;
+#pragma unroll
+                for (int i = 0; i < NET::sz(l); ++i) {
+                    const double hi = (LPR == 1) ? h[i] : __shfl_sync(mask, h[i / LPR], i % LPR, LPR);
+                    if (s * LPR < NET::sz(l + 1)) acc = R2P2_FMA(hi, gs[NET::woff(l) + i * NET::sz(l + 1) + jc], acc);
                 }
                 hn[s] = (s * LPR < NET::sz(l + 1)) ? ((l + 2 < NET::kLayers) ? activate(activation, acc) : acc) : 0.0;
             }
