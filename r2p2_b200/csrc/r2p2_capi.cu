@@ -266,7 +266,7 @@ int launch_episode(r2p2_handle h, const KParams& kp, size_t smem, int* occ_out) 
             return extra ? launch_kernel<LPR>(h, episode_kernel_ws<LPR, NET, true>, kp, smem, occ_out)
                          : launch_kernel<LPR>(h, episode_kernel_ws<LPR, NET, false>, kp, smem, occ_out);
     }
-    if constexpr (!NET::kSmemWeights) {
+    if constexpr (!NET::kSmemWeights || LPR == 1) {
         return extra ? launch_kernel<LPR>(h, episode_kernel<LPR, SMEM, NET, true>, kp, smem, occ_out)
                      : launch_kernel<LPR>(h, episode_kernel<LPR, SMEM, NET, false>, kp, smem, occ_out);
     } else {
@@ -299,6 +299,12 @@ int launch_episode_s(r2p2_handle h, KParams& kp, bool smem_stage, int* occ_out) 
             kp.w_in_smem = 0;
             return launch_episode<LPR, false, NetSimple>(h, kp, episode_smem_bytes(LPR, false, kp.plane_bytes, kp.has50, kp.maxw, 0, kp.G), occ_out);
         }
+    }
+    // one lane per robot: compile-time shape over the transposed genome array
+    if constexpr (LPR == 1) if (!smem_stage) {
+        const size_t sm = episode_smem_bytes(1, false, kp.plane_bytes, kp.has50, kp.maxw, 0, kp.G);
+        if (net_matches<NetNeuro>(kp)) return launch_episode<1, false, SmemNet<NetNeuro>>(h, kp, sm, occ_out);
+        if (net_matches<NetSimple>(kp)) return launch_episode<1, false, SmemNet<NetSimple>>(h, kp, sm, occ_out);
     }
     // 2..8 lanes with the genomes of the robots in flight in shared memory: compile-time shape, weights read from there
     if constexpr (LPR >= 2 && LPR <= 8) if (!smem_stage && kp.w_in_smem && ws_allowed(kp)) {

@@ -762,6 +762,39 @@ struct FixedMlp {
         out1 = h[1];
     }
 };
+// One lane per robot, compile-time shape: activations in shared memory (stride NR), the neuron loop rolled, the input
+// loop unrolled so that a neuron's weight loads (coalesced over the warp's 32 robots in the transposed genome array
+// wt[q * P]) are all in flight ahead of its ordered FMA chain; one activation instance per layer.
+template <class NET, int L>
+__device__ __forceinline__ void lane_layer(const double* __restrict__ wt, size_t P, const double* hin, double* hout, int NR, int activation) {
+    constexpr int nin = NET::sz(L), nout = NET::sz(L + 1);
+    constexpr bool last = (L + 2 == NET::kLayers);
+#pragma unroll 1
+    for (int j = 0; j < nout; ++j) {
+        double wv[nin], hv[nin];
+#pragma unroll
+        for (int i = 0; i < nin; ++i) {
+            wv[i] = __ldg(wt + (size_t)(NET::woff(L) + i * nout + j) * P);
+            hv[i] = hin[i * NR];
+        }
+        double acc = 0.0;
+#pragma unroll
+        for (int i = 0; i < nin; ++i) acc = R2P2_FMA(hv[i], wv[i], acc);
+        hout[j * NR] = last ? acc : activate(activation, acc);
+    }
+}
+template <class NET>
+__device__ __forceinline__ void lane_mlp(const double* __restrict__ wt, size_t P, double* a, double* b, int NR, int activation,
+                                         double& out0, double& out1) {
+    lane_layer<NET, 0>(wt, P, a, b, NR, activation);
+    double* res = b;
+    if constexpr (NET::kLayers > 2) { lane_layer<NET, 1>(wt, P, b, a, NR, activation); res = a; }
+    if constexpr (NET::kLayers > 3) { lane_layer<NET, 2>(wt, P, a, b, NR, activation); res = b; }
+    if constexpr (NET::kLayers > 4) { lane_layer<NET, 3>(wt, P, b, a, NR, activation); res = a; }
+    out0 = res[0];
+    out1 = res[NR];
+}
+
 template <int LPR>
 struct FixedMlp<LPR, GenericNet> {
     static constexpr int kSlots = 1;
@@ -770,7 +803,7 @@ struct FixedMlp<LPR, GenericNet> {
 // EXTRA: goal flagging / r2p2_move's skip_sense compiled in.  The plain instance is what evaluations run; keeping the
 // rarely used switches out of it is worth 2-3 % on config B (register allocation of the latency-bound chain).
 template <int LPR, bool SMEM_STAGE, class NET, bool EXTRA = false>
-__global__ void __launch_bounds__(kBlock, (NET::kLayers > 0) ? 1 : 4) episode_kernel(const __grid_constant__ KParams p) {
+__global__ void __launch_bounds__(kBlock, (NET::kLayers > 0 && !NET::kSmemWeights) ? 1 : 4) episode_kernel(const __grid_constant__ KParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NR = kBlock / LPR;                      // robots in flight per CTA
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw);
@@ -850,7 +883,7 @@ __global__ void __launch_bounds__(kBlock, (NET::kLayers > 0) ? 1 : 4) episode_ke
         // the genome is read every tick for T ticks: keep it next to the SM
         const double* gen = p.genomes + (size_t)rb * (size_t)p.G;
         FixedMlp<LPR, NET> mlp;
-        if constexpr (NET::kLayers > 0) {
+        if constexpr (NET::kLayers > 0 && !NET::kSmemWeights) {
             if constexpr (LPR > 1) mlp.load(gen, g.sub);
         } else if (LPR > 1 && p.w_in_smem) {
             double* dst_g = s_gen + (size_t)slot * p.G;
@@ -953,7 +986,12 @@ __global__ void __launch_bounds__(kBlock, (NET::kLayers > 0) ? 1 : 4) episode_ke
             }
             PT(1)
             double v, w;
-            if constexpr (NET::kLayers > 0) {
+            if constexpr (NET::kSmemWeights) {            // one lane per robot, compile-time shape (capi dispatches it for LPR == 1 only)
+#pragma unroll
+                for (int i = 0; i < NET::sz(0); ++i) bufA[i * NR] = R2P2_DIV(p.vr1, bufA[i * NR]);   // 25/dst (inf when dst == 0)
+                lane_mlp<NET>(p.genomes + rb, (size_t)p.P, bufA, bufB, NR, p.activation, v, w);
+                if (v > 180.0) v = R2P2_SUB(v, 360.0);
+            } else if constexpr (NET::kLayers > 0) {
                 double h[FixedMlp<LPR, NET>::kSlots];
 #pragma unroll
                 for (int s = 0; s < FixedMlp<LPR, NET>::kSlots; ++s) {
