@@ -344,15 +344,21 @@ __global__ void __launch_bounds__(kBlock, (NET::kLayers > 0 && !NET::kSmemWeight
                     need_ring = !ring_clear;
                 }
             }
-            if (__any_sync(FULL, need_ring)) {
-                // 360 probes over the lanes of the group; the reference stops at the first wall, so an IndexError only
-                // counts if it comes before the first wall probe.  Groups that do not need the ring idle through it.
-                unsigned key = 0xffffffffu;
-                if (need_ring) key = ring_scan<LPR>(sv, g.sub, x, y, p.radius, s_crx, s_cry);
-                key = g.min_u(key);
-                if (need_ring && key != 0xffffffffu) {
-                    if (key & 1u) crash = true;
-                    else { flags |= R2P2_F_FAULT; live = false; }
+            // 360 probes; the reference stops at the first wall, so an IndexError only counts if it comes before the first
+            // wall probe (ring_scan's key).
+            {
+                // The whole warp serves one robot at a time: 12 probes per lane and one REDUX, instead of 360 / LPR probes
+                // per lane of the group while the other groups idle (8,192 robots: 12.6 -> 11.9 ms).
+                unsigned todo = __ballot_sync(FULL, need_ring && g.sub == 0);
+                while (todo) {
+                    const int leader = __ffs(todo) - 1;
+                    todo &= todo - 1u;
+                    const double rx = __shfl_sync(FULL, x, leader), ry = __shfl_sync(FULL, y, leader);
+                    const unsigned key = __reduce_min_sync(FULL, ring_scan<32>(sv, (int)lane, rx, ry, p.radius, s_crx, s_cry));
+                    if ((int)(lane & ~(unsigned)(LPR - 1)) == leader && key != 0xffffffffu) {   // the lanes of that robot's group
+                        if (key & 1u) crash = true;
+                        else { flags |= R2P2_F_FAULT; live = false; }
+                    }
                 }
             }
             if (live) {

@@ -39,6 +39,9 @@ __device__ unsigned long long g_robot_cycles[65536 * 12];   // per robot, per ph
 #define PT_FLUSH(cond)
 #endif
 
+#ifndef R2P2_RING_T
+#define R2P2_RING_T 8           // one-lane mapping: above this many rings per converged warp every lane scans its own (measured: 4, 8, 12, 16)
+#endif
 constexpr int kBlock = 128;                    // threads per CTA
 constexpr double kRad = 3.14159265358979323846 / 180.0;   // CPython math.radians multiplier
 constexpr double kDeg = 180.0 / 3.14159265358979323846;   // CPython math.degrees multiplier
@@ -439,6 +442,71 @@ __device__ __forceinline__ unsigned ring_scan(const StageView& sv, int sub, doub
                                               const double* s_crx, const double* s_cry) {
     unsigned key = 0xffffffffu;
     constexpr int kPer = (360 + LPR - 1) / LPR;
+    // The whole ring strictly inside the map (the usual case: |offset| <= |radius|): every probe index is in range and
+    // non-negative, so neither Python's index wrap nor an IndexError can occur and only the wall bit is read.
+    const double ar = r2p2_fabs(radius);
+    const bool inside = (R2P2_SUB(x, ar) >= 1.0) & (R2P2_ADD(x, ar) < (double)(sv.W - 1)) & (R2P2_SUB(y, ar) >= 1.0) & (R2P2_ADD(y, ar) < (double)(sv.H - 1));
+    if (inside) {                                          // uniform in the group
+#pragma unroll 1
+        for (int m0 = 0; m0 < kPer; m0 += 4) {
+            unsigned w[4];
+            int bx[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = sub + (m0 + u) * LPR;
+                const int ii = (i < 360) ? i : 0;
+                int ix, iy;
+                fast_floor(R2P2_ADD(x, s_crx[ii]), ix);
+                fast_floor(R2P2_ADD(y, s_cry[ii]), iy);
+                w[u] = sv.wall[iy * sv.wpr + (ix >> 5)];
+                bx[u] = ix & 31;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = sub + (m0 + u) * LPR;
+                const bool hit = (i < 360) & (((w[u] >> bx[u]) & 1u) != 0u);
+                key = min(key, hit ? (unsigned)(2 * i + 1) : 0xffffffffu);
+            }
+        }
+        return key;
+    }
+#pragma unroll 1
+    for (int m0 = 0; m0 < kPer; m0 += 4) {
+        unsigned w[4], ev[4];
+        int bx[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = sub + (m0 + u) * LPR;
+            const bool ok = i < 360;
+            const int ii = ok ? i : 0;
+            const double px = R2P2_ADD(x, s_crx[ii]), py = R2P2_ADD(y, s_cry[ii]);
+            int ix, iy;
+            if (!(fast_floor(px, ix) & fast_floor(py, iy))) {   // negative / huge / NaN: Python's int() and index wrap, exactly
+                ix = dtrunc(px); iy = dtrunc(py);
+                if (ix < 0) ix += sv.W;
+                if (iy < 0) iy += sv.H;
+            }
+            const bool f = ((unsigned)ix >= (unsigned)sv.W) | ((unsigned)iy >= (unsigned)sv.H);
+            w[u] = sv.wall[f ? 0 : (iy * sv.wpr + (ix >> 5))];
+            bx[u] = ix & 31;
+            ev[u] = !ok ? 0xffffffffu : (f ? (unsigned)(2 * i) : 0xfffffffeu);   // 0xfffffffe: decided by the bit
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = sub + (m0 + u) * LPR;
+            unsigned e = ev[u];
+            if (e == 0xfffffffeu) e = ((w[u] >> bx[u]) & 1u) ? (unsigned)(2 * i + 1) : 0xffffffffu;
+            key = min(key, e);
+        }
+    }
+    return key;
+}
+
+// The same scan with a run-time number of lanes (the lanes of a warp that happen to be converged, one-lane mapping).
+__device__ __forceinline__ unsigned ring_scan_rt(const StageView& sv, int sub, int LPR, double x, double y, double radius,
+                                                 const double* s_crx, const double* s_cry) {
+    unsigned key = 0xffffffffu;
+    const int kPer = (360 + LPR - 1) / LPR;
     // The whole ring strictly inside the map (the usual case: |offset| <= |radius|): every probe index is in range and
     // non-negative, so neither Python's index wrap nor an IndexError can occur and only the wall bit is read.
     const double ar = r2p2_fabs(radius);
@@ -1148,7 +1216,32 @@ __global__ void __launch_bounds__(kBlock, (NET::kLayers > 0 && !NET::kSmemWeight
                     if (((unsigned)cxp < (unsigned)p.W) & ((unsigned)cyp < (unsigned)p.H))
                         ring_clear = (int)__ldg(p.g_dist + (size_t)cyp * p.W + cxp) >= p.crash_clear;
                 }
-                if (!crash && !ring_clear) {
+                if constexpr (LPR == 1) {
+                    // One lane per robot: a lane alone would walk 360 probes while the rest of its warp waits.  Instead
+                    // the lanes that are at this point together (whatever robots and ticks they are on) serve the robots
+                    // among them that need the ring one after the other: 360 / n probes per lane and one REDUX each.
+                    const unsigned act = __activemask();
+                    const unsigned lane = threadIdx.x & 31u;
+                    const bool need = !crash && !ring_clear;
+                    unsigned todo = __ballot_sync(act, need);
+                    const int cnt = __popc(act), idx = __popc(act & ((1u << lane) - 1u));
+                    unsigned mykey = 0xffffffffu;
+                    if (__popc(todo) > R2P2_RING_T) {     // many of them need it: every lane scans its own ring, all in parallel
+                        if (need) mykey = ring_scan<1>(sv, 0, x, y, p.radius, s_crx, s_cry);
+                        todo = 0u;
+                    }
+                    while (todo) {
+                        const int owner = __ffs(todo) - 1;
+                        todo &= todo - 1u;
+                        const double rx = __shfl_sync(act, x, owner), ry = __shfl_sync(act, y, owner);
+                        const unsigned key = __reduce_min_sync(act, ring_scan_rt(sv, idx, cnt, rx, ry, p.radius, s_crx, s_cry));
+                        if ((int)lane == owner) mykey = key;
+                    }
+                    if (need && mykey != 0xffffffffu) {
+                        if (!(mykey & 1u)) { flags |= R2P2_F_FAULT; break; }
+                        crash = true;
+                    }
+                } else if (!crash && !ring_clear) {
                     // 360 probes spread over the group; the reference stops at the first wall, so an
                     // IndexError only counts if it comes before the first wall probe
                     const int cr = crash_ring<LPR>(sv, g, x, y, p.radius, s_crx, s_cry);
