@@ -314,6 +314,44 @@ def gen_noisy_episodes(E):
     np.savez_compressed(os.path.join(OUT, "episodes_noise.npz"), meta=meta(), specs=json.dumps(specs), **out)
 
 
+def gen_act_episodes(E):
+    """Neuro episodes with the other activations sklearn's MLP accepts (neurocontroller.py:26,117) and other layer shapes
+    -> tests/golden/episodes_act.npz."""
+    out, specs = {}, []
+    cases = [("relu_10_7_4", "track_2.png", "robot-neuro.json", [10, 7, 4], "relu", 21, 1.0, 250),
+             ("logistic_10_7_4", "track_2.png", "robot-neuro.json", [10, 7, 4], "logistic", 22, 1.0, 250),
+             ("identity_6", "stage.png", "robot-neuro.json", [6], "identity", 23, 0.2, 250),
+             ("tanh_3_3", "track.png", "robot-track.json", [3, 3], "tanh", 24, 2.0, 250),
+             ("relu_12", "stage.png", "robot.json", [12], "relu", 25, 0.7, 250),
+             ("logistic_2_9", "track_2.png", "robot-neuro.json", [2, 9], "logistic", 26, 3.0, 250)]
+    for name, stage, robot_json, hidden, act, seed, scale, T in cases:
+        sizes = [5] + hidden + [2]
+        G = sum(a * b for a, b in zip(sizes, sizes[1:]))
+        w = np.random.RandomState(seed).uniform(-1, 1, G) * scale
+        ctrl = E.neuro_controller(w, hidden, activation=act)
+        env = E.load_env(stage)
+        with contextlib.redirect_stdout(io.StringIO()):
+            r = E.make_robot(robot_json, ctrl)
+        ncol = [0]
+        orig = ctrl.on_collision
+
+        def oc(pos, orig=orig):
+            ncol[0] += 1
+            orig(pos)
+        ctrl.on_collision = oc
+        pose = np.zeros((T, 5)); dst = np.zeros((T, 5)); ncoll = np.zeros(T, dtype=np.int32)
+        for t in range(T):
+            r.update(env, 0.1, False)
+            pose[t] = (r.x, r.y, r.orientation, r.speed, r.angular_velocity)
+            dst[t] = ctrl.dst
+            ncoll[t] = ncol[0]
+        out[name + "/pose"] = pose; out[name + "/dst"] = dst; out[name + "/ncoll"] = ncoll
+        out[name + "/genome"] = w; out[name + "/fitness"] = np.float64(ctrl.fitness())
+        specs.append({"name": name, "stage": stage, "robot": robot_json, "T": T, "layers": sizes, "activation": act})
+        print("activation episode", name, "collides", ncol[0], "fitness", repr(float(ctrl.fitness())), "final", pose[-1, :3])
+    np.savez_compressed(os.path.join(OUT, "episodes_act.npz"), meta=meta(), specs=json.dumps(specs), **out)
+
+
 def gen_logs(E):
     """Log files the reference writes (robot.py:158-168, 337-352) for two short episodes -> tests/golden/logs.json."""
     Scripted = make_scripted(E)
@@ -421,6 +459,9 @@ def gen_grids(E):
 def main():
     E = ref_harness.RefEnv()
     try:
+        if "--act-only" in sys.argv:
+            gen_act_episodes(E)
+            return
         if "--grids-only" in sys.argv:
             gen_grids(E)
             return
@@ -437,6 +478,7 @@ def main():
         gen_ticks(E)
         gen_episodes(E)
         gen_noisy_episodes(E)
+        gen_act_episodes(E)
         gen_logs(E)
         gen_goal(E)
         gen_grids(E)

@@ -383,3 +383,27 @@ def test_noise_device_generator_statistics():
     assert abs(d.mean()) < 0.01 and abs(d.std() - 0.5) < 0.01
     assert abs(((d / d.std()) ** 4).mean() - 3.0) < 0.1
     assert abs(np.corrcoef(d[:-1], d[1:])[0, 1]) < 0.02
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("lpr", [1, 4, 32])
+def test_activation_episodes_golden(lpr):
+    """relu / logistic / identity networks and other layer shapes against episodes recorded from the reference."""
+    import json
+    e = common.golden("episodes_act")
+    for sp in json.loads(str(e["specs"])):
+        n = sp["name"]
+        rob = common.ROBOTS[sp["robot"]]
+        sim = common.make_sim(sp["stage"], sp["robot"], "neuro", hidden=sp["layers"][1:-1], activation=sp["activation"], lpr=lpr)
+        sim.upload_genomes(e[n + "/genome"][None, :])
+        sim.reset(rob["x"], rob["y"], 0.0)
+        sim.set_trace(True, sp["T"])
+        sim.run(sp["T"])
+        tr = sim.trace(sp["T"])
+        gp = e[n + "/pose"]
+        assert np.array_equal(np.cumsum(tr["ncoll"][:, 0]), e[n + "/ncoll"]), n
+        assert np.array_equal(np.rint(tr["dst"][:, 0]), np.rint(e[n + "/dst"])), n
+        assert np.max(np.abs(tr["pose"][:, 0, :3] - gp[:, :3]) / np.maximum(1, np.abs(gp[:, :3]))) < 1e-9, n
+        gf = float(e[n + "/fitness"])
+        assert abs(sim.fitness()[0] - gf) <= 1e-9 * max(1.0, abs(gf)), n
+        sim.close()

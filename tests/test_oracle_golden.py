@@ -138,3 +138,24 @@ def test_noisy_episodes(flavour, oracle_libm, oracle_port):
         else:
             assert np.array_equal(out["pose"][:, 0], e[n + "/pose"]), n
             assert np.array_equal(out["dst"][:, 0], e[n + "/dst"]), n
+
+
+@pytest.mark.parametrize("flavour", ["libm", "port"])
+def test_activation_episodes(flavour, oracle_libm, oracle_port):
+    """The other activations sklearn's MLP accepts (relu, logistic, identity) and other layer shapes, recorded from the
+    reference (tests/golden/episodes_act.npz): same hit step on every ray of every tick, same collisions, poses and
+    fitness to 1e-9 (BLAS summation order / SIMD exp of the reference are only restated to the ulp)."""
+    import json
+    O = oracle_libm if flavour == "libm" else oracle_port
+    e = common.golden("episodes_act")
+    for sp in json.loads(str(e["specs"])):
+        n = sp["name"]
+        rob = common.ROBOTS[sp["robot"]]
+        out = O.run(common.load_stage(sp["stage"]), ctrl="neuro", genomes=e[n + "/genome"][None, :], x0=rob["x"], y0=rob["y"], theta0=0.0,
+                    T=sp["T"], layers=sp["layers"], activation=sp["activation"], trace=True, **common.oracle_robot_kwargs(sp["robot"]))
+        gp = e[n + "/pose"]
+        assert np.array_equal(np.cumsum(out["ncoll"][:, 0]), e[n + "/ncoll"]), n
+        assert np.array_equal(np.rint(out["dst"][:, 0]), np.rint(e[n + "/dst"])), n
+        assert np.max(np.abs(out["pose"][:, 0, :3] - gp[:, :3]) / np.maximum(1, np.abs(gp[:, :3]))) < 1e-9, n
+        gf = float(e[n + "/fitness"])
+        assert abs(out["fitness"][0] - gf) <= 1e-9 * max(1.0, abs(gf)), n
