@@ -153,6 +153,16 @@ int r2p2_fitness_device(r2p2_handle h, double** d_fitness);
 /* Kernels launched by this handle since creation (every one is ours; no library kernels are used). */
 int r2p2_launch_count(r2p2_handle h, uint64_t* n);
 
+/* ---- checkpoint / resume ------------------------------------------------------------------------ */
+/* Everything a running episode carries between launches (pose, last position, odometry, controller timer, fitness,
+ * flags, collision / tick / noise-draw counters, sample counters, goal ticks) as one opaque host blob of
+ * r2p2_state_bytes; loading it into a handle with the same population size, stage, robot and genomes continues the
+ * episode bit for bit.  (The reference keeps all of this in Robot / Controller attributes, r2p2/robot.py:63-97,
+ * r2p2/controllers/neurocontroller.py:27-33,100-104.) */
+int r2p2_state_bytes(r2p2_handle h, uint64_t* bytes);
+int r2p2_save_state(r2p2_handle h, void* blob);
+int r2p2_load_state(r2p2_handle h, const void* blob);
+
 /* ---- per-tick trace (parity tests, Robot.update facade) -------------------------------------- */
 /* Enable recording for the next runs: up to T_max ticks per run, layouts [T][P][...]. */
 int r2p2_set_trace(r2p2_handle h, int32_t enable, int32_t T_max);

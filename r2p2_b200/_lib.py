@@ -63,6 +63,9 @@ _SIGS = {
     "r2p2_set_trace": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32]),
     "r2p2_read_trace": (C.c_int, [C.c_void_p, C.c_int32] + [C.c_void_p] * 6),
     "r2p2_read_trace_collisions": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
+    "r2p2_state_bytes": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
+    "r2p2_save_state": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "r2p2_load_state": (C.c_int, [C.c_void_p, C.c_void_p]),
     "r2p2_cost_grid": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "r2p2_set_goal": (C.c_int, [C.c_void_p, C.c_int32, C.c_double, C.c_double]),
     "r2p2_read_goal": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -848,6 +848,49 @@ int r2p2_read_state(r2p2_handle h, double* x, double* y, double* theta, double* 
     return R2P2_OK;
 }
 
+/* ---- checkpoint / resume of the population's episode state ---- */
+/* every per-robot array the episode kernel carries between launches, in blob order */
+static int copy_state(r2p2_handle h, char* blob, bool to_host) {
+    StateArrays& s = h->st;
+    const size_t P = (size_t)h->P;
+    struct Arr { void* d; size_t n; };
+    const Arr arrs[] = {
+        {s.x, 8 * P}, {s.y, 8 * P}, {s.theta, 8 * P}, {s.speed, 8 * P}, {s.omega, 8 * P}, {s.last_x, 8 * P}, {s.last_y, 8 * P},
+        {s.dist, 8 * P}, {s.odom_x, 8 * P}, {s.odom_y, 8 * P}, {s.origin_x, 8 * P}, {s.origin_y, 8 * P}, {s.time, 8 * P}, {s.fitness, 8 * P},
+        {s.nsamp_sonar, 8 * P}, {s.nsamp_coll, 8 * P},
+        {s.flags, 4 * P}, {s.ncollide, 4 * P}, {s.ticks, 4 * P}, {s.ndraws, 4 * P}, {s.goal_tick, 4 * P}};
+    size_t off = 0;
+    for (const Arr& a : arrs) {
+        if (to_host) CK(cudaMemcpyAsync(blob + off, a.d, a.n, cudaMemcpyDeviceToHost, h->stream));
+        else CK(cudaMemcpyAsync(a.d, blob + off, a.n, cudaMemcpyHostToDevice, h->stream));
+        off += a.n;
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    return R2P2_OK;
+}
+
+int r2p2_state_bytes(r2p2_handle h, uint64_t* bytes) {
+    if (!h || !bytes) return R2P2_E_ARG;
+    *bytes = (uint64_t)h->P * (16 * 8 + 5 * 4);
+    return R2P2_OK;
+}
+
+int r2p2_save_state(r2p2_handle h, void* blob) {
+    if (!h || !blob) return R2P2_E_ARG;
+    if (h->P < 1 || !h->have_reset) return fail(h, R2P2_E_ARG, "r2p2_save_state: population not initialised");
+    CK(cudaSetDevice(h->device));
+    return copy_state(h, (char*)blob, true);
+}
+
+int r2p2_load_state(r2p2_handle h, const void* blob) {
+    if (!h || !blob) return R2P2_E_ARG;
+    if (h->P < 1) return fail(h, R2P2_E_ARG, "r2p2_load_state: no population (upload genomes first)");
+    CK(cudaSetDevice(h->device));
+    const int rc = copy_state(h, (char*)blob, false);
+    if (rc == R2P2_OK) h->have_reset = true;
+    return rc;
+}
+
 int r2p2_read_counters(r2p2_handle h, uint64_t* sonar_samples, uint64_t* collision_samples, uint64_t* robot_steps) {
     if (!h) return R2P2_E_ARG;
     if (h->P < 1) return fail(h, R2P2_E_ARG, "no population");

@@ -200,6 +200,25 @@ class BatchSim:
         self._ck(self._L.r2p2_read_trace_collisions(self._h, int(T), out["cinfo"].ctypes.data))
         return out
 
+    # ---- checkpoint / resume ---------------------------------------------------------------------------
+    def save_state(self):
+        """Opaque snapshot (bytes) of everything the running episodes carry between launches."""
+        import ctypes as C
+        n = C.c_uint64()
+        self._ck(self._L.r2p2_state_bytes(self._h, C.byref(n)))
+        blob = np.empty(n.value, dtype=np.uint8)
+        self._ck(self._L.r2p2_save_state(self._h, blob.ctypes.data))
+        return blob.tobytes()
+
+    def load_state(self, blob):
+        b = np.frombuffer(blob, dtype=np.uint8)
+        import ctypes as C
+        n = C.c_uint64()
+        self._ck(self._L.r2p2_state_bytes(self._h, C.byref(n)))
+        if b.size != n.value:
+            raise ValueError("snapshot of %d bytes does not fit a population of %d robots (%d bytes)" % (b.size, self.P, n.value))
+        self._ck(self._L.r2p2_load_state(self._h, b.ctypes.data))
+
     # ---- path planner's cost grid --------------------------------------------------------------------
     def cost_grid(self, divider):
         """path_planning.generate_grid + Node.value for `divider` (int or [div_x, div_y]): (values, costs), both

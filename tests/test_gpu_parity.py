@@ -407,3 +407,37 @@ def test_activation_episodes_golden(lpr):
         gf = float(e[n + "/fitness"])
         assert abs(sim.fitness()[0] - gf) <= 1e-9 * max(1.0, abs(gf)), n
         sim.close()
+
+
+@pytest.mark.gpu
+def test_checkpoint_resume_is_bit_exact():
+    """save_state after 120 ticks, finish the episode, load the snapshot into a fresh handle, finish again: same bits
+    (poses, fitness, flags, counters, noise draws), with evolve semantics and replayed noise on."""
+    rj = "robot-neuro.json"
+    rob = common.ROBOTS[rj]
+    P = 300
+    genomes = np.random.RandomState(77).uniform(-1, 1, (P, 156))
+    noise = np.random.RandomState(78).normal(0, 0.5, (P, 5 * 400))
+
+    def fresh():
+        sim = common.make_sim("track_2.png", rj, "neuro", hidden=[10, 7, 4])
+        sim.upload_genomes(genomes)
+        sim.set_noise("replay", stream=noise)
+        sim.set_goal((240.0, 252.0))
+        return sim
+    a = fresh()
+    a.reset(rob["x"], rob["y"], 0.0, time_budget=30000.0)
+    a.run(120, delta_ctrl=100.0, evolve=True)
+    snap = a.save_state()
+    a.run(280, delta_ctrl=100.0, evolve=True)
+    b = fresh()
+    b.load_state(snap)
+    b.run(280, delta_ctrl=100.0, evolve=True)
+    sa, sb = a.state(), b.state()
+    for k in sa:
+        assert np.array_equal(sa[k], sb[k]), k
+    assert np.array_equal(a.fitness(), b.fitness()) and a.counters() == b.counters()
+    assert np.array_equal(a.noise_draws(), b.noise_draws()) and np.array_equal(a.goal_ticks(), b.goal_ticks())
+    with pytest.raises(ValueError):
+        b.load_state(snap[:-8])
+    a.close(); b.close()
