@@ -3,6 +3,8 @@
 oracle -- bit for bit.  The shipped stages keep robots 13+ pixels away from the map border; these cases drive the
 paths they never reach: Python index wrap and IndexError in the crash ring, rays leaving the map, border collisions,
 robots starting inside walls, knife-edge limits."""
+import os
+
 import numpy as np
 import pytest
 
@@ -68,7 +70,7 @@ def random_case(seed):
                 goal=((float(rs.uniform(0, W - 1)), float(rs.uniform(0, H - 1))) if rs.rand() < 0.5 else None))
 
 
-@pytest.mark.parametrize("seed", range(160))
+@pytest.mark.parametrize("seed", range(int(os.environ.get("R2P2_FUZZ_CASES", "160"))))     # soak runs: R2P2_FUZZ_CASES=4000
 def test_fuzz_vs_port_oracle(seed, oracle_port):
     c = random_case(1000 + seed)
     layers = ([len(c["rays"])] + c["hidden"] + [2]) if c["hidden"] else []
