@@ -441,3 +441,22 @@ def test_checkpoint_resume_is_bit_exact():
     with pytest.raises(ValueError):
         b.load_state(snap[:-8])
     a.close(); b.close()
+
+
+@pytest.mark.gpu
+def test_sharding_invariance():
+    """SURVEY 8e result check: the fitness vector does not depend on how the population is cut into shards (the automatic
+    lane mapping changes with the shard size: 4 096 robots -> 8 lanes, 1 024 -> 32, 512 -> 32), so N = 1, 2, 4, 8 GPUs give
+    bit-identical generations."""
+    from r2p2_b200.evaluator import PopulationEvaluator
+    from r2p2_b200.distributed import shard_bounds
+    rob = common.ROBOTS["robot-neuro.json"]
+    P, T = 4096, 200
+    genomes = np.random.RandomState(5).uniform(-1, 1, (P, 156))
+    ev = PopulationEvaluator(common.load_stage("stage.png"), sonar_range=rob["sonar_range"], radius=rob["radius"], max_speed=rob["max_speed"],
+                             sonars=rob["sonars"], controller="neuro", hidden_layer=[10, 7, 4], x=rob["x"], y=rob["y"], ticks=T,
+                             delta_ctrl=100.0, time_budget=15000.0, evolve=True)
+    full = ev.evaluate(genomes).copy()
+    for world in (2, 4, 8):
+        parts = [ev.evaluate(genomes[lo:hi]).copy() for lo, hi in (shard_bounds(P, world, r) for r in range(world))]
+        assert np.array_equal(np.concatenate(parts), full), world
