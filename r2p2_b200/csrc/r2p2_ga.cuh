@@ -10,9 +10,8 @@
 //
 // Every random number is a pure function of (seed, generation, individual, gene, purpose) through Philox4x32-10, so
 // the result does not depend on the launch geometry, every GPU of a multi-GPU run breeds the same next generation
-// from the all-gathered fitness without exchanging genomes, and the host restatement in r2p2_b200/ea.py
-// (philox4x32, breed_host) reproduces it: selection and crossover bit for bit, mutated genes to the last ulps of
-// log / cospi.
+// from the all-gathered fitness without exchanging genomes, and a numpy restatement kept with the test infrastructure
+// reproduces it: selection and crossover bit for bit, mutated genes to the last ulps of log / cospi.
 #pragma once
 
 #include <stdint.h>
