@@ -46,6 +46,9 @@ struct r2p2_sim {
     uint32_t *d_wall = nullptr, *d_l50 = nullptr;
     uint8_t* d_dist = nullptr;       // Chebyshev distance field [H][W]
     uint8_t* d_levels = nullptr;     // grey levels env[x][y] as uploaded (path planner's cost grid)
+    uint32_t* d_hot = nullptr;       // padded event plane of the marches (r2p2_kernels.cuh: hot_word / hot_shift), built lazily
+    int hot_pad = 0, hot_wpr = 0, hot_rows = 0;
+    uint64_t stage_epoch = 0, hot_epoch = 0;
     // robot
     bool have_robot = false;
     int R = 0;
@@ -195,7 +198,36 @@ int pack_stage(r2p2_handle h, const uint8_t* d_levels, int W, int H) {
     cudaFree(d_hrow);
     h->W = W; h->H = H; h->wpr = wpr; h->has50 = has; h->plane_bytes = (uint32_t)bytes;
     h->cfg_epoch++;
+    h->stage_epoch++;
     h->goal_on = 0;                     // the goal is judged against the stage it was set on
+    return R2P2_OK;
+}
+
+// The marches' event plane: the map plus a margin wide enough for every sonar ray of this robot (limit + the overshoot
+// of the unrolled walk), rebuilt when the stage or the margin changes.  Collision rays are short (speed * delta +
+// radius); one that would not fit the margin takes the exact loop.  No plane above a 1024-pixel margin.
+int ensure_hot(r2p2_handle h, double delta) {
+    const double L = h->vr1 + h->radius;
+    int kB = 16;
+    if (L > -1.0 && L < 30000.0) kB = std::max(kB, (int)std::ceil(L + 1e-6));
+    const double climit = std::fabs(h->max_speed * delta) + std::fabs(h->radius);
+    int half = kB + 34;                                    // see window_geometry: the widest team walks 32 samples per pass
+    if (climit < 4096.0) half = std::max(half, (int)std::ceil(climit + 1e-6) + 22);
+    int pad = ((half + 8 + 96 + 31) / 32) * 32;
+    if (h->d_hot && h->hot_epoch == h->stage_epoch && h->hot_pad >= pad && h->hot_pad <= 2 * pad + 64) return R2P2_OK;   // (a wider margin from an earlier run is as good)
+    if (pad > 2048) {
+        if (h->d_hot) { CK(cudaStreamSynchronize(h->stream)); cudaFree(h->d_hot); h->d_hot = nullptr; }
+        h->hot_pad = 0; h->hot_epoch = h->stage_epoch;
+        return R2P2_OK;
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    const int hwpr = ((h->W + 2 * pad + 7) / 8 + 3) / 4 * 4, hrows = (h->H + 2 * pad + 3) / 4;
+    CK(dalloc(&h->d_hot, (size_t)hwpr * hrows));
+    hot_plane_kernel<<<dim3((hwpr + 127) / 128, hrows), 128, 0, h->stream>>>(h->d_levels, h->W, h->H, pad, hwpr, hrows, h->d_hot);
+    h->launches++;
+    CK(cudaGetLastError());
+    h->hot_pad = pad; h->hot_wpr = hwpr; h->hot_rows = hrows; h->hot_epoch = h->stage_epoch;
+    h->cfg_epoch++;
     return R2P2_OK;
 }
 
@@ -253,7 +285,28 @@ int launch_kernel(r2p2_handle h, KERN kern, const KParams& kp, size_t smem, int*
 // stopped; r2p2_move's skip_sense lives in the per-group kernel only.
 bool ws_allowed(const KParams& kp) {
     static const bool ws = [] { const char* e = getenv("R2P2_WS"); return !(e && e[0] == '0'); }();
-    return ws && !kp.skip_sense && kp.L > -1.0 && kp.L < 30000.0;
+    return ws && !kp.skip_sense && kp.L > -1.0 && kp.L < 30000.0 && kp.g_hot && kp.win_ww > 0;
+}
+
+// Window geometry of the warp-synchronous kernel for `lpr` lanes per robot (same numbers as the kernel: sonar team size,
+// own samples per pass).  half = the farthest pixel, counted from the sonar origin, a fast march of the tick can read.
+void window_geometry(KParams& kp, int lpr) {
+    kp.win_ww = kp.win_wb = kp.win_half = kp.win_slack = 0;
+    static const bool no_win = [] { const char* e = getenv("R2P2_NO_WIN"); return e && e[0] == '1'; }();   // A/B measurements
+    if (lpr < 2 || lpr > 16 || !kp.g_hot || no_win || !(kp.L > -1.0 && kp.L < 30000.0)) return;
+    int tl = 1;
+    while (tl * 2 * kp.R <= lpr && tl < kMaxSonarTeam) tl *= 2;
+    const int own_s = sonar_nown(tl, lpr <= 2 ? 8 : 4), own_c = (lpr >= 16 ? 1 : lpr >= 8 ? 2 : 4);
+    const int kB_s = (int)std::ceil(kp.L + 1e-6);
+    const double climit = std::fabs(kp.max_speed * kp.delta) + std::fabs(kp.radius);
+    if (!(climit < 4096.0)) return;
+    const int kB_c = (int)std::ceil(climit + 1e-6) + 1;
+    const int half = std::max(std::max(kB_s + tl * own_s + 1, kB_c + lpr * own_c + 3), (int)std::ceil(std::fabs(kp.radius)) + 4) + 1;
+    const int slack = 8;                                   // a fetched window is kept until the robot has moved this far
+    const int ww = (((2 * (half + slack) + 32 + 7) / 8) + 3) / 4 * 4, wb = (2 * (half + slack) + 4 + 3) / 4;
+    if (half + slack + 96 > kp.hpad) return;                                             // the window must stay inside the plane's margin
+    if ((size_t)(kBlock / lpr) * ww * wb * 4 > 64 * 1024) return;                 // too fat: the per-group kernel reads the plane through L1
+    kp.win_ww = ww; kp.win_wb = wb; kp.win_half = half; kp.win_slack = slack;
 }
 
 template <int LPR, bool SMEM, class NET>
@@ -293,11 +346,11 @@ int launch_episode_s(r2p2_handle h, KParams& kp, bool smem_stage, int* occ_out) 
     if constexpr (LPR >= 16) if (!smem_stage) {
         if (net_matches<NetNeuro>(kp)) {
             kp.w_in_smem = 0;
-            return launch_episode<LPR, false, NetNeuro>(h, kp, episode_smem_bytes(LPR, false, kp.plane_bytes, kp.has50, kp.maxw, 0, kp.G), occ_out);
+            return launch_episode<LPR, false, NetNeuro>(h, kp, episode_smem_bytes(LPR, false, kp.plane_bytes, kp.has50, kp.maxw, 0, kp.G, kp.win_ww * kp.win_wb), occ_out);
         }
         if (net_matches<NetSimple>(kp)) {
             kp.w_in_smem = 0;
-            return launch_episode<LPR, false, NetSimple>(h, kp, episode_smem_bytes(LPR, false, kp.plane_bytes, kp.has50, kp.maxw, 0, kp.G), occ_out);
+            return launch_episode<LPR, false, NetSimple>(h, kp, episode_smem_bytes(LPR, false, kp.plane_bytes, kp.has50, kp.maxw, 0, kp.G, kp.win_ww * kp.win_wb), occ_out);
         }
     }
     // one lane per robot: compile-time shape over the transposed genome array
@@ -306,21 +359,33 @@ int launch_episode_s(r2p2_handle h, KParams& kp, bool smem_stage, int* occ_out) 
         if (net_matches<NetNeuro>(kp)) return launch_episode<1, false, SmemNet<NetNeuro>>(h, kp, sm, occ_out);
         if (net_matches<NetSimple>(kp)) return launch_episode<1, false, SmemNet<NetSimple>>(h, kp, sm, occ_out);
     }
-    // 2..8 lanes with the genomes of the robots in flight in shared memory: compile-time shape, weights read from there
-    if constexpr (LPR >= 2 && LPR <= 8) if (!smem_stage && kp.w_in_smem && ws_allowed(kp)) {
-        const size_t sm = episode_smem_bytes(LPR, false, kp.plane_bytes, kp.has50, kp.maxw, 1, kp.G);
+    // 2..8 lanes: compile-time shape, weights read through one pointer per robot -- its genome's copy in shared memory
+    // when the robots in flight fit there (w_in_smem), else the [P][G] array itself (L1/L2)
+    if constexpr (LPR >= 2 && LPR <= 8) if (!smem_stage && ws_allowed(kp)) {
+        const size_t sm = episode_smem_bytes(LPR, false, kp.plane_bytes, kp.has50, kp.maxw, kp.w_in_smem, kp.G, kp.win_ww * kp.win_wb);
         if (net_matches<NetNeuro>(kp)) return launch_episode<LPR, false, SmemNet<NetNeuro>>(h, kp, sm, occ_out);
         if (net_matches<NetSimple>(kp)) return launch_episode<LPR, false, SmemNet<NetSimple>>(h, kp, sm, occ_out);
+        if constexpr (LPR >= 4) if (net_matches<NetSweep>(kp) && !(kp.goal_on || kp.skip_sense))
+            return launch_kernel<LPR>(h, episode_kernel_ws<LPR, SmemNet<NetSweep>, false>, kp, sm, occ_out);
     }
-    const size_t smem = episode_smem_bytes(LPR, smem_stage, kp.plane_bytes, kp.has50, kp.maxw, kp.w_in_smem, kp.G);
+    const size_t smem = episode_smem_bytes(LPR, smem_stage, kp.plane_bytes, kp.has50, kp.maxw, kp.w_in_smem, kp.G, kp.win_ww * kp.win_wb);
     return smem_stage ? launch_episode<LPR, true, GenericNet>(h, kp, smem, occ_out) : launch_episode<LPR, false, GenericNet>(h, kp, smem, occ_out);
 }
 
 // genomes of the robots in flight live in shared memory when the group mapping leaves room for them
-int w_in_smem_for(int lpr, int G) { return (lpr > 1 && (size_t)(kBlock / lpr) * G * 8 <= 48 * 1024) ? 1 : 0; }
+int w_in_smem_for(int lpr, int G) {
+    // R2P2_WSMEM_KB (experiments): largest genome block a CTA may hold in shared memory; two CTAs per SM must still fit
+    static const size_t lim = [] { const char* e = getenv("R2P2_WSMEM_KB"); return (size_t)(e ? atoi(e) : 48) * 1024; }();
+    return (lpr > 1 && (size_t)(kBlock / lpr) * G * 8 <= lim) ? 1 : 0;
+}
 
 int dispatch_episode(r2p2_handle h, KParams& kp, int lpr, bool smem_stage, int* occ_out) {
     kp.w_in_smem = w_in_smem_for(lpr, kp.G);
+    window_geometry(kp, lpr);
+    // four CTAs per SM (what the register budget allows) need <= ~55 KB each: the windows come first, the genomes of the
+    // robots in flight stay in shared memory only if both fit (else they are read through L1/L2)
+    if (kp.w_in_smem && kp.win_ww && episode_smem_bytes(lpr, false, kp.plane_bytes, kp.has50, kp.maxw, 1, kp.G, kp.win_ww * kp.win_wb) > 55 * 1024)
+        kp.w_in_smem = 0;
     switch (lpr) {
         case 1: return launch_episode_s<1>(h, kp, smem_stage, occ_out);
         case 2: return launch_episode_s<2>(h, kp, smem_stage, occ_out);
@@ -343,8 +408,9 @@ int choose_lpr(r2p2_handle h, const KParams& kp) {
         const long long ctas = ((long long)h->P * lpr + kBlock - 1) / kBlock;
         if (ctas <= (long long)occ * h->sm_count) return lpr;
     }
-    // many rays per robot (config E: 32 rays, 262144 robots): two lanes per robot split the ray fan (1.42 s vs 2.24 s)
-    return h->R >= 16 ? 2 : 1;
+    // more robots than fit at once.  Many rays per robot (config E: 32 rays, 262144 robots): eight lanes split the fan, the
+    // windows of the robots in flight fit shared memory (measured, 200 ticks: 8 lanes 134 ms, 4 lanes 150, 16 lanes 185)
+    return h->R >= 16 ? 8 : 1;
 }
 
 }  // namespace
@@ -400,7 +466,7 @@ int r2p2_destroy(r2p2_handle h) {
     void* ptrs[] = {s.x, s.y, s.theta, s.speed, s.omega, s.last_x, s.last_y, s.dist, s.odom_x, s.odom_y, s.origin_x, s.origin_y,
                     s.time, s.fitness, s.flags, s.ncollide, s.ticks, s.ndraws, s.goal_tick, s.nsamp_sonar, s.nsamp_coll, h->d_noise, h->d_x0, h->d_y0, h->d_t0,
                     h->d_wall, h->d_l50, h->d_dist, h->d_crxy, h->d_sincostab, h->d_genomes, h->d_genomes_t, h->d_work, h->d_cnt3,
-                    h->d_ga_pop[0], h->d_ga_pop[1], h->d_ga_fit, h->d_ga_elite, h->d_sense_dst, h->d_sense_px, h->d_cmd, h->d_levels};
+                    h->d_ga_pop[0], h->d_ga_pop[1], h->d_ga_fit, h->d_ga_elite, h->d_sense_dst, h->d_sense_px, h->d_cmd, h->d_levels, h->d_hot};
     for (void* p : ptrs) cudaFree(p);
     free_trace(h);
     cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
@@ -594,6 +660,12 @@ static int fill_params(r2p2_handle h, KParams& kp, int32_t T, double delta, doub
     kp.W = h->W; kp.H = h->H; kp.wpr = h->wpr; kp.has50 = h->has50;
     kp.g_wall = h->d_wall; kp.g_lvl50 = h->d_l50; kp.plane_bytes = h->plane_bytes;
     kp.g_dist = h->d_dist;
+    {
+        const int rc = ensure_hot(h, delta);
+        if (rc) return rc;
+        static const bool no_hot = [] { const char* e = getenv("R2P2_NO_HOT"); return e && e[0] == '1'; }();   // A/B measurements
+        if (h->d_hot && !no_hot) { kp.g_hot = h->d_hot + (size_t)(h->hot_pad / 4) * h->hot_wpr + h->hot_pad / 8; kp.hwpr = h->hot_wpr; kp.hpad = h->hot_pad; }
+    }
     kp.crash_clear = (int)std::ceil(std::fabs(h->radius)) + 2;
     if (!(h->radius >= 0.0 && h->radius < 250.0)) kp.crash_clear = 1 << 20;   // never skip the ring
     kp.R = h->R;
@@ -1115,6 +1187,7 @@ static int cast_rays_impl(r2p2_handle h, int plain, int32_t n, const double* ox,
     CK(cudaMemcpyAsync(d_in + 2 * n, angle_rad, nb, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(d_in + 3 * n, limit, nb, cudaMemcpyHostToDevice, h->stream));
     StageView sv; sv.wall = h->d_wall; sv.lvl50 = h->d_l50; sv.dist = h->d_dist; sv.W = h->W; sv.H = h->H; sv.wpr = h->wpr;
+    sv.hot = nullptr; sv.hwpr = 0; sv.hx0 = sv.hy0 = 1; sv.hx1 = sv.hy1 = 0; sv.win_sb = 0u; sv.win_ww = 0;       // r2p2_cast_rays: the distance-field march and the plain loop
     cast_rays_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(sv, plain, h->d_sincostab, n, d_in, d_in + n, d_in + 2 * n, d_in + 3 * n,
                                                              d_i, d_out, d_out + n, d_i + n, reinterpret_cast<uint32_t*>(d_i + 2 * n));
     h->launches++;

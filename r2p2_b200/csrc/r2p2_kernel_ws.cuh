@@ -16,6 +16,12 @@
 
 namespace r2p2 {
 
+#ifdef R2P2_EXP_FETCH_ONLY      // experiment: windows are fetched but the marches read the global plane
+constexpr bool kWsWin = false;
+#else
+constexpr bool kWsWin = true;
+#endif
+
 template <int LPR>
 struct WGroup {
     int sub;
@@ -45,6 +51,11 @@ struct WGroup {
     }
 };
 
+// own samples per pass of the sonar teams (below 8 lanes per ray) and of the collision team (the whole group, 16 samples
+// per pass: collision rays are speed * delta + radius long); the host sizes the windows with the same numbers
+template <int LPR> constexpr int kWsSonarOwn = (LPR <= 2 ? 8 : 4);
+template <int LPR> constexpr int kWsCollOwn = (LPR >= 16 ? 1 : LPR >= 8 ? 2 : 4);
+
 template <int LPR, class NET, bool EXTRA = false>
 __global__ void __launch_bounds__(kBlock, (NET::kLayers > 0 && !NET::kSmemWeights) ? 1 : 4) episode_kernel_ws(const __grid_constant__ KParams p) {
     static_assert(LPR >= 2 && LPR <= 16, "warp-synchronous kernel: 2..16 lanes per robot");
@@ -59,6 +70,9 @@ __global__ void __launch_bounds__(kBlock, (NET::kLayers > 0 && !NET::kSmemWeight
     double* s_bufA = s_cry + 360;
     double* s_bufB = s_bufA + (size_t)p.maxw * NR;
     double* s_gen = s_bufB + (size_t)p.maxw * NR;         // [NR][G], only when p.w_in_smem
+    // per-robot windows of the hot plane (see below)
+    const int win_words = p.win_ww * p.win_wb;
+    uint32_t* s_win = reinterpret_cast<uint32_t*>(s_gen + (p.w_in_smem ? (size_t)NR * p.G : 0));
 
     const uint32_t mb = smem_u32(mbar);
     if (threadIdx.x == 0) {
@@ -73,6 +87,7 @@ __global__ void __launch_bounds__(kBlock, (NET::kLayers > 0 && !NET::kSmemWeight
     StageView sv;
     sv.wall = p.g_wall; sv.lvl50 = p.g_lvl50; sv.dist = p.g_dist;
     sv.W = p.W; sv.H = p.H; sv.wpr = p.wpr;
+    view_global_hot(sv, p.g_hot, p.hwpr, p.hpad);
 
     const WGroup<LPR> g;
     const unsigned lane = threadIdx.x & 31u;
@@ -92,6 +107,13 @@ __global__ void __launch_bounds__(kBlock, (NET::kLayers > 0 && !NET::kSmemWeight
     const MarchPlan sonar_plan = make_plan(p.L, tl);
     Team coll_team;
     coll_team.tl = LPR; coll_team.j = g.sub; coll_team.mask = g.gbits << g.gbase; coll_team.sync = FULL;
+    // The robot's window: win_ww x win_wb words of the hot plane around its sonar origin, copied once per tick by the
+    // lanes of its group in 16-byte asynchronous copies (LDGSTS, L2 -> shared memory, not through L1) -- every sample of
+    // the sonar fan, the collision ray and the crash ring of the tick is then a shared-memory read with a fixed latency,
+    // whatever L1 holds.  (Measured: one cp.async.bulk per 64-byte band row is 2x slower than no window at all -- the TMA
+    // unit's per-copy cost dominates at this size.)
+    const uint32_t win_saddr = smem_u32(s_win + (size_t)slot * win_words);
+    const int win_cpb = p.win_ww >> 2;                    // 16-byte chunks per band
 
     for (;;) {
         // ---- the warp fetches its next 32/LPR robots ---------------------------------------------------
@@ -126,6 +148,9 @@ __global__ void __launch_bounds__(kBlock, (NET::kLayers > 0 && !NET::kSmemWeight
 
         unsigned goal_tick = (EXTRA && p.goal_on) ? p.goal_tick[rb] : 0xffffffffu;
         bool alive = valid && !(flags & (R2P2_F_FAULT | R2P2_F_DONE));
+        StageView svw = sv;                               // the robot's view: its window instead of the global plane
+        svw.win_ww = p.win_ww;
+        svw.hx0 = 1; svw.hy0 = 1; svw.hx1 = 0; svw.hy1 = 0;   // (nothing fetched yet)
         int tdone = 0;                                    // ticks completed in this launch
         unsigned ncollide0 = ncollide;
         for (int t = 0; t < p.T; ++t) {
@@ -142,13 +167,40 @@ __global__ void __launch_bounds__(kBlock, (NET::kLayers > 0 && !NET::kSmemWeight
             const double ox = rint(x), oy = rint(y);
             MarchPlan plan = sonar_plan;                                  // a stopped robot marches zero-length rays
             if (!sensing) { plan.kA = 0; plan.kB = 0; plan.chunk = 0; }
+            {
+                const bool near_map = sensing & (ox > -32.0) & (ox < (double)(p.W + 32)) & (oy > -32.0) & (oy < (double)(p.H + 32));   // the window stays inside the plane's margin
+                const int iox = near_map ? __double2int_rn(ox) : 0, ioy = near_map ? __double2int_rn(oy) : 0;
+                // the window fetched on an earlier tick still covers this tick's box: nothing to do (robots move a few pixels per tick)
+                const bool covered = (iox - p.win_half >= svw.hx0) & (iox + p.win_half <= svw.hx1) & (ioy - p.win_half >= svw.hy0) & (ioy + p.win_half <= svw.hy1);
+                if (sensing && !near_map) { svw.hx0 = 1; svw.hy0 = 1; svw.hx1 = 0; svw.hy1 = 0; }
+                __syncwarp();                                             // last tick's reads of the window are done
+#ifdef R2P2_EXP_STALE
+                if (near_map && t == 0) {
+#else
+                if (near_map && !covered) {
+#endif
+                    const int wx0 = ((iox - p.win_half - p.win_slack) >> 5) << 5, wy0 = ((ioy - p.win_half - p.win_slack) >> 2) << 2;
+                    const uint32_t* src = p.g_hot + hot_word(wx0, wy0, p.hwpr);
+                    int b = 0, q = g.sub;
+                    while (q >= win_cpb) { q -= win_cpb; ++b; }
+                    while (b < p.win_wb) {
+                        cp_async16(win_saddr + (uint32_t)(b * p.win_ww + q * 4) * 4u, src + (size_t)b * p.hwpr + q * 4);
+                        q += LPR;
+                        while (q >= win_cpb) { q -= win_cpb; ++b; }
+                    }
+                    svw.hx0 = wx0; svw.hy0 = wy0; svw.hx1 = wx0 + p.win_ww * 8 - 1; svw.hy1 = wy0 + p.win_wb * 4 - 1;
+                    svw.win_sb = win_saddr - 4u * (unsigned)hot_word(wx0, wy0, p.win_ww);
+                }
+                asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+                __syncwarp();                                             // the group's copies are visible to all its lanes
+            }
             for (int base_r = 0; base_r < R; base_r += rays_per_round) {
                 const int i = base_r + team_ray;
                 const bool have_ray = sensing & (team_ray < rays_per_round) & (i < R);
                 const double ang = have_ray ? R2P2_ADD(p.ray_deg[i], theta) : 0.0;
                 const SinCos sc = sincos_call(R2P2_MUL(ang, kRad), s_tab);
                 if (!sc.ok && have_ray) { flags |= R2P2_F_TRIGRANGE; fault = true; }
-                const Hit h = team_march<(LPR < kMaxSonarTeam ? LPR : kMaxSonarTeam), (LPR <= 2 ? 8 : 4)>(sv, sonar_team, plan, ox, oy, sc.c, sc.s, p.L);
+                const Hit h = team_march<(LPR < kMaxSonarTeam ? LPR : kMaxSonarTeam), kWsSonarOwn<LPR>, kWsWin>(kWsWin ? svw : sv, sonar_team, plan, ox, oy, sc.c, sc.s, p.L);
                 if (h.fault && have_ray) fault = true;
                 const bool leader = have_ray && (team_j == 0);
                 double d = 0.0;
@@ -195,7 +247,17 @@ __global__ void __launch_bounds__(kBlock, (NET::kLayers > 0 && !NET::kSmemWeight
                 }
             }
             double v, w;
-            if constexpr (NET::kLayers > 0) {
+#ifdef R2P2_EXP_OLDMLP
+            if constexpr (false) {
+#else
+            if constexpr (NET::kLayers > 0 && NET::kSmemWeights) {
+#endif
+                for (int i = g.sub; i < NET::sz(0); i += LPR) bufA[i * NR] = R2P2_DIV(p.vr1, bufA[i * NR]);   // 25/dst (inf when dst == 0)
+                __syncwarp();
+                group_mlp<LPR, NET>(gen, bufA, bufB, NR, g.sub, p.activation, v, w);
+                if (v > 180.0) v = R2P2_SUB(v, 360.0);
+                __syncwarp();
+            } else if constexpr (NET::kLayers > 0) {
                 double h[FixedMlp<LPR, NET>::kSlots];
 #pragma unroll
                 for (int s = 0; s < FixedMlp<LPR, NET>::kSlots; ++s) {
@@ -278,7 +340,7 @@ __global__ void __launch_bounds__(kBlock, (NET::kLayers > 0 && !NET::kSmemWeight
                 const bool teamed = must_march && windowed;
                 MarchPlan cplan = make_plan(teamed ? climit : 0.0, LPR);
                 if (!teamed) { cplan.kA = 0; cplan.kB = 0; cplan.chunk = 0; }
-                const Hit mh = team_march_t<LPR, (LPR >= 8 ? 32 / LPR : 4)>(sv, coll_team, cplan, x, y, csc.c, csc.s, climit);
+                const Hit mh = team_march_t<LPR, kWsCollOwn<LPR>, kWsWin>(kWsWin ? svw : sv, coll_team, cplan, x, y, csc.c, csc.s, climit);
                 if (teamed) ms = mh;
                 else if (must_march) ms = march_plain(sv, x, y, csc.c, csc.s, climit);
             }
@@ -354,7 +416,12 @@ __global__ void __launch_bounds__(kBlock, (NET::kLayers > 0 && !NET::kSmemWeight
                     const int leader = __ffs(todo) - 1;
                     todo &= todo - 1u;
                     const double rx = __shfl_sync(FULL, x, leader), ry = __shfl_sync(FULL, y, leader);
-                    const unsigned key = __reduce_min_sync(FULL, ring_scan<32>(sv, (int)lane, rx, ry, p.radius, s_crx, s_cry));
+                    StageView svr = sv;                      // that robot's window
+                    svr.win_ww = p.win_ww;
+                    svr.hx0 = __shfl_sync(FULL, svw.hx0, leader); svr.hy0 = __shfl_sync(FULL, svw.hy0, leader);
+                    svr.hx1 = __shfl_sync(FULL, svw.hx1, leader); svr.hy1 = __shfl_sync(FULL, svw.hy1, leader);
+                    svr.win_sb = __shfl_sync(FULL, svw.win_sb, leader);
+                    const unsigned key = __reduce_min_sync(FULL, ring_scan<32, kWsWin>(svr, (int)lane, rx, ry, p.radius, s_crx, s_cry));
                     if ((int)(lane & ~(unsigned)(LPR - 1)) == leader && key != 0xffffffffu) {   // the lanes of that robot's group
                         if (key & 1u) crash = true;
                         else { flags |= R2P2_F_FAULT; live = false; }

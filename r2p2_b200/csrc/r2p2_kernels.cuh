@@ -55,6 +55,11 @@ struct KParams {
     const uint32_t* g_lvl50;           //                         <=> level(x, y) == 50
     const uint8_t* g_dist;             // [H][W] Chebyshev distance to the nearest blocked pixel (wall or outer ring), <= 255
     uint32_t plane_bytes;              // bytes of one plane, multiple of 16
+    const uint32_t* g_hot;             // padded "event" plane for the ray march (see HotPlane), pre-offset to pixel (0, 0); may be NULL
+    int32_t hwpr, hpad;                // its words per row (one row = 4 pixel rows) and padding in pixels
+    int32_t win_ww, win_wb, win_half;  // warp-synchronous kernel: per-robot window of the hot plane in shared memory -- words per
+                                       // band (multiple of 4), bands, and the half-size in pixels a tick needs around the robot
+    int32_t win_slack;                 // extra pixels on every side when a window is fetched: it is kept until the robot has moved that far
     int32_t crash_clear;               // distance from which the crash-radius ring cannot touch a wall: ceil(radius) + 2
     // robot
     int32_t R;
@@ -100,7 +105,36 @@ struct StageView {
     const uint32_t* lvl50;
     const uint8_t* dist;
     int W, H, wpr;
+    const uint32_t* hot;               // see hot_word / hot_shift; NULL: no fast path
+    int hwpr;
+    int hx0, hy0, hx1, hy1;            // pixels (inclusive) at which the fast plane in use may be read; empty: no fast path
+    uint32_t win_sb;                   // window variant: shared-memory byte address of the word of pixel (0, 0) (may lie outside the window)
+    int win_ww;                        //                 words per band of the window
 };
+__device__ __forceinline__ void view_global_hot(StageView& sv, const uint32_t* hot, int hwpr, int hpad) {
+    sv.hot = hot; sv.hwpr = hwpr; sv.win_sb = 0u; sv.win_ww = 0;
+    if (hot) { sv.hx0 = -hpad; sv.hy0 = -hpad; sv.hx1 = sv.W + hpad - 1; sv.hy1 = sv.H + hpad - 1; }
+    else { sv.hx0 = 1; sv.hy0 = 1; sv.hx1 = 0; sv.hy1 = 0; }
+}
+__device__ __forceinline__ unsigned lds_u32(uint32_t saddr) {
+    unsigned v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+
+// The "hot" plane: what the marches and the crash ring read.  One bit per pixel of the map AND of a margin of `hpad`
+// pixels around it; a bit is set when the pixel is a wall (level 0) or is not an interior pixel of the map (the
+// outermost pixel ring and everything outside) -- i.e. whenever a sample on that pixel is not simply "free, carry on".
+// A 32-bit word covers 8 x 4 pixels (x by y), words of one 4-row band are contiguous: the 61 x 61 pixel neighbourhood a
+// 30-pixel sonar fan touches is 16 bands x ~160 bytes instead of 61 rows of the row-major wall plane.  Word and bit of
+// pixel (ix, iy), both possibly negative inside the margin (arithmetic shifts, hpad is a multiple of 8):
+//     word = (iy >> 2) * hwpr + (ix >> 3)       relative to the pre-offset pointer
+//     bit  = (ix + 8 * iy) & 31                 a permutation of the word's 32 pixels: one IMAD, and the funnel shift
+//                                               that extracts it wraps the shift count by itself
+__host__ __device__ __forceinline__ int hot_word(int ix, int iy, int hwpr) { return (iy >> 2) * hwpr + (ix >> 3); }
+__host__ __device__ __forceinline__ int hot_shift(int ix, int iy) { return ix + 8 * iy; }
+// floor(v) for |v| < 2^31 (negative values too) from the low word of RD(v + 1.5 * 2^52); no validity check
+__device__ __forceinline__ int floor_lo(double v) { return __double2loint(__dadd_rd(v, 6755399441055744.0)); }
 
 // ---------------------------------------------------------------------------------------------
 // TMA (1-D bulk copy) + mbarrier helpers
@@ -127,6 +161,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t mbar, uint32_t parity) {
 __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint32_t mbar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(mbar) : "memory");
+}
+
+// 16-byte asynchronous copy global -> shared (LDGSTS), cached at L2 only
+__device__ __forceinline__ void cp_async16(uint32_t dst_saddr, const void* src_gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_saddr), "l"(src_gmem) : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -322,13 +361,21 @@ __device__ __forceinline__ MarchPlan make_plan(double limit, int tl) {
 // Strided team march (the one the kernels use).  TL lanes -- a power of two, an aligned segment of the warp --
 // cooperate on ONE ray; lane j owns the samples k = j, j + TL, j + 2 TL, ...  A warp issues in order, so the code is
 // laid out as the hardware should see it: one unpredicated chain of the reference's sequential additions (a predicated
-// DADD chain runs at half speed, measured), the position recorded and the bit-plane load issued whenever the lane
-// passes one of its own samples, and all the tests after the chain, when the loads have landed; NOWN own samples
-// (TL * NOWN samples of the ray) per pass, fully unrolled.  The earliest event of the ray -- wall hit, while-condition
-// false at the knife-edge sample, or a sample off the interior of the map -- is a min-reduction over the team of
-// (k << 2 | kind); in the last case the exact loop takes over from that sample.  All collectives are issued with
-// tm.sync, one mask value shared by every lane that executes this code together.
-template <int TL, int NOWN>
+// DADD chain runs at half speed, measured), the pixel word of the hot plane requested whenever the lane passes one of
+// its own samples, and the tests after the chain, when the loads have landed; NOWN own samples (TL * NOWN samples of
+// the ray) per pass, fully unrolled.  Per own sample: 2 DADD (position), 2 DADD.RD (floor), word / shift arithmetic, one
+// load, two funnel shifts that push the sample's event bit into a per-pass mask.  A set bit means "wall, or not an
+// interior pixel"; the lane's first one ends its walk and is classified (hit / leave it to the exact loop).  The
+// earliest event of the ray -- wall hit, while-condition false at the knife-edge sample, or a sample off the interior
+// of the map -- is a min-reduction over the team of (k << 2 | kind); in the last case the exact loop takes over from
+// that sample.  All collectives are issued with tm.sync, one mask value shared by every lane that executes this code
+// together.
+//
+// Nothing is range-checked per sample: with |v| <= 1 per axis the walk stays within k + 1 pixels of the origin pixel
+// after k steps and (passes are not cut at kB) ends below kB + TL * NOWN, so one box test per ray against the pixels the
+// plane in use covers -- the hot plane's margin, or (WIN) the robot's window of it in shared memory -- decides.  Rays
+// that fail it (far off the map, a limit beyond the margin, no plane) go to the exact loop from sample 0.
+template <int TL, int NOWN, bool WIN = false>
 __device__ __forceinline__ Hit team_march_t(const StageView& s, const Team& tm, const MarchPlan& mp, double ox, double oy,
                                             double vx, double vy, double limit) {
     const int kA = mp.kA, kB = mp.kB;
@@ -340,7 +387,15 @@ __device__ __forceinline__ Hit team_march_t(const StageView& s, const Team& tm, 
     constexpr unsigned kSampleSlow = 3u;
     unsigned key = kNone;
     double x = ox, y = oy, hx = -1.0, hy = -1.0;
-    const int nwalk = min(TL, kB) - 1;                     // to this lane's first sample: additions of v or of 0.0
+    // every pixel the walk can read -- within kB + TL * NOWN of the origin pixel -- must be inside the plane in use
+    bool fast = (r2p2_fabs(ox) < 1e9) & (r2p2_fabs(oy) < 1e9) & (r2p2_fabs(vx) <= 1.0) & (r2p2_fabs(vy) <= 1.0);
+    {
+        const int iox = floor_lo(ox), ioy = floor_lo(oy), reach = kB + TL * NOWN + 1;
+        fast &= (iox - reach >= s.hx0) & (iox + reach <= s.hx1) & (ioy - reach >= s.hy0) & (ioy + reach <= s.hy1);
+    }
+    const int kEnd = fast ? kB : 0;
+    if (!fast && kB > 0) { key = kSampleSlow; hx = ox; hy = oy; }     // (0 << 2 | slow): the exact loop runs the whole ray
+    const int nwalk = min(TL, kEnd) - 1;                   // to this lane's first sample: additions of v or of 0.0
 #pragma unroll 4
     for (int i = 0; i < nwalk; ++i) {
         const bool on = i < j;
@@ -348,45 +403,72 @@ __device__ __forceinline__ Hit team_march_t(const StageView& s, const Team& tm, 
         y = R2P2_ADD(y, on ? vy : 0.0);
     }
     const bool has_window = kB > kA;                       // uniform
+    const bool win_owner = has_window & ((kA & (TL - 1)) == j);
     double xw = 0.0, yw = 0.0;
-    for (int k0 = j; k0 < kB; k0 += TL * NOWN) {
-        double xs[NOWN], ys[NOWN];
+    const uint32_t* __restrict__ hot = s.hot;
+    const int hwpr = WIN ? s.win_ww : s.hwpr;
+    for (int k0 = j; k0 < kEnd; k0 += TL * NOWN) {
+        // Position of an own sample when it is needed afterwards (the lane's first event, the knife-edge sample).  One
+        // lane per ray: re-walked from the pass start with the same additions (at most NOWN - 1 of them; no registers
+        // held across the pass).  Teams: kept per sample -- a re-walk of up to TL * (NOWN - 1) dependent additions would
+        // sit on the critical path of the latency-bound mappings (config B: +7 %).
+        constexpr int NKEEP = (TL > 1) ? NOWN : 1;
+        double xs[NKEEP], ys[NKEEP];
+        xs[0] = x; ys[0] = y;                               // this lane's first sample of the pass
         unsigned w[NOWN];
-        int ixs[NOWN];
-        bool inter[NOWN];
+        int sh[NOWN];
 #pragma unroll
         for (int m = 0; m < NOWN; ++m) {
-            xs[m] = x; ys[m] = y;
-            int ix, iy;
-            const bool okx = fast_floor(x, ix), oky = fast_floor(y, iy);
-            inter[m] = okx & oky & ((unsigned)(ix - 1) < (unsigned)(s.W - 2)) & ((unsigned)(iy - 1) < (unsigned)(s.H - 2));
-            w[m] = s.wall[inter[m] ? (iy * s.wpr + (ix >> 5)) : 0];              // always a valid address
-            ixs[m] = ix;
+            if constexpr (TL > 1) { xs[m] = x; ys[m] = y; }
+            const int ix = floor_lo(x), iy = floor_lo(y);
+            if constexpr (WIN) w[m] = lds_u32(s.win_sb + 4u * (unsigned)hot_word(ix, iy, hwpr));
+            else w[m] = __ldg(hot + hot_word(ix, iy, hwpr));
+            sh[m] = hot_shift(ix, iy);
             if (m + 1 < NOWN) {
 #pragma unroll
                 for (int u = 0; u < TL; ++u) { x = R2P2_ADD(x, vx); y = R2P2_ADD(y, vy); }
             }
         }
-        if (has_window) {
+        unsigned evm = 0u;                                  // sample m's bit ends up at bit 32 - NOWN + m
 #pragma unroll
-            for (int m = 0; m < NOWN; ++m)
-                if (k0 + m * TL == kA) { xw = xs[m]; yw = ys[m]; }
-        }
+        for (int m = 0; m < NOWN; ++m) evm = __funnelshift_r(evm, __funnelshift_r(w[m], 0u, (unsigned)sh[m]), 1u);
+        evm >>= (32 - NOWN);
+        const int rem = kEnd - k0;                          // samples of the ray from this lane's first of the pass on
+        if (rem <= TL * NOWN) {                             // last pass
+            if (rem < TL * NOWN) evm &= (1u << ((rem + TL - 1) / TL)) - 1u;   // own samples at or beyond kB do not count
+            if (win_owner) {                                // the knife-edge sample, if any, is the last one of the ray
+                xw = xs[0]; yw = ys[0];
+                if constexpr (TL > 1) {
+                    const int mw = (kA - k0) / TL;
 #pragma unroll
-        for (int m = 0; m < NOWN; ++m) {
-            const int k = k0 + m * TL;
-            const unsigned kind = !inter[m] ? kSampleSlow : (((w[m] >> (ixs[m] & 31)) & 1u) ? (unsigned)kSampleHit : 0u);
-            if ((k < kB) && kind != 0u && key == kNone) { key = ((unsigned)k << 2) | kind; hx = xs[m]; hy = ys[m]; }
+                    for (int m = 1; m < NOWN; ++m) if (mw == m) { xw = xs[m]; yw = ys[m]; }
+                } else {
+                    for (int u = kA - k0; u > 0; --u) { xw = R2P2_ADD(xw, vx); yw = R2P2_ADD(yw, vy); }
+                }
+            }
         }
-        if (key != kNone) break;                            // this lane's later samples cannot come before its first event
-        if (k0 + TL * NOWN < kB) {                          // another pass follows
+        if (evm) {                                          // this lane's first event: its position, its kind
+            const int me = __ffs((int)evm) - 1;
+            hx = xs[0]; hy = ys[0];
+            if constexpr (TL > 1) {
+#pragma unroll
+                for (int m = 1; m < NOWN; ++m) if (me == m) { hx = xs[m]; hy = ys[m]; }
+            } else {
+                for (int u = me; u > 0; --u) { hx = R2P2_ADD(hx, vx); hy = R2P2_ADD(hy, vy); }
+            }
+            const int ix = floor_lo(hx), iy = floor_lo(hy);
+            const bool inter = ((unsigned)(ix - 1) < (unsigned)(s.W - 2)) & ((unsigned)(iy - 1) < (unsigned)(s.H - 2));
+            key = ((unsigned)(k0 + me * TL) << 2) | (inter ? (unsigned)kSampleHit : kSampleSlow);
+            break;                                          // this lane's later samples cannot come before its first event
+        }
+        if (rem > TL * NOWN) {                              // another pass follows
 #pragma unroll
             for (int u = 0; u < TL; ++u) { x = R2P2_ADD(x, vx); y = R2P2_ADD(y, vy); }
         }
     }
     // the knife-edge sample (at most one, k = kA = kB - 1): the reference's limit test comes before its pixel test, and
     // after its bounds test
-    if (has_window && ((kA & (TL - 1)) == j)) {
+    if (win_owner && fast) {
         const bool in_range = r2p2_norm2sq(R2P2_SUB(xw, ox), R2P2_SUB(yw, oy)) < mp.qstar;
         const bool earlier = (key != kNone) && ((int)(key >> 2) < kA || (key & 3u) == kSampleSlow);
         if (!in_range && !earlier) { key = ((unsigned)kA << 2) | (unsigned)kSampleExit; hx = xw; hy = yw; }
@@ -419,17 +501,18 @@ __device__ __forceinline__ Hit team_march_t(const StageView& s, const Team& tm, 
 // Team sizes the kernels use: sonar rays 1, 2, 4 or 8 lanes (the largest that gives every ray of the fan a team within
 // the group), the collision ray the whole group.  MAXTL = lanes per robot.
 constexpr int kMaxSonarTeam = 8;
-template <int MAXTL, int MAXOWN = 8>
+__host__ __device__ constexpr int sonar_nown(int tl, int maxown) { return tl >= 32 ? 1 : tl >= 16 ? 2 : tl >= 8 ? 4 : maxown; }
+template <int MAXTL, int MAXOWN = 8, bool WIN = false>
 __device__ __forceinline__ Hit team_march(const StageView& s, const Team& tm, const MarchPlan& mp, double ox, double oy,
                                           double vx, double vy, double limit) {
     constexpr int O = MAXOWN;
     switch (tm.tl) {                                       // uniform
-        case 32: if constexpr (MAXTL >= 32) return team_march_t<32, 1>(s, tm, mp, ox, oy, vx, vy, limit);
-        case 16: if constexpr (MAXTL >= 16) return team_march_t<16, 2>(s, tm, mp, ox, oy, vx, vy, limit);
-        case 8: if constexpr (MAXTL >= 8) return team_march_t<8, 4>(s, tm, mp, ox, oy, vx, vy, limit);
-        case 4: if constexpr (MAXTL >= 4) return team_march_t<4, O>(s, tm, mp, ox, oy, vx, vy, limit);
-        case 2: if constexpr (MAXTL >= 2) return team_march_t<2, O>(s, tm, mp, ox, oy, vx, vy, limit);
-        default: return team_march_t<1, O>(s, tm, mp, ox, oy, vx, vy, limit);
+        case 32: if constexpr (MAXTL >= 32) return team_march_t<32, 1, WIN>(s, tm, mp, ox, oy, vx, vy, limit);
+        case 16: if constexpr (MAXTL >= 16) return team_march_t<16, 2, WIN>(s, tm, mp, ox, oy, vx, vy, limit);
+        case 8: if constexpr (MAXTL >= 8) return team_march_t<8, 4, WIN>(s, tm, mp, ox, oy, vx, vy, limit);
+        case 4: if constexpr (MAXTL >= 4) return team_march_t<4, O, WIN>(s, tm, mp, ox, oy, vx, vy, limit);
+        case 2: if constexpr (MAXTL >= 2) return team_march_t<2, O, WIN>(s, tm, mp, ox, oy, vx, vy, limit);
+        default: return team_march_t<1, O, WIN>(s, tm, mp, ox, oy, vx, vy, limit);
     }
 }
 
@@ -437,7 +520,7 @@ __device__ __forceinline__ Hit team_march(const StageView& s, const Team& tm, co
 // returns the lane's earliest event as 2 i (IndexError at probe i) or 2 i + 1 (wall at probe i), 0xffffffff for none;
 // the reference stops at the first wall, so an IndexError counts only if it comes before the first wall probe: after
 // a min-reduction over the lanes, an even key is a fault, an odd key a crash.
-template <int LPR>
+template <int LPR, bool WIN = false>
 __device__ __forceinline__ unsigned ring_scan(const StageView& sv, int sub, double x, double y, double radius,
                                               const double* s_crx, const double* s_cry) {
     unsigned key = 0xffffffffu;
@@ -447,6 +530,15 @@ __device__ __forceinline__ unsigned ring_scan(const StageView& sv, int sub, doub
     const double ar = r2p2_fabs(radius);
     const bool inside = (R2P2_SUB(x, ar) >= 1.0) & (R2P2_ADD(x, ar) < (double)(sv.W - 1)) & (R2P2_SUB(y, ar) >= 1.0) & (R2P2_ADD(y, ar) < (double)(sv.H - 1));
     if (inside) {                                          // uniform in the group
+        // (every probed pixel is an interior pixel, where the hot plane's bit is the wall bit)
+        // the robot's window in shared memory when the whole ring lies inside it, else the hot plane, else the wall plane
+        bool in_win = false;
+        if constexpr (WIN) {
+            const int icx = floor_lo(x), icy = floor_lo(y), rr = (int)ar + 2;
+            in_win = (icx - rr >= sv.hx0) & (icx + rr <= sv.hx1) & (icy - rr >= sv.hy0) & (icy + rr <= sv.hy1);
+        }
+        const bool use_hot = sv.hot != nullptr;
+        const uint32_t* __restrict__ plane = use_hot ? sv.hot : sv.wall;
 #pragma unroll 1
         for (int m0 = 0; m0 < kPer; m0 += 4) {
             unsigned w[4];
@@ -455,16 +547,15 @@ __device__ __forceinline__ unsigned ring_scan(const StageView& sv, int sub, doub
             for (int u = 0; u < 4; ++u) {
                 const int i = sub + (m0 + u) * LPR;
                 const int ii = (i < 360) ? i : 0;
-                int ix, iy;
-                fast_floor(R2P2_ADD(x, s_crx[ii]), ix);
-                fast_floor(R2P2_ADD(y, s_cry[ii]), iy);
-                w[u] = sv.wall[iy * sv.wpr + (ix >> 5)];
-                bx[u] = ix & 31;
+                const int ix = floor_lo(R2P2_ADD(x, s_crx[ii])), iy = floor_lo(R2P2_ADD(y, s_cry[ii]));
+                if (WIN && in_win) w[u] = lds_u32(sv.win_sb + 4u * (unsigned)hot_word(ix, iy, sv.win_ww));
+                else w[u] = plane[use_hot ? hot_word(ix, iy, sv.hwpr) : (iy * sv.wpr + (ix >> 5))];
+                bx[u] = use_hot ? hot_shift(ix, iy) : ix;
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int i = sub + (m0 + u) * LPR;
-                const bool hit = (i < 360) & (((w[u] >> bx[u]) & 1u) != 0u);
+                const bool hit = (i < 360) & ((__funnelshift_r(w[u], 0u, (unsigned)bx[u]) & 1u) != 0u);
                 key = min(key, hit ? (unsigned)(2 * i + 1) : 0xffffffffu);
             }
         }
@@ -512,6 +603,9 @@ __device__ __forceinline__ unsigned ring_scan_rt(const StageView& sv, int sub, i
     const double ar = r2p2_fabs(radius);
     const bool inside = (R2P2_SUB(x, ar) >= 1.0) & (R2P2_ADD(x, ar) < (double)(sv.W - 1)) & (R2P2_SUB(y, ar) >= 1.0) & (R2P2_ADD(y, ar) < (double)(sv.H - 1));
     if (inside) {                                          // uniform in the group
+        // (every probed pixel is an interior pixel, where the hot plane's bit is the wall bit)
+        const bool use_hot = sv.hot != nullptr;
+        const uint32_t* __restrict__ plane = use_hot ? sv.hot : sv.wall;
 #pragma unroll 1
         for (int m0 = 0; m0 < kPer; m0 += 4) {
             unsigned w[4];
@@ -520,16 +614,14 @@ __device__ __forceinline__ unsigned ring_scan_rt(const StageView& sv, int sub, i
             for (int u = 0; u < 4; ++u) {
                 const int i = sub + (m0 + u) * LPR;
                 const int ii = (i < 360) ? i : 0;
-                int ix, iy;
-                fast_floor(R2P2_ADD(x, s_crx[ii]), ix);
-                fast_floor(R2P2_ADD(y, s_cry[ii]), iy);
-                w[u] = sv.wall[iy * sv.wpr + (ix >> 5)];
-                bx[u] = ix & 31;
+                const int ix = floor_lo(R2P2_ADD(x, s_crx[ii])), iy = floor_lo(R2P2_ADD(y, s_cry[ii]));
+                w[u] = plane[use_hot ? hot_word(ix, iy, sv.hwpr) : (iy * sv.wpr + (ix >> 5))];
+                bx[u] = use_hot ? hot_shift(ix, iy) : ix;
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int i = sub + (m0 + u) * LPR;
-                const bool hit = (i < 360) & (((w[u] >> bx[u]) & 1u) != 0u);
+                const bool hit = (i < 360) & ((__funnelshift_r(w[u], 0u, (unsigned)bx[u]) & 1u) != 0u);
                 key = min(key, hit ? (unsigned)(2 * i + 1) : 0xffffffffu);
             }
         }
@@ -687,11 +779,14 @@ __device__ __forceinline__ double activate(int kind, double v) {
 //   [.., +plane_bytes)             level-50 plane  (SMEM_STAGE and has50 only)
 //   [.., +2*maxw*NR*8)             MLP / sonar buffers A and B, element i of robot slot r at [i*NR + r]
 //   [.., +NR*G*8)                  genomes of the robots in flight (w_in_smem only), row r at [r*G]
-__host__ __device__ inline size_t episode_smem_bytes(int lpr, bool smem_stage, uint32_t plane_bytes, int has50, int maxw, int w_in_smem, int G) {
+//   [.., +NR*win_words*4)          per-robot windows of the hot plane (warp-synchronous kernel)
+__host__ __device__ inline size_t episode_smem_bytes(int lpr, bool smem_stage, uint32_t plane_bytes, int has50, int maxw, int w_in_smem, int G,
+                                                     int win_words = 0) {
     size_t n = 16 + R2P2_SINCOSTAB_LEN * 8 + 720 * 8;
     if (smem_stage) n += (size_t)plane_bytes * (has50 ? 2 : 1);
     n += (size_t)2 * maxw * (kBlock / lpr) * 8;
     if (w_in_smem) n += (size_t)(kBlock / lpr) * G * 8;
+    if (win_words) n += (size_t)(kBlock / lpr) * (size_t)win_words * 4;
     return n;
 }
 
@@ -735,6 +830,7 @@ struct SmemNet : SHAPE {
 };
 using NetNeuro = NetShape<5, 10, 7, 4, 2>;     // conf/controller-neuro.json on robot-neuro.json (5 rays)
 using NetSimple = NetShape<5, 1, 2, 0, 0>;     // conf/controller-neuro-simple.json
+using NetSweep = NetShape<32, 16, 8, 2, 0>;    // BASELINE.json configs[4]: the 32-ray synthetic sweep
 
 template <int LPR, class NET>
 struct FixedMlp {
@@ -863,6 +959,50 @@ __device__ __forceinline__ void lane_mlp(const double* __restrict__ wt, size_t P
     out1 = res[NR];
 }
 
+// Compile-time shape, LPR lanes per robot, activations in shared memory (element i of this robot at buf[i * NR]): lane
+// `sub` owns the neurons sub, sub + LPR, ... of every layer.  One pass over the inputs feeds all of the lane's neurons
+// (one LDS per input, broadcast to the group), the weights come through `gs` -- the robot's genome in shared memory or
+// in the [P][G] array -- and each neuron keeps the reference's ordered chain acc = fma(h_i, w_ij, acc), i ascending.
+// (The first version exchanged activations with __shfl_sync: two SHFL per double and input were 11 % of the synthetic
+// sweep's instructions.)
+template <int LPR, class NET, int L>
+__device__ __forceinline__ void group_layer(const double* __restrict__ gs, const double* hin, double* hout, int NR, int sub, int activation) {
+    constexpr int nin = NET::sz(L), nout = NET::sz(L + 1), slots = (nout + LPR - 1) / LPR;
+    constexpr bool last = (L + 2 == NET::kLayers);
+    const double* wp[slots];
+    double acc[slots];
+#pragma unroll
+    for (int q = 0; q < slots; ++q) {
+        const int jn = sub + q * LPR;
+        wp[q] = gs + NET::woff(L) + (jn < nout ? jn : 0);          // lanes without a neuron read a valid column
+        acc[q] = 0.0;
+    }
+#pragma unroll 8
+    for (int i = 0; i < nin; ++i) {
+        const double hi = hin[i * NR];
+#pragma unroll
+        for (int q = 0; q < slots; ++q) acc[q] = R2P2_FMA(hi, wp[q][i * nout], acc[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < slots; ++q) {
+        const int jn = sub + q * LPR;
+        if (jn < nout) hout[jn * NR] = last ? acc[q] : activate(activation, acc[q]);
+    }
+}
+// in: a[i * NR] = input i (already vr1 / dst); a and b are overwritten; returns outputs 0 and 1 in every lane of the group.
+// `sync` is the group-wide barrier (a __syncwarp in the warp-synchronous kernel).
+template <int LPR, class NET>
+__device__ __forceinline__ void group_mlp(const double* __restrict__ gs, double* a, double* b, int NR, int sub, int activation, double& out0, double& out1) {
+    group_layer<LPR, NET, 0>(gs, a, b, NR, sub, activation);
+    __syncwarp();
+    double* res = b;
+    if constexpr (NET::kLayers > 2) { group_layer<LPR, NET, 1>(gs, b, a, NR, sub, activation); __syncwarp(); res = a; }
+    if constexpr (NET::kLayers > 3) { group_layer<LPR, NET, 2>(gs, a, b, NR, sub, activation); __syncwarp(); res = b; }
+    if constexpr (NET::kLayers > 4) { group_layer<LPR, NET, 3>(gs, b, a, NR, sub, activation); __syncwarp(); res = a; }
+    out0 = res[0];
+    out1 = res[NR];
+}
+
 template <int LPR>
 struct FixedMlp<LPR, GenericNet> {
     static constexpr int kSlots = 1;
@@ -915,6 +1055,7 @@ __global__ void __launch_bounds__(kBlock, (NET::kLayers > 0 && !NET::kSmemWeight
     sv.lvl50 = SMEM_STAGE ? s_l50 : p.g_lvl50;
     sv.dist = p.g_dist;
     sv.W = p.W; sv.H = p.H; sv.wpr = p.wpr;
+    view_global_hot(sv, p.g_hot, p.hwpr, p.hpad);
 
     const Group<LPR> g;
     const int slot = threadIdx.x / LPR;                   // robot slot inside the CTA
@@ -1315,6 +1456,23 @@ __global__ void pack_stage_kernel(const uint8_t* __restrict__ levels, int W, int
     if (b5) atomicOr(has50, 1);
 }
 
+// Hot plane (see hot_word / hot_shift): one thread per 32-bit word = 8 x 4 pixels of the padded map.
+__global__ void hot_plane_kernel(const uint8_t* __restrict__ levels, int W, int H, int hpad, int hwpr, int hrows, uint32_t* __restrict__ hot) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x, rr = blockIdx.y;
+    if (c >= hwpr || rr >= hrows) return;
+    uint32_t bits = 0u;
+    for (int dy = 0; dy < 4; ++dy) {
+        const int iy = 4 * (rr - hpad / 4) + dy;
+        for (int dx = 0; dx < 8; ++dx) {
+            const int ix = 8 * (c - hpad / 8) + dx;
+            const bool interior = (ix >= 1) & (ix <= W - 2) & (iy >= 1) & (iy <= H - 2);
+            const bool blocked = !interior || levels[(size_t)ix * H + iy] == 0;
+            bits |= (uint32_t)blocked << (hot_shift(ix, iy) & 31);
+        }
+    }
+    hot[(size_t)rr * hwpr + c] = bits;
+}
+
 // Distance field, pass 1: per map row, distance along x to the nearest blocked pixel (wall or outer ring), <= 255.
 // One thread per row (one-time setup work; the walk is sequential in x by nature).
 __global__ void dist_rows_kernel(const uint8_t* __restrict__ levels, int W, int H, uint8_t* __restrict__ hrow) {
@@ -1477,6 +1635,7 @@ __global__ void sense_kernel(const __grid_constant__ SenseParams sp) {
     if (flags & (R2P2_F_FAULT | R2P2_F_DONE)) return;
     StageView sv;
     sv.wall = p.g_wall; sv.lvl50 = p.g_lvl50; sv.dist = p.g_dist; sv.W = p.W; sv.H = p.H; sv.wpr = p.wpr;
+    view_global_hot(sv, p.g_hot, p.hwpr, p.hpad);
     const double x = p.x[rb], y = p.y[rb], theta = p.theta[rb];
     bool fault = !(isfinite(x) && isfinite(y));
     const double ox = rint(x), oy = rint(y);

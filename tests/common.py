@@ -8,13 +8,17 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 GOLDEN = os.path.join(HERE, "golden")
 STAGES = ["track_2.png", "stage.png", "track.png"]
 
+CONF = os.path.join(GOLDEN, "conf")          # byte copies of the reference's conf/*.json (make_golden.py --conf-only)
+
+
+def conf(name):
+    """One of the reference's conf/*.json files, as shipped."""
+    with open(os.path.join(CONF, name)) as fp:
+        return json.load(fp)
+
+
 # the robot jsons shipped by the reference (conf/robot-neuro.json, robot_omni.json, robot-track.json, robot.json)
-ROBOTS = {
-    "robot-neuro.json": dict(x=230, y=250, orientation=0, sonar_range=[0.5, 25], radius=5, sonars=[0, 45, 70, 290, 315], max_speed=50),
-    "robot_omni.json": dict(x=193, y=249, orientation=0, sonar_range=[1, 50], radius=5, sonars=8, max_speed=50),
-    "robot-track.json": dict(x=260, y=250, orientation=0, sonar_range=[0.5, 40], radius=5, sonars=[0, 45, 70, 290, 315], max_speed=50),
-    "robot.json": dict(x=260, y=200, orientation=0, sonar_range=[0.5, 25], radius=5, sonars=[0, 45, 70, 290, 315], max_speed=50),
-}
+ROBOTS = {name: conf(name) for name in ("robot-neuro.json", "robot_omni.json", "robot-track.json", "robot.json")}
 
 
 def load_stage(name):

@@ -456,7 +456,23 @@ def gen_grids(E):
     np.savez_compressed(os.path.join(OUT, "grids.npz"), specs=json.dumps(specs), **out)
 
 
+def gen_conf():
+    """The reference's conf/*.json, byte for byte -> tests/golden/conf/ (robot / controller / scenario numbers are read
+    from these copies by tests/common.py and bench.py instead of being typed in)."""
+    import shutil
+    dst = os.path.join(OUT, "conf")
+    os.makedirs(dst, exist_ok=True)
+    src = os.path.join(ref_harness.REF, "conf")
+    for f in sorted(os.listdir(src)):
+        if f.endswith(".json"):
+            shutil.copyfile(os.path.join(src, f), os.path.join(dst, f))
+    print("conf:", len(os.listdir(dst)), "files")
+
+
 def main():
+    if "--conf-only" in sys.argv:
+        gen_conf()
+        return
     E = ref_harness.RefEnv()
     try:
         if "--act-only" in sys.argv:
@@ -474,6 +490,7 @@ def main():
         if "--noise-only" in sys.argv:
             gen_noisy_episodes(E)
             return
+        gen_conf()
         gen_rays(E)
         gen_ticks(E)
         gen_episodes(E)

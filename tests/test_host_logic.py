@@ -17,14 +17,8 @@ def write_conf(tmp, stage="track_2"):
     os.makedirs(os.path.join(tmp, "conf")); os.makedirs(os.path.join(tmp, "res"))
     env = common.load_stage(stage + ".png").astype(np.uint8)                # env[x, y]
     Image.fromarray(np.ascontiguousarray(env.T), mode="L").save(os.path.join(tmp, "res", stage + ".png"))
-    rob = dict(common.ROBOTS["robot-neuro.json"], id=0)
-    json.dump(rob, open(os.path.join(tmp, "conf", "robot-neuro.json"), "w"))
-    json.dump({"class": "neurocontroller.Neuro_controller", "weights": [0.0, 0.0], "hidden_layer": [10, 7, 4], "activation": "tanh",
-               "time": 20, "evolve": True}, open(os.path.join(tmp, "conf", "controller-neuro.json"), "w"))
-    json.dump({"controller_type": "NEURO", "weights": [0] * 7, "hidden_layer": [1], "activation": "tanh", "time": 20, "evolve": False},
-              open(os.path.join(tmp, "conf", "controller-neuro-simple.json"), "w"))
-    json.dump({"class": "inspyred.Inspyred_controller", "weights": [0] * 10, "time": 20, "evolve": True},
-              open(os.path.join(tmp, "conf", "controller-inspyred.json"), "w"))
+    for name in ("robot-neuro.json", "controller-neuro.json", "controller-neuro-simple.json", "controller-inspyred.json"):
+        json.dump(common.conf(name), open(os.path.join(tmp, "conf", name), "w"))      # the reference's files, as shipped
     for name, ctrl in (("scenario-neuro.json", "controller-neuro.json"), ("scenario-neuro-simple.json", "controller-neuro-simple.json"),
                        ("scenario-inspyred.json", "controller-inspyred.json")):
         json.dump({"stage": "../res/%s.png" % stage, "robot": "../conf/robot-neuro.json", "controller": "../conf/" + ctrl, "gui": False},

@@ -53,24 +53,24 @@ for (f, ln), (ie, sm) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]:
 # ---- coarse buckets -------------------------------------------------------------------------------------
 def bucket(f, ln):
     if f == "r2p2_math.h":
-        if ln < 100: return "math: bits/norm2/sqrt"
-        if ln < 235: return "math: sincos"
-        if ln < 292: return "math: atan2"
+        if ln < 131: return "math: bits/norm2/sqrt"
+        if ln < 309: return "math: sincos"
+        if ln < 362: return "math: atan2"
         return "math: exp/tanh/logistic"
-    if f == "r2p2_kernels.cuh":
-        txt = src[f][ln - 1] if ln - 1 < len(src[f]) else ""
+    if f in ("r2p2_kernels.cuh", "r2p2_kernel_ws.cuh"):
         return "kernel"
+    if "intrinsics" in f: return "intrinsics (shfl/funnelshift/...)"
     return "other:" + f
 if os.environ.get("BUCKETS"):
     # kernel file: split by line ranges given as "name:lo-hi,name:lo-hi"
     ranges = []
     for item in os.environ["BUCKETS"].split(","):
-        nm, r = item.split(":"); lo, hi = r.split("-"); ranges.append((nm, int(lo), int(hi)))
+        nm, fn, r = item.split(":"); lo, hi = r.split("-"); ranges.append((nm, {"k": "r2p2_kernels.cuh", "w": "r2p2_kernel_ws.cuh"}[fn], int(lo), int(hi)))
     b = {}
     for (f, ln), (ie, sm) in agg.items():
         name = bucket(f, ln)
         if name == "kernel":
-            name = next((nm for nm, lo, hi in ranges if lo <= ln <= hi), "kernel: other")
+            name = next((nm for nm, fn, lo, hi in ranges if fn == f and lo <= ln <= hi), "kernel: other " + f)
         a = b.setdefault(name, [0, 0]); a[0] += ie; a[1] += sm
     print("---- buckets")
     for name, (ie, sm) in sorted(b.items(), key=lambda kv: -kv[1][1]):

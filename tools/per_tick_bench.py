@@ -15,11 +15,11 @@ a = ap.parse_args()
 w = dict(bench.WORKLOADS[a.workload])
 if a.pop: w["P"] = a.pop
 rob = bench.ROBOTS[w["robot"]]
-px, py, pt = bench.start_poses(w, w["P"], 4321)
+px, py, pt = bench.start_poses(w, w["P"])
 ev = PopulationEvaluator(bench.load_stage(w["stage"]), sonar_range=rob["sonar_range"], radius=rob["radius"], max_speed=rob["max_speed"],
                          sonars=rob["sonars"], controller=w["ctrl"], hidden_layer=w["hidden"], x=px, y=py, orientation=pt, ticks=a.frames)
 sim = ev.sim
-g = bench.make_genomes(w, 1234, w["P"])
+g = bench.make_genomes(w, 1234, 0, w["P"])
 P, G, R = w["P"], g.shape[1], sim.R
 # persistent episode
 f_ref = ev.evaluate(g).copy()

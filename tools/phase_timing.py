@@ -18,7 +18,7 @@ w = dict(bench.WORKLOADS[a.workload]); w["T"] = a.ticks
 rob = bench.ROBOTS[w["robot"]]
 ev = PopulationEvaluator(bench.load_stage(w["stage"]), sonar_range=rob["sonar_range"], radius=rob["radius"], max_speed=rob["max_speed"],
                          sonars=rob["sonars"], controller=w["ctrl"], hidden_layer=w["hidden"], x=rob["x"], y=rob["y"], ticks=w["T"], lanes_per_robot=a.lpr)
-g = bench.make_genomes(w, 1234, w["P"])
+g = bench.make_genomes(w, 1234, 0, w["P"])
 L = _lib.lib()
 out = (C.c_ulonglong * 16)()
 ev.evaluate(g); L.r2p2_debug_phase_cycles(out, 1)

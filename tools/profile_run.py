@@ -15,11 +15,11 @@ w = dict(bench.WORKLOADS[a.workload])
 if a.ticks: w["T"] = a.ticks
 if a.pop: w["P"] = a.pop
 rob = bench.ROBOTS[w["robot"]]
-px, py, pt = bench.start_poses(w, w["P"], 4321)
+px, py, pt = bench.start_poses(w, w["P"])
 ev = PopulationEvaluator(bench.load_stage(w["stage"]), sonar_range=rob["sonar_range"], radius=rob["radius"], max_speed=rob["max_speed"],
                          sonars=rob["sonars"], controller=w["ctrl"], hidden_layer=w["hidden"], x=px, y=py, orientation=pt, ticks=w["T"],
                          lanes_per_robot=a.lpr, stage_in_smem=a.smem)
-g = bench.make_genomes(w, 1234, w["P"])
+g = bench.make_genomes(w, 1234, 0, w["P"])
 for i in range(a.iters):
     f = ev.evaluate(g)
     print("iter", i, "kernel ms %.3f" % ev.sim.last_run_ms(), "fitness sum", repr(float(f.sum())))
