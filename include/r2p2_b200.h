@@ -62,6 +62,7 @@ typedef struct r2p2_sim* r2p2_handle;
 #define R2P2_F_FAULT 2u      /* the reference would have raised (IndexError off-map, ValueError on NaN) */
 #define R2P2_F_DONE 4u       /* evolve mode: the episode ended (timer ran out or collision)             */
 #define R2P2_F_GOAL 16u      /* r2p2_set_goal: the goal predicate held after some tick                    */
+#define R2P2_F_NOISE 32u     /* noise replay: the robot's stream ran out, later draws were 0.0 (results no longer follow the reference) */
 #define R2P2_F_TRIGRANGE 8u  /* heading beyond the supported sin/cos range (|radians| >= 105414350)     */
 
 /* limits */
@@ -112,6 +113,9 @@ int r2p2_set_controller(r2p2_handle h, int32_t kind, const int32_t* layers, int3
 int r2p2_set_noise(r2p2_handle h, int32_t mode, uint64_t seed, const double* stream, int32_t P, int32_t len);
 /* Draws consumed per robot since the last reset (uint32[P]). */
 int r2p2_read_noise_draws(r2p2_handle h, uint32_t* ndraws);
+/* Index of this handle's robot 0 in the whole (sharded) population: the device generator (mode 2) is keyed by the GLOBAL
+ * robot index, so an individual draws the same noise whichever GPU evaluates it.  r2p2_ga_evaluate sets it to `first`. */
+int r2p2_set_robot_index_offset(r2p2_handle h, uint32_t first);
 
 /* Thread mapping: lanes per robot (1, 2, 4, 8, 16, 32) or R2P2_LPR_AUTO; stage_in_smem: 1 force the
  * shared-memory copy of the bit planes, 0 read them through L1/L2, -1 choose. */
@@ -125,9 +129,19 @@ int r2p2_upload_genomes(r2p2_handle h, const double* genomes, int32_t P, int32_t
 /* Same, from a DEVICE pointer (e.g. a torch tensor's data_ptr on the same device). */
 int r2p2_set_genomes_device(r2p2_handle h, const double* d_genomes, int32_t P, int32_t G);
 
+/* Current population size and genome length (0, 0 before the first upload).  Every r2p2_read_* call copies P elements:
+ * size the host arrays from this, not from a cached value (r2p2_ga_evaluate resizes the population to the shard). */
+int r2p2_population_size(r2p2_handle h, int32_t* P, int32_t* G);
+
 /* (Re)start every robot: pose from x0/y0/theta0 (n = 1: broadcast one pose, n = P: per robot),
  * speed = 0, odometry/origin = pose, distance = 0, flags = 0, controller timer = time_budget. */
 int r2p2_reset(r2p2_handle h, const double* x0, const double* y0, const double* theta0, int32_t n, double time_budget);
+
+/* Overwrite pose attributes of robots [first, first + count) the way host code assigns them in the reference
+ * (Robot.set_position / set_last_position / `robot.orientation = ...`, r2p2/robot.py:98-107): only the arrays given
+ * (any pointer may be NULL) are written, odometry, fitness and flags are left alone.  Host arrays of `count` doubles. */
+int r2p2_write_pose(r2p2_handle h, int32_t first, int32_t count, const double* x, const double* y, const double* theta,
+                    const double* last_x, const double* last_y);
 
 /* ---- execution ----------------------------------------------------------------------------- */
 /* Advance every robot by up to T ticks of Robot.update(env, delta) in ONE kernel launch (state stays in
@@ -161,6 +175,8 @@ int r2p2_launch_count(r2p2_handle h, uint64_t* n);
  * r2p2/controllers/neurocontroller.py:27-33,100-104.) */
 int r2p2_state_bytes(r2p2_handle h, uint64_t* bytes);
 int r2p2_save_state(r2p2_handle h, void* blob);
+/* The blob starts with a header (magic, format version, P, R, G, controller kind); a blob that does not fit this handle's
+ * configuration is refused with R2P2_E_ARG. */
 int r2p2_load_state(r2p2_handle h, const void* blob);
 
 /* ---- per-tick trace (parity tests, Robot.update facade) -------------------------------------- */
@@ -236,6 +252,12 @@ int r2p2_ga_breed(r2p2_handle h);
  * (the history_*.log record of evolution.py:45-47). */
 int r2p2_ga_best(r2p2_handle h, int32_t* index, double* fitness, double* genome);
 int r2p2_ga_generation(r2p2_handle h, uint32_t* generation);
+/* Checkpoint of the EA: header (magic, version, P, G), seed, range, operators, generation counter, the current
+ * generation [P][G] and its fitness vector [P].  r2p2_ga_load into a handle (with or without a GA of the same shape)
+ * resumes the run reproducibly: the Philox draws depend only on (seed, generation, individual, gene). */
+int r2p2_ga_state_bytes(r2p2_handle h, uint64_t* bytes);
+int r2p2_ga_save(r2p2_handle h, void* blob);
+int r2p2_ga_load(r2p2_handle h, const void* blob, uint64_t bytes);
 
 /* ---- raw ray-caster (utils.search_edge_in_angle_with_limit, r2p2/utils.py:420-432) --------------- */
 /* n independent rays against the current stage; host arrays in, host arrays out.

@@ -90,8 +90,9 @@ class Oracle:
 
     def run(self, env, *, rays, vr, radius, max_speed, ctrl, genomes, x0, y0, theta0, T, delta=0.1,
             layers=None, activation="tanh", evolve=False, delta_ctrl=None, time_budget=20000.0,
-            noise=None, trace=False, threads=1, goal=None):
-        """Run P robots for T ticks.  Returns dict(state=structured array [P], plus traces [T,P,...])."""
+            noise=None, trace=False, threads=1, goal=None, state=None):
+        """Run P robots for T ticks.  Returns dict(state=structured array [P], plus traces [T,P,...]).
+        state: continue from this structured array (a copy is advanced) instead of starting at x0 / y0 / theta0."""
         env = self._env(env)
         genomes = np.ascontiguousarray(genomes, dtype=np.float64)
         P, G = genomes.shape
@@ -119,15 +120,24 @@ class Oracle:
             assert noise.ndim == 2 and noise.shape[0] == P      # per-robot stream of N(0, 0.5) draws, consumed sequentially
             cfg.noise = noise.ctypes.data
             cfg.noise_len = noise.shape[1]
-        st = np.zeros(P, dtype=ROBOT_DTYPE)
+        if state is not None:
+            st = np.array(state, dtype=ROBOT_DTYPE, copy=True)
+            assert st.shape == (P,)
+            x0 = y0 = theta0 = 0.0
+        else:
+            st = None
+        st_given = st is not None
+        if not st_given:
+            st = np.zeros(P, dtype=ROBOT_DTYPE)
         x0 = np.broadcast_to(np.asarray(x0, dtype=np.float64), (P,))
         y0 = np.broadcast_to(np.asarray(y0, dtype=np.float64), (P,))
         th0 = np.broadcast_to(np.asarray(theta0, dtype=np.float64), (P,))
-        for f, v in (("x", x0), ("last_x", x0), ("odom_x", x0), ("origin_x", x0),
-                     ("y", y0), ("last_y", y0), ("odom_y", y0), ("origin_y", y0), ("theta", th0)):
-            st[f] = v
-        st["time"] = cfg.time_budget
-        st["goal_tick"] = 0xFFFFFFFF
+        if not st_given:
+            for f, v in (("x", x0), ("last_x", x0), ("odom_x", x0), ("origin_x", x0),
+                         ("y", y0), ("last_y", y0), ("odom_y", y0), ("origin_y", y0), ("theta", th0)):
+                st[f] = v
+            st["time"] = cfg.time_budget
+            st["goal_tick"] = 0xFFFFFFFF
         out = {}
         ptrs = [None] * 7
         if trace:
@@ -143,6 +153,15 @@ class Oracle:
         out["state"] = st
         out["fitness"] = st["fitness"].copy()
         return out
+
+
+def _resume(self, env, state, **kw):
+    """Advance an existing state array by T more ticks (see ``run``)."""
+    kw.setdefault("x0", 0.0); kw.setdefault("y0", 0.0); kw.setdefault("theta0", 0.0)
+    return self.run(env, state=state, **kw)
+
+
+Oracle.resume = _resume
 
 
 def cost_grid(env, divider):

@@ -67,6 +67,7 @@ enum { ORC_ACT_IDENTITY = 0, ORC_ACT_TANH = 1, ORC_ACT_RELU = 2, ORC_ACT_LOGISTI
 #define ORC_F_FAULT 2u      /* the reference would have raised (IndexError / ValueError / OverflowError) */
 #define ORC_F_DONE 4u       /* evolve: the episode ended (timer or collision) */
 #define ORC_F_GOAL 16u      /* the goal predicate held after some tick */
+#define ORC_F_NOISE 32u     /* the replayed noise stream ran out: later draws were 0.0 */
 #define ORC_F_TRIGRANGE 8u  /* |angle| beyond the supported sin/cos range (port mode only) */
 
 typedef struct {
@@ -184,7 +185,10 @@ static int orc_sense(const orc_cfg* c, orc_robot* rb, double* dst, const orc_tra
             tr->hitpx[2 * i + 1] = h.hit ? (int32_t)(int64_t)h.y : -1;
         }
         if ((d < c->vr0 + c->radius && d > c->vr0 * 0.125 + c->radius) || d > c->vr1 + c->radius) d = c->vr1 + c->radius;
-        else if (noise_stream) { d += (rb->ndraws < (uint32_t)c->noise_len) ? noise_stream[rb->ndraws] : 0.0; rb->ndraws++; }
+        else if (noise_stream) {
+            if (rb->ndraws < (uint32_t)c->noise_len) d += noise_stream[rb->ndraws]; else { d += 0.0; rb->flags |= ORC_F_NOISE; }
+            rb->ndraws++;
+        }
         dst[i] = d;
         if (tr && tr->dst) tr->dst[i] = d;
     }

@@ -48,6 +48,12 @@ _SIGS = {
     "r2p2_set_controller": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32]),
     "r2p2_set_noise": (C.c_int, [C.c_void_p, C.c_int32, C.c_uint64, C.c_void_p, C.c_int32, C.c_int32]),
     "r2p2_read_noise_draws": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "r2p2_set_robot_index_offset": (C.c_int, [C.c_void_p, C.c_uint32]),
+    "r2p2_population_size": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "r2p2_write_pose": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32] + [C.c_void_p] * 5),
+    "r2p2_ga_state_bytes": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
+    "r2p2_ga_save": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "r2p2_ga_load": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
     "r2p2_set_mapping": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32]),
     "r2p2_upload_genomes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
     "r2p2_set_genomes_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),

@@ -77,6 +77,7 @@ struct r2p2_sim {
     // sensor noise
     int noise_mode = 0, noise_len = 0, noise_P = 0;
     unsigned long long noise_seed = 0;
+    uint32_t robot_index0 = 0;       // global index of robot 0 (sharded populations)
     double* d_noise = nullptr;
     // trace
     bool trace = false;
@@ -127,6 +128,35 @@ int fail(r2p2_handle h, int code, const char* fmt, ...) {
         if (e_ != cudaSuccess) return fail(h, R2P2_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
     } while (0)
 
+// The caller's current device is restored when an entry point returns (a torch / multi-GPU host process keeps its own).
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int dev) {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != dev) { err = cudaSetDevice(dev); switched = (err == cudaSuccess); }
+    }
+    ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+#define ON_DEVICE(h)                                                                                           \
+    DeviceGuard dev_guard_((h)->device);                                                                       \
+    if (dev_guard_.err != cudaSuccess) return fail((h), R2P2_E_CUDA, "cudaSetDevice(%d): %s", (h)->device, cudaGetErrorString(dev_guard_.err))
+
+// Scratch device memory of one call: freed on every return path.
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    DevBuf() = default;
+    ~DevBuf() { if (p) cudaFree(p); }
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    cudaError_t alloc(size_t n) { return cudaMalloc(reinterpret_cast<void**>(&p), std::max<size_t>(n, 1) * sizeof(T)); }
+    operator T*() const { return p; }
+};
+
 template <typename T>
 cudaError_t dalloc(T** p, size_t n) {
     if (*p) { cudaFree(*p); *p = nullptr; }
@@ -174,8 +204,8 @@ int pack_stage(r2p2_handle h, const uint8_t* d_levels, int W, int H) {
     CK(dalloc(&h->d_l50, bytes / 4));
     CK(cudaMemsetAsync(h->d_wall, 0, bytes, h->stream));
     CK(cudaMemsetAsync(h->d_l50, 0, bytes, h->stream));
-    int* d_has = nullptr;
-    CK(cudaMalloc(&d_has, sizeof(int)));
+    DevBuf<int> d_has;
+    CK(d_has.alloc(1));
     CK(cudaMemsetAsync(d_has, 0, sizeof(int), h->stream));
     dim3 grid((H + 127) / 128, wpr);
     pack_stage_kernel<<<grid, 128, 0, h->stream>>>(d_levels, W, H, wpr, h->d_wall, h->d_l50, d_has);
@@ -184,8 +214,8 @@ int pack_stage(r2p2_handle h, const uint8_t* d_levels, int W, int H) {
     CK(dalloc(&h->d_levels, (size_t)W * H));
     CK(cudaMemcpyAsync(h->d_levels, d_levels, (size_t)W * H, cudaMemcpyDeviceToDevice, h->stream));
     // distance field (Chebyshev distance to the nearest wall / outer-ring pixel, saturated at 255)
-    uint8_t* d_hrow = nullptr;
-    CK(cudaMalloc(&d_hrow, (size_t)W * H));
+    DevBuf<uint8_t> d_hrow;
+    CK(d_hrow.alloc((size_t)W * H));
     CK(dalloc(&h->d_dist, (size_t)W * H));
     dist_rows_kernel<<<(H + 63) / 64, 64, 0, h->stream>>>(d_levels, W, H, d_hrow);
     dist_cols_kernel<<<dim3((W + 127) / 128, H), 128, 0, h->stream>>>(d_hrow, W, H, h->d_dist);
@@ -194,8 +224,6 @@ int pack_stage(r2p2_handle h, const uint8_t* d_levels, int W, int H) {
     int has = 0;
     CK(cudaMemcpyAsync(&has, d_has, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    cudaFree(d_has);
-    cudaFree(d_hrow);
     h->W = W; h->H = H; h->wpr = wpr; h->has50 = has; h->plane_bytes = (uint32_t)bytes;
     h->cfg_epoch++;
     h->stage_epoch++;
@@ -440,7 +468,8 @@ int r2p2_create(int device, r2p2_handle* out) {
     s->device = device;
     s->sm_count = prop.multiProcessorCount;
     s->smem_optin = prop.sharedMemPerBlockOptin;
-    e = cudaSetDevice(device);
+    DeviceGuard guard(device);                             // the caller's current device comes back when this returns
+    e = guard.err;
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking);
     s->stream = s->own_stream;
     if (e == cudaSuccess) e = cudaEventCreate(&s->ev0);
@@ -451,7 +480,8 @@ int r2p2_create(int device, r2p2_handle* out) {
     if (e == cudaSuccess) e = cudaMemcpy(s->d_sincostab, r2p2_h_sincostab, R2P2_SINCOSTAB_LEN * sizeof(double), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
         fail(nullptr, R2P2_E_CUDA, "r2p2_create: %s", cudaGetErrorString(e));
-        delete s;
+        cudaGetLastError();
+        r2p2_destroy(s);                                   // frees whatever was created (stream, events, buffers)
         return R2P2_E_CUDA;
     }
     *out = s;
@@ -460,8 +490,8 @@ int r2p2_create(int device, r2p2_handle* out) {
 
 int r2p2_destroy(r2p2_handle h) {
     if (!h) return R2P2_OK;
-    cudaSetDevice(h->device);
-    cudaStreamSynchronize(h->stream);
+    DeviceGuard guard(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
     StateArrays& s = h->st;
     void* ptrs[] = {s.x, s.y, s.theta, s.speed, s.omega, s.last_x, s.last_y, s.dist, s.odom_x, s.odom_y, s.origin_x, s.origin_y,
                     s.time, s.fitness, s.flags, s.ncollide, s.ticks, s.ndraws, s.goal_tick, s.nsamp_sonar, s.nsamp_coll, h->d_noise, h->d_x0, h->d_y0, h->d_t0,
@@ -469,15 +499,16 @@ int r2p2_destroy(r2p2_handle h) {
                     h->d_ga_pop[0], h->d_ga_pop[1], h->d_ga_fit, h->d_ga_elite, h->d_sense_dst, h->d_sense_px, h->d_cmd, h->d_levels, h->d_hot};
     for (void* p : ptrs) cudaFree(p);
     free_trace(h);
-    cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
-    cudaStreamDestroy(h->own_stream);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
     return R2P2_OK;
 }
 
 int r2p2_set_stream(r2p2_handle h, void* cuda_stream) {
     if (!h) return R2P2_E_ARG;
-    CK(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     CK(cudaStreamSynchronize(h->stream));
     h->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : h->own_stream;
     return R2P2_OK;
@@ -485,10 +516,10 @@ int r2p2_set_stream(r2p2_handle h, void* cuda_stream) {
 
 int r2p2_fp64_peak(r2p2_handle h, double* dfma_per_s) {
     if (!h || !dfma_per_s) return R2P2_E_ARG;
-    CK(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     const int blocks = h->sm_count * 8, threads = 256, iters = 1 << 16;
-    double* d = nullptr;
-    CK(cudaMalloc(&d, sizeof(double) * blocks * threads));
+    DevBuf<double> d;
+    CK(d.alloc((size_t)blocks * threads));
     float best = 1e30f;
     for (int rep = 0; rep < 4; ++rep) {
         CK(cudaEventRecord(h->ev0, h->stream));
@@ -501,7 +532,6 @@ int r2p2_fp64_peak(r2p2_handle h, double* dfma_per_s) {
         if (rep > 0) best = std::min(best, ms);
     }
     h->ev_valid = false;
-    cudaFree(d);
     *dfma_per_s = (double)blocks * threads * 8.0 * iters / (best * 1e-3);
     return R2P2_OK;
 }
@@ -510,23 +540,21 @@ int r2p2_set_stage(r2p2_handle h, const uint8_t* levels_xy, int32_t W, int32_t H
     if (!h) return R2P2_E_ARG;
     if (!levels_xy || W < 3 || H < 3) return fail(h, R2P2_E_ARG, "stage must be at least 3x3");
     if (W > 32768 || H > 32768) return fail(h, R2P2_E_LIMIT, "stage larger than 32768 px per side");
-    CK(cudaSetDevice(h->device));
-    uint8_t* d = nullptr;
-    CK(cudaMalloc(&d, (size_t)W * H));
+    ON_DEVICE(h);
+    DevBuf<uint8_t> d;
+    CK(d.alloc((size_t)W * H));
     CK(cudaMemcpyAsync(d, levels_xy, (size_t)W * H, cudaMemcpyHostToDevice, h->stream));
-    const int rc = pack_stage(h, d, W, H);
-    cudaFree(d);
-    return rc;
+    return pack_stage(h, d, W, H);
 }
 
 int r2p2_set_stage_i32(r2p2_handle h, const int32_t* levels_xy, int32_t W, int32_t H) {
     if (!h) return R2P2_E_ARG;
     if (!levels_xy || W < 3 || H < 3) return fail(h, R2P2_E_ARG, "stage must be at least 3x3");
     if (W > 32768 || H > 32768) return fail(h, R2P2_E_LIMIT, "stage larger than 32768 px per side");
-    CK(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     const size_t n = (size_t)W * H;
-    int32_t* d32 = nullptr; uint8_t* d8 = nullptr; int* d_bad = nullptr;
-    CK(cudaMalloc(&d32, n * 4)); CK(cudaMalloc(&d8, n)); CK(cudaMalloc(&d_bad, 4));
+    DevBuf<int32_t> d32; DevBuf<uint8_t> d8; DevBuf<int> d_bad;
+    CK(d32.alloc(n)); CK(d8.alloc(n)); CK(d_bad.alloc(1));
     CK(cudaMemsetAsync(d_bad, 0, 4, h->stream));
     CK(cudaMemcpyAsync(d32, levels_xy, n * 4, cudaMemcpyHostToDevice, h->stream));
     i32_to_u8_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(d32, d8, n, d_bad);
@@ -534,16 +562,14 @@ int r2p2_set_stage_i32(r2p2_handle h, const int32_t* levels_xy, int32_t W, int32
     int bad = 0;
     CK(cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    int rc = bad ? fail(h, R2P2_E_ARG, "stage levels must be grey values 0..255") : pack_stage(h, d8, W, H);
-    cudaFree(d32); cudaFree(d8); cudaFree(d_bad);
-    return rc;
+    return bad ? fail(h, R2P2_E_ARG, "stage levels must be grey values 0..255") : pack_stage(h, d8, W, H);
 }
 
 int r2p2_set_robot(r2p2_handle h, double vr0, double vr1, double radius, double max_speed, const double* ray_deg, int32_t n_rays) {
     if (!h) return R2P2_E_ARG;
     if (!ray_deg || n_rays < 1) return fail(h, R2P2_E_ARG, "need at least one sonar ray");
     if (n_rays > R2P2_MAX_RAYS) return fail(h, R2P2_E_LIMIT, "at most %d sonar rays", R2P2_MAX_RAYS);
-    CK(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     h->vr0 = vr0; h->vr1 = vr1; h->radius = radius; h->max_speed = max_speed; h->R = n_rays;
     memcpy(h->ray_deg, ray_deg, sizeof(double) * (size_t)n_rays);
     h->have_robot = true;
@@ -576,7 +602,7 @@ int r2p2_set_controller(r2p2_handle h, int32_t kind, const int32_t* layers, int3
 int r2p2_set_noise(r2p2_handle h, int32_t mode, uint64_t seed, const double* stream, int32_t P, int32_t len) {
     if (!h) return R2P2_E_ARG;
     if (mode < 0 || mode > 2) return fail(h, R2P2_E_ARG, "noise mode must be 0 (off), 1 (host stream) or 2 (device generator)");
-    CK(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     if (mode == 1) {
         if (!stream || P < 1 || len < 1) return fail(h, R2P2_E_ARG, "noise mode 1 needs a stream [P][len]");
         CK(cudaStreamSynchronize(h->stream));
@@ -590,10 +616,40 @@ int r2p2_set_noise(r2p2_handle h, int32_t mode, uint64_t seed, const double* str
     return R2P2_OK;
 }
 
+int r2p2_set_robot_index_offset(r2p2_handle h, uint32_t first) {
+    if (!h) return R2P2_E_ARG;
+    h->robot_index0 = first;
+    return R2P2_OK;
+}
+
+int r2p2_population_size(r2p2_handle h, int32_t* P, int32_t* G) {
+    if (!h) return R2P2_E_ARG;
+    if (P) *P = h->P;
+    if (G) *G = h->G;
+    return R2P2_OK;
+}
+
+int r2p2_write_pose(r2p2_handle h, int32_t first, int32_t count, const double* x, const double* y, const double* theta,
+                    const double* last_x, const double* last_y) {
+    if (!h) return R2P2_E_ARG;
+    if (h->P < 1 || !h->have_reset) return fail(h, R2P2_E_ARG, "r2p2_write_pose: population not initialised (r2p2_reset first)");
+    if (first < 0 || count < 0 || first + count > h->P) return fail(h, R2P2_E_ARG, "r2p2_write_pose: robots [%d, %d) out of range (P = %d)", first, first + count, h->P);
+    ON_DEVICE(h);
+    StateArrays& s = h->st;
+    const size_t nb = sizeof(double) * (size_t)count;
+    if (x) CK(cudaMemcpyAsync(s.x + first, x, nb, cudaMemcpyHostToDevice, h->stream));
+    if (y) CK(cudaMemcpyAsync(s.y + first, y, nb, cudaMemcpyHostToDevice, h->stream));
+    if (theta) CK(cudaMemcpyAsync(s.theta + first, theta, nb, cudaMemcpyHostToDevice, h->stream));
+    if (last_x) CK(cudaMemcpyAsync(s.last_x + first, last_x, nb, cudaMemcpyHostToDevice, h->stream));
+    if (last_y) CK(cudaMemcpyAsync(s.last_y + first, last_y, nb, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));              // the host arrays may be pageable and reused by the caller
+    return R2P2_OK;
+}
+
 int r2p2_read_noise_draws(r2p2_handle h, uint32_t* ndraws) {
     if (!h || !ndraws) return R2P2_E_ARG;
     if (h->P < 1) return fail(h, R2P2_E_ARG, "no population");
-    CK(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     CK(cudaMemcpyAsync(ndraws, h->st.ndraws, sizeof(uint32_t) * h->P, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return R2P2_OK;
@@ -612,7 +668,7 @@ int r2p2_set_mapping(r2p2_handle h, int32_t lanes_per_robot, int32_t stage_in_sm
 int r2p2_upload_genomes(r2p2_handle h, const double* genomes, int32_t P, int32_t G) {
     if (!h) return R2P2_E_ARG;
     if (!genomes || P < 1 || G < 1) return fail(h, R2P2_E_ARG, "genomes: need P >= 1, G >= 1");
-    CK(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     int rc = ensure_genomes(h, P, G);
     if (rc) return rc;
     CK(cudaMemcpyAsync(h->d_genomes, genomes, (size_t)P * G * sizeof(double), cudaMemcpyHostToDevice, h->stream));
@@ -623,7 +679,7 @@ int r2p2_upload_genomes(r2p2_handle h, const double* genomes, int32_t P, int32_t
 int r2p2_set_genomes_device(r2p2_handle h, const double* d_genomes, int32_t P, int32_t G) {
     if (!h) return R2P2_E_ARG;
     if (!d_genomes || P < 1 || G < 1) return fail(h, R2P2_E_ARG, "genomes: need P >= 1, G >= 1");
-    CK(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     int rc = ensure_genomes(h, P, G);
     if (rc) return rc;
     CK(cudaMemcpyAsync(h->d_genomes, d_genomes, (size_t)P * G * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
@@ -635,7 +691,7 @@ int r2p2_reset(r2p2_handle h, const double* x0, const double* y0, const double* 
     if (!h) return R2P2_E_ARG;
     if (h->P < 1) return fail(h, R2P2_E_ARG, "upload genomes (population size) before r2p2_reset");
     if (!x0 || !y0 || !theta0 || !(n == 1 || n == h->P)) return fail(h, R2P2_E_ARG, "reset: n must be 1 or P");
-    CK(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     CK(cudaMemcpyAsync(h->d_x0, x0, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_y0, y0, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_t0, theta0, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
@@ -691,6 +747,7 @@ static int fill_params(r2p2_handle h, KParams& kp, int32_t T, double delta, doub
     kp.nsamp_sonar = s.nsamp_sonar; kp.nsamp_coll = s.nsamp_coll;
     kp.ndraws = s.ndraws;
     kp.noise_mode = h->noise_mode; kp.noise_len = h->noise_len; kp.noise_seed = h->noise_seed; kp.noise_stream = h->d_noise;
+    kp.robot_index0 = h->robot_index0;
     if (h->noise_mode == 1 && h->noise_P != h->P) return fail(h, R2P2_E_ARG, "noise stream was uploaded for %d robots, population is %d", h->noise_P, h->P);
     kp.work_counter = h->d_work;
     kp.genomes = h->d_genomes;
@@ -720,7 +777,7 @@ int r2p2_run(r2p2_handle h, int32_t T, double delta, double delta_ctrl, int32_t 
         return fail(h, R2P2_E_ARG, "constant-command genome must be [speed, angular_velocity]");
     }
     if (h->trace && (T > h->trace_T)) return fail(h, R2P2_E_ARG, "trace enabled for at most %d ticks per run", h->trace_T);
-    CK(cudaSetDevice(h->device));
+    ON_DEVICE(h);
 
     KParams kp;
     int rc0 = fill_params(h, kp, T, delta, delta_ctrl, evolve);
@@ -770,17 +827,16 @@ int r2p2_cost_grid(r2p2_handle h, int32_t div_x, int32_t div_y, int32_t* values,
     if (!h->d_levels) return fail(h, R2P2_E_ARG, "r2p2_cost_grid: no stage (call r2p2_set_stage)");
     if (div_x < 1 || div_y < 1 || div_x > h->W || div_y > h->H) return fail(h, R2P2_E_ARG, "grid divisions must be in 1..W x 1..H");
     if (!values && !costs) return fail(h, R2P2_E_ARG, "values and costs are both NULL");
-    CK(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     const size_t n = (size_t)div_x * div_y;
-    int32_t *d_v = nullptr, *d_c = nullptr;
-    CK(cudaMalloc(&d_v, n * sizeof(int32_t))); CK(cudaMalloc(&d_c, n * sizeof(int32_t)));
+    DevBuf<int32_t> d_v, d_c;
+    CK(d_v.alloc(n)); CK(d_c.alloc(n));
     cost_grid_kernel<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(h->d_levels, h->W, h->H, div_x, div_y, d_v, d_c);
     h->launches++;
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess && values) e = cudaMemcpyAsync(values, d_v, n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess && costs) e = cudaMemcpyAsync(costs, d_c, n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-    cudaFree(d_v); cudaFree(d_c);
     if (e != cudaSuccess) return fail(h, R2P2_E_CUDA, "r2p2_cost_grid: %s", cudaGetErrorString(e));
     return R2P2_OK;
 }
@@ -795,7 +851,7 @@ int r2p2_set_goal(r2p2_handle h, int32_t enable, double gx, double gy) {
     if (ix < 0) ix += h->W;
     if (iy < 0) iy += h->H;
     if (ix < 0 || ix >= h->W || iy < 0 || iy >= h->H) return fail(h, R2P2_E_ARG, "goal pixel off the map (the reference raises IndexError)");
-    CK(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     uint32_t word = 0;
     CK(cudaMemcpyAsync(&word, h->d_wall + (size_t)iy * h->wpr + (size_t)(ix >> 5), sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -806,7 +862,7 @@ int r2p2_set_goal(r2p2_handle h, int32_t enable, double gx, double gy) {
 int r2p2_read_goal(r2p2_handle h, uint32_t* goal_tick) {
     if (!h || !goal_tick) return R2P2_E_ARG;
     if (h->P < 1) return fail(h, R2P2_E_ARG, "no population");
-    CK(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     CK(cudaMemcpyAsync(goal_tick, h->st.goal_tick, (size_t)h->P * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return R2P2_OK;
@@ -819,7 +875,7 @@ static int bridge_ready(r2p2_handle h, const char* who) {
     if (!h->have_robot) return fail(h, R2P2_E_ARG, "%s: no robot (call r2p2_set_robot)", who);
     if (h->P < 1 || !h->have_reset) return fail(h, R2P2_E_ARG, "%s: population not initialised (upload genomes to size it, then r2p2_reset)", who);
     if (h->P > h->bridge_cap || h->R != h->bridge_R) {
-        CK(cudaSetDevice(h->device));
+        ON_DEVICE(h);
         CK(cudaStreamSynchronize(h->stream));
         CK(dalloc(&h->d_sense_dst, (size_t)h->P * h->R));
         CK(dalloc(&h->d_sense_px, (size_t)h->P * h->R * 2));
@@ -832,7 +888,7 @@ static int bridge_ready(r2p2_handle h, const char* who) {
 int r2p2_sense(r2p2_handle h, double* dst, int32_t* hitpx) {
     int rc = bridge_ready(h, "r2p2_sense"); if (rc) return rc;
     if (!dst) return fail(h, R2P2_E_ARG, "dst is NULL");
-    CK(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     SenseParams sp;
     rc = fill_params(h, sp.k, 1, 0.0, 0.0, 0);
     if (rc) return rc;
@@ -852,7 +908,7 @@ int r2p2_move(r2p2_handle h, const double* commands, double delta) {
     int rc = bridge_ready(h, "r2p2_move"); if (rc) return rc;
     if (!commands) return fail(h, R2P2_E_ARG, "commands is NULL");
     if (h->trace && h->trace_T < 1) return fail(h, R2P2_E_ARG, "trace enabled for 0 ticks");
-    CK(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     CK(cudaMemcpyAsync(h->d_cmd, commands, (size_t)h->P * 2 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     KParams kp;
     rc = fill_params(h, kp, 1, delta, 0.0, 0);
@@ -878,7 +934,7 @@ int r2p2_move(r2p2_handle h, const double* commands, double delta) {
 
 int r2p2_sync(r2p2_handle h) {
     if (!h) return R2P2_E_ARG;
-    CK(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     CK(cudaStreamSynchronize(h->stream));
     return R2P2_OK;
 }
@@ -886,7 +942,7 @@ int r2p2_sync(r2p2_handle h) {
 int r2p2_last_run_ms(r2p2_handle h, float* ms) {
     if (!h || !ms) return R2P2_E_ARG;
     if (!h->ev_valid) return fail(h, R2P2_E_ARG, "no run yet");
-    CK(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     CK(cudaEventSynchronize(h->ev1));
     CK(cudaEventElapsedTime(ms, h->ev0, h->ev1));
     return R2P2_OK;
@@ -895,7 +951,7 @@ int r2p2_last_run_ms(r2p2_handle h, float* ms) {
 int r2p2_read_fitness(r2p2_handle h, double* fitness) {
     if (!h || !fitness) return R2P2_E_ARG;
     if (h->P < 1) return fail(h, R2P2_E_ARG, "no population");
-    CK(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     CK(cudaMemcpyAsync(fitness, h->st.fitness, sizeof(double) * h->P, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return R2P2_OK;
@@ -905,7 +961,7 @@ int r2p2_read_state(r2p2_handle h, double* x, double* y, double* theta, double* 
                     uint32_t* ncollide, uint32_t* ticks) {
     if (!h) return R2P2_E_ARG;
     if (h->P < 1) return fail(h, R2P2_E_ARG, "no population");
-    CK(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     const StateArrays& s = h->st;
     const size_t nb = sizeof(double) * h->P, nu = sizeof(uint32_t) * h->P;
     if (x) CK(cudaMemcpyAsync(x, s.x, nb, cudaMemcpyDeviceToHost, h->stream));
@@ -941,32 +997,50 @@ static int copy_state(r2p2_handle h, char* blob, bool to_host) {
     return R2P2_OK;
 }
 
+/* blob = StateHeader + the arrays of copy_state */
+struct StateHeader {
+    uint32_t magic, version;
+    int32_t P, R, G, kind;
+    uint32_t robot_index0, reserved;
+};
+static const uint32_t kStateMagic = 0x53503252u;   /* "R2PS" */
+static const uint32_t kStateVersion = 2u;
+
 int r2p2_state_bytes(r2p2_handle h, uint64_t* bytes) {
     if (!h || !bytes) return R2P2_E_ARG;
-    *bytes = (uint64_t)h->P * (16 * 8 + 5 * 4);
+    *bytes = sizeof(StateHeader) + (uint64_t)h->P * (16 * 8 + 5 * 4);
     return R2P2_OK;
 }
 
 int r2p2_save_state(r2p2_handle h, void* blob) {
     if (!h || !blob) return R2P2_E_ARG;
     if (h->P < 1 || !h->have_reset) return fail(h, R2P2_E_ARG, "r2p2_save_state: population not initialised");
-    CK(cudaSetDevice(h->device));
-    return copy_state(h, (char*)blob, true);
+    ON_DEVICE(h);
+    StateHeader hd = {kStateMagic, kStateVersion, h->P, h->R, h->G, h->have_ctrl ? h->kind : -1, h->robot_index0, 0u};
+    memcpy(blob, &hd, sizeof hd);
+    return copy_state(h, (char*)blob + sizeof hd, true);
 }
 
 int r2p2_load_state(r2p2_handle h, const void* blob) {
     if (!h || !blob) return R2P2_E_ARG;
     if (h->P < 1) return fail(h, R2P2_E_ARG, "r2p2_load_state: no population (upload genomes first)");
-    CK(cudaSetDevice(h->device));
-    const int rc = copy_state(h, (char*)blob, false);
-    if (rc == R2P2_OK) h->have_reset = true;
+    StateHeader hd;
+    memcpy(&hd, blob, sizeof hd);
+    if (hd.magic != kStateMagic) return fail(h, R2P2_E_ARG, "r2p2_load_state: not a state blob (bad magic)");
+    if (hd.version != kStateVersion) return fail(h, R2P2_E_ARG, "r2p2_load_state: blob format version %u, this library reads %u", hd.version, kStateVersion);
+    if (hd.P != h->P || hd.R != h->R || hd.G != h->G || hd.kind != (h->have_ctrl ? h->kind : -1))
+        return fail(h, R2P2_E_ARG, "r2p2_load_state: blob was saved for P=%d R=%d G=%d controller %d; this handle has P=%d R=%d G=%d controller %d",
+                    hd.P, hd.R, hd.G, hd.kind, h->P, h->R, h->G, h->have_ctrl ? h->kind : -1);
+    ON_DEVICE(h);
+    const int rc = copy_state(h, (char*)blob + sizeof hd, false);
+    if (rc == R2P2_OK) { h->have_reset = true; h->robot_index0 = hd.robot_index0; }
     return rc;
 }
 
 int r2p2_read_counters(r2p2_handle h, uint64_t* sonar_samples, uint64_t* collision_samples, uint64_t* robot_steps) {
     if (!h) return R2P2_E_ARG;
     if (h->P < 1) return fail(h, R2P2_E_ARG, "no population");
-    CK(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     CK(cudaMemsetAsync(h->d_cnt3, 0, 3 * sizeof(unsigned long long), h->stream));
     const int blocks = std::min((h->P + 255) / 256, 4 * h->sm_count);
     sum_counters_kernel<<<blocks, 256, 0, h->stream>>>(h->st.nsamp_sonar, h->st.nsamp_coll, h->st.ticks, h->P, h->d_cnt3);
@@ -996,7 +1070,7 @@ int r2p2_launch_count(r2p2_handle h, uint64_t* n) {
 
 int r2p2_set_trace(r2p2_handle h, int32_t enable, int32_t T_max) {
     if (!h) return R2P2_E_ARG;
-    CK(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     CK(cudaStreamSynchronize(h->stream));
     free_trace(h);
     h->trace = false;
@@ -1015,7 +1089,7 @@ int r2p2_read_trace(r2p2_handle h, int32_t T, double* pose, double* dst, int32_t
     if (!h) return R2P2_E_ARG;
     if (!h->trace) return fail(h, R2P2_E_ARG, "trace not enabled");
     if (T < 0 || T > h->trace_T) return fail(h, R2P2_E_ARG, "T out of range");
-    CK(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     const size_t rows = (size_t)T * h->trace_P, R = (size_t)h->trace_R;
     if (pose) CK(cudaMemcpyAsync(pose, h->tr_pose, rows * 5 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     if (dst) CK(cudaMemcpyAsync(dst, h->tr_dst, rows * R * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -1032,7 +1106,7 @@ int r2p2_read_trace_collisions(r2p2_handle h, int32_t T, double* cinfo) {
     if (!h->trace) return fail(h, R2P2_E_ARG, "trace not enabled");
     if (T < 0 || T > h->trace_T) return fail(h, R2P2_E_ARG, "T out of range");
     if (!cinfo) return fail(h, R2P2_E_ARG, "cinfo is NULL");
-    CK(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     CK(cudaMemcpyAsync(cinfo, h->tr_cinfo, (size_t)T * h->trace_P * 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return R2P2_OK;
@@ -1049,7 +1123,7 @@ int r2p2_ga_create(r2p2_handle h, int32_t P, int32_t G, uint64_t seed, double mi
     if (!h) return R2P2_E_ARG;
     if (P < 2 || G < 1) return fail(h, R2P2_E_ARG, "GA: need P >= 2, G >= 1");
     if (!(min_gen < max_gen)) return fail(h, R2P2_E_ARG, "GA: need min_gen < max_gen");
-    CK(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     CK(cudaStreamSynchronize(h->stream));
     for (int i = 0; i < 2; ++i) CK(dalloc(&h->d_ga_pop[i], (size_t)P * G));
     CK(dalloc(&h->d_ga_fit, (size_t)P));
@@ -1091,7 +1165,7 @@ int r2p2_ga_fitness_device(r2p2_handle h, double** d_fit) {
 int r2p2_ga_write_fitness(r2p2_handle h, const double* fitness, int32_t first, int32_t count) {
     int rc = ga_ready(h); if (rc) return rc;
     if (!fitness || first < 0 || count < 0 || first + count > h->ga_P) return fail(h, R2P2_E_ARG, "GA: fitness range out of bounds");
-    CK(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     CK(cudaMemcpyAsync(h->d_ga_fit + first, fitness, (size_t)count * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return R2P2_OK;
@@ -1099,7 +1173,7 @@ int r2p2_ga_write_fitness(r2p2_handle h, const double* fitness, int32_t first, i
 
 int r2p2_ga_read(r2p2_handle h, double* population, double* fitness) {
     int rc = ga_ready(h); if (rc) return rc;
-    CK(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     if (population) CK(cudaMemcpyAsync(population, h->d_ga_pop[h->ga_cur], (size_t)h->ga_P * h->ga_G * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     if (fitness) CK(cudaMemcpyAsync(fitness, h->d_ga_fit, (size_t)h->ga_P * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -1112,6 +1186,7 @@ int r2p2_ga_evaluate(r2p2_handle h, int32_t first, int32_t count, int32_t T, dou
     if (!h->have_pose1) return fail(h, R2P2_E_ARG, "GA: no start pose (call r2p2_reset with n == 1 once)");
     rc = r2p2_set_genomes_device(h, h->d_ga_pop[h->ga_cur] + (size_t)first * h->ga_G, count, h->ga_G);
     if (rc) return rc;
+    h->robot_index0 = (uint32_t)first;                     // the device noise generator is keyed by the global individual index
     rc = r2p2_reset(h, &h->rx0, &h->ry0, &h->rt0, 1, h->rbudget);
     if (rc) return rc;
     rc = r2p2_run(h, T, delta, delta_ctrl, evolve);
@@ -1122,7 +1197,7 @@ int r2p2_ga_evaluate(r2p2_handle h, int32_t first, int32_t count, int32_t T, dou
 
 int r2p2_ga_breed(r2p2_handle h) {
     int rc = ga_ready(h); if (rc) return rc;
-    CK(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     GaParams g;
     g.P = h->ga_P; g.G = h->ga_G; g.tournament = h->ga_tournament; g.elites = std::min(h->ga_elites, h->ga_P);
     g.crossover_rate = h->ga_cx; g.mutation_rate = h->ga_mut; g.mutation_sigma = h->ga_sigma; g.min_gen = h->ga_min; g.max_gen = h->ga_max;
@@ -1142,7 +1217,7 @@ int r2p2_ga_breed(r2p2_handle h) {
 int r2p2_ga_best(r2p2_handle h, int32_t* index, double* fitness, double* genome) {
     int rc = ga_ready(h); if (rc) return rc;
     if (h->ga_generation == 0) return fail(h, R2P2_E_ARG, "GA: no generation bred yet");
-    CK(cudaSetDevice(h->device));
+    ON_DEVICE(h);
     int idx = -1;
     CK(cudaMemcpyAsync(&idx, h->d_ga_elite, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -1151,6 +1226,62 @@ int r2p2_ga_best(r2p2_handle h, int32_t* index, double* fitness, double* genome)
     if (fitness) CK(cudaMemcpyAsync(fitness, h->d_ga_fit + idx, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     if (genome) CK(cudaMemcpyAsync(genome, h->d_ga_pop[h->ga_cur ^ 1] + (size_t)idx * h->ga_G, (size_t)h->ga_G * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    return R2P2_OK;
+}
+
+struct GaHeader {
+    uint32_t magic, version;
+    int32_t P, G, tournament, elites, cur_unused, reserved;
+    uint64_t seed;
+    uint32_t generation, pad;
+    double min_gen, max_gen, cx, mut, sigma;
+};
+static const uint32_t kGaMagic = 0x47503252u;      /* "R2PG" */
+
+int r2p2_ga_state_bytes(r2p2_handle h, uint64_t* bytes) {
+    int rc = ga_ready(h); if (rc) return rc;
+    if (!bytes) return fail(h, R2P2_E_ARG, "bytes is NULL");
+    *bytes = sizeof(GaHeader) + ((uint64_t)h->ga_P * h->ga_G + (uint64_t)h->ga_P) * sizeof(double);
+    return R2P2_OK;
+}
+
+int r2p2_ga_save(r2p2_handle h, void* blob) {
+    int rc = ga_ready(h); if (rc) return rc;
+    if (!blob) return fail(h, R2P2_E_ARG, "blob is NULL");
+    ON_DEVICE(h);
+    GaHeader hd;
+    memset(&hd, 0, sizeof hd);
+    hd.magic = kGaMagic; hd.version = 1u; hd.P = h->ga_P; hd.G = h->ga_G; hd.tournament = h->ga_tournament; hd.elites = h->ga_elites;
+    hd.seed = h->ga_seed; hd.generation = h->ga_generation;
+    hd.min_gen = h->ga_min; hd.max_gen = h->ga_max; hd.cx = h->ga_cx; hd.mut = h->ga_mut; hd.sigma = h->ga_sigma;
+    memcpy(blob, &hd, sizeof hd);
+    char* q = (char*)blob + sizeof hd;
+    const size_t npop = (size_t)h->ga_P * h->ga_G * sizeof(double);
+    CK(cudaMemcpyAsync(q, h->d_ga_pop[h->ga_cur], npop, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(q + npop, h->d_ga_fit, (size_t)h->ga_P * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return R2P2_OK;
+}
+
+int r2p2_ga_load(r2p2_handle h, const void* blob, uint64_t bytes) {
+    if (!h) return R2P2_E_ARG;
+    if (!blob || bytes < sizeof(GaHeader)) return fail(h, R2P2_E_ARG, "r2p2_ga_load: blob too short");
+    GaHeader hd;
+    memcpy(&hd, blob, sizeof hd);
+    if (hd.magic != kGaMagic || hd.version != 1u) return fail(h, R2P2_E_ARG, "r2p2_ga_load: not a GA blob of format version 1");
+    if (hd.P < 2 || hd.G < 1 || bytes != sizeof(GaHeader) + ((uint64_t)hd.P * hd.G + (uint64_t)hd.P) * sizeof(double))
+        return fail(h, R2P2_E_ARG, "r2p2_ga_load: blob size does not match its header (P=%d, G=%d)", hd.P, hd.G);
+    int rc = r2p2_ga_create(h, hd.P, hd.G, hd.seed, hd.min_gen, hd.max_gen);
+    if (rc) return rc;
+    rc = r2p2_ga_set_operators(h, hd.tournament, hd.cx, hd.mut, hd.sigma, hd.elites);
+    if (rc) return rc;
+    ON_DEVICE(h);
+    const char* q = (const char*)blob + sizeof hd;
+    const size_t npop = (size_t)hd.P * hd.G * sizeof(double);
+    CK(cudaMemcpyAsync(h->d_ga_pop[0], q, npop, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_ga_fit, q + npop, (size_t)hd.P * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->ga_cur = 0; h->ga_generation = hd.generation;
     return R2P2_OK;
 }
 
@@ -1178,27 +1309,26 @@ static int cast_rays_impl(r2p2_handle h, int plain, int32_t n, const double* ox,
     if (!h) return R2P2_E_ARG;
     if (!h->d_wall) return fail(h, R2P2_E_ARG, "no stage");
     if (n < 1 || !ox || !oy || !angle_rad || !limit || !status || !hx || !hy || !k || !nsamp) return fail(h, R2P2_E_ARG, "cast_rays: bad arguments");
-    CK(cudaSetDevice(h->device));
-    double* d_in = nullptr; double* d_out = nullptr; int32_t* d_i = nullptr;
-    CK(cudaMalloc(&d_in, sizeof(double) * 4 * n)); CK(cudaMalloc(&d_out, sizeof(double) * 2 * n)); CK(cudaMalloc(&d_i, sizeof(int32_t) * 3 * n));
+    ON_DEVICE(h);
+    DevBuf<double> d_in, d_out; DevBuf<int32_t> d_i;
+    CK(d_in.alloc((size_t)4 * n)); CK(d_out.alloc((size_t)2 * n)); CK(d_i.alloc((size_t)3 * n));
     const size_t nb = sizeof(double) * n;
     CK(cudaMemcpyAsync(d_in, ox, nb, cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(d_in + n, oy, nb, cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(d_in + 2 * n, angle_rad, nb, cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(d_in + 3 * n, limit, nb, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d_in.p + n, oy, nb, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d_in.p + 2 * n, angle_rad, nb, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(d_in.p + 3 * n, limit, nb, cudaMemcpyHostToDevice, h->stream));
     StageView sv; sv.wall = h->d_wall; sv.lvl50 = h->d_l50; sv.dist = h->d_dist; sv.W = h->W; sv.H = h->H; sv.wpr = h->wpr;
     sv.hot = nullptr; sv.hwpr = 0; sv.hx0 = sv.hy0 = 1; sv.hx1 = sv.hy1 = 0; sv.win_sb = 0u; sv.win_ww = 0;       // r2p2_cast_rays: the distance-field march and the plain loop
-    cast_rays_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(sv, plain, h->d_sincostab, n, d_in, d_in + n, d_in + 2 * n, d_in + 3 * n,
-                                                             d_i, d_out, d_out + n, d_i + n, reinterpret_cast<uint32_t*>(d_i + 2 * n));
+    cast_rays_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(sv, plain, h->d_sincostab, n, d_in.p, d_in.p + n, d_in.p + 2 * n, d_in.p + 3 * n,
+                                                             d_i.p, d_out.p, d_out.p + n, d_i.p + n, reinterpret_cast<uint32_t*>(d_i.p + 2 * n));
     h->launches++;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(status, d_i, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(k, d_i + n, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(nsamp, d_i + 2 * n, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(k, d_i.p + n, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(nsamp, d_i.p + 2 * n, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(hx, d_out, nb, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(hy, d_out + n, nb, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(hy, d_out.p + n, nb, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    cudaFree(d_in); cudaFree(d_out); cudaFree(d_i);
     return R2P2_OK;
 }
 

@@ -460,6 +460,7 @@ __global__ void __launch_bounds__(kBlock, (NET::kLayers > 0 && !NET::kSmemWeight
                 fitness = R2P2_ADD(dist, r2p2_norm2(R2P2_SUB(odom_x, origin_x), R2P2_SUB(odom_y, origin_y)));
         }
         const unsigned ns_sonar = g.sum_u(my_ns_sonar);
+        if (p.noise_mode == 1 && ndraws > (unsigned)p.noise_len) flags |= R2P2_F_NOISE;   // the replayed stream ran out
         if (valid && g.sub == 0) {
             p.x[rb] = x; p.y[rb] = y; p.theta[rb] = theta; p.speed[rb] = speed; p.omega[rb] = omega;
             p.last_x[rb] = last_x; p.last_y[rb] = last_y;

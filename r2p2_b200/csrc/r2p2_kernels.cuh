@@ -86,6 +86,7 @@ struct KParams {
     int32_t noise_mode;                // 0 off, 1 host stream, 2 device generator
     int32_t noise_len;                 // draws per robot in noise_stream
     unsigned long long noise_seed;
+    uint32_t robot_index0;             // global index of robot 0 (sharded populations): key of the device noise generator
     const double* noise_stream;        // [P][noise_len], consumed one per unclamped ray in ray order
     uint32_t* ndraws;                  // [P] draws consumed so far
     // trace (optional)
@@ -723,7 +724,7 @@ __device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint
 }
 __device__ __forceinline__ double noise_draw(const KParams& p, unsigned rb, unsigned idx) {
     if (p.noise_mode == 1) return (idx < (unsigned)p.noise_len) ? __ldg(p.noise_stream + (size_t)rb * p.noise_len + idx) : 0.0;
-    uint32_t c[4] = {idx, rb, 0u, 0u};
+    uint32_t c[4] = {idx, rb + p.robot_index0, 0u, 0u};
     uint32_t k0 = (uint32_t)p.noise_seed, k1 = (uint32_t)(p.noise_seed >> 32);
 #pragma unroll
     for (int r = 0; r < 10; ++r) { philox_round(c, k0, k1); k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
@@ -1419,6 +1420,7 @@ __global__ void __launch_bounds__(kBlock, (NET::kLayers > 0 && !NET::kSmemWeight
         if (!(flags & R2P2_F_DONE))      // controller.fitness() after the last update
             fitness = R2P2_ADD(dist, r2p2_norm2(R2P2_SUB(odom_x, origin_x), R2P2_SUB(odom_y, origin_y)));
         const unsigned ns_sonar = (LPR == 1) ? my_ns_sonar : g.sum_u(my_ns_sonar);
+        if (p.noise_mode == 1 && ndraws > (unsigned)p.noise_len) flags |= R2P2_F_NOISE;   // the replayed stream ran out
         if (g.sub == 0) {
             p.x[rb] = x; p.y[rb] = y; p.theta[rb] = theta; p.speed[rb] = speed; p.omega[rb] = omega;
             p.last_x[rb] = last_x; p.last_y[rb] = last_y;
@@ -1657,6 +1659,7 @@ __global__ void sense_kernel(const __grid_constant__ SenseParams sp) {
         }
     }
     if (fault) flags |= R2P2_F_FAULT;
+    if (p.noise_mode == 1 && ndraws > (unsigned)p.noise_len) flags |= R2P2_F_NOISE;
     p.flags[rb] = flags;
     p.nsamp_sonar[rb] += ns;
     if (p.noise_mode) p.ndraws[rb] = ndraws;

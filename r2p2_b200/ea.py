@@ -127,6 +127,19 @@ class DeviceGA:
         self._ck(self._L.r2p2_ga_evaluate(self._h, int(first), int(count), int(ticks), float(delta),
                                           float(delta if delta_ctrl is None else delta_ctrl), int(bool(evolve))))
 
+    def save(self):
+        """Checkpoint of the EA (bytes): seed, range, operators, generation counter, current generation and fitness."""
+        n = self._C.c_uint64()
+        self._ck(self._L.r2p2_ga_state_bytes(self._h, self._C.byref(n)))
+        blob = np.empty(n.value, dtype=np.uint8)
+        self._ck(self._L.r2p2_ga_save(self._h, blob.ctypes.data))
+        return blob.tobytes()
+
+    def load(self, blob):
+        """Resume from ``save()``: the next ``breed`` draws exactly what the saved run would have drawn."""
+        b = np.frombuffer(blob, dtype=np.uint8)
+        self._ck(self._L.r2p2_ga_load(self._h, b.ctypes.data, int(b.size)))
+
     def write_fitness(self, fitness, first=0):
         f = np.ascontiguousarray(fitness, dtype=np.float64)
         self._ck(self._L.r2p2_ga_write_fitness(self._h, f.ctypes.data, int(first), int(f.size)))

@@ -40,7 +40,7 @@ class BatchSim:
             raise R2P2Error("r2p2_create failed (%d): %s" % (rc, msg.decode() if msg else "?"))
         self._h = h
         self.device = int(device)
-        self.P = self.G = self.R = 0
+        self.R = 0
         self._trace_T = 0
         self._keep = []
 
@@ -57,6 +57,21 @@ class BatchSim:
 
     def _ck(self, rc):
         check(self._h, rc)
+
+    # The population size lives in the library (r2p2_ga_evaluate resizes it to the evaluated shard): every host buffer
+    # below is sized from what the library reports, never from a value cached here.
+    def _size(self):
+        P, G = C.c_int32(), C.c_int32()
+        self._ck(self._L.r2p2_population_size(self._h, C.byref(P), C.byref(G)))
+        return P.value, G.value
+
+    @property
+    def P(self):
+        return self._size()[0]
+
+    @property
+    def G(self):
+        return self._size()[1]
 
     def set_stream(self, cuda_stream):
         """Run on the caller's CUDA stream (integer cudaStream_t, e.g. torch.cuda.current_stream().cuda_stream)."""
@@ -121,17 +136,14 @@ class BatchSim:
         if g.ndim != 2:
             raise ValueError("genomes must be [P, G]")
         self._keep = [g]
-        self.P, self.G = g.shape
-        self._ck(self._L.r2p2_upload_genomes(self._h, g.ctypes.data, self.P, self.G))
+        self._ck(self._L.r2p2_upload_genomes(self._h, g.ctypes.data, g.shape[0], g.shape[1]))
 
     def upload_genomes_ptr(self, host_ptr, P, G):
         """Host pointer variant (e.g. a pinned torch tensor's data_ptr()); the buffer must stay alive."""
-        self.P, self.G = int(P), int(G)
-        self._ck(self._L.r2p2_upload_genomes(self._h, C.c_void_p(int(host_ptr)), self.P, self.G))
+        self._ck(self._L.r2p2_upload_genomes(self._h, C.c_void_p(int(host_ptr)), int(P), int(G)))
 
     def set_genomes_device(self, dev_ptr, P, G):
-        self.P, self.G = int(P), int(G)
-        self._ck(self._L.r2p2_set_genomes_device(self._h, C.c_void_p(int(dev_ptr)), self.P, self.G))
+        self._ck(self._L.r2p2_set_genomes_device(self._h, C.c_void_p(int(dev_ptr)), int(P), int(G)))
 
     def reset(self, x0, y0, theta0=0.0, time_budget=20000.0):
         x0, y0, t0 = np.atleast_1d(_f64(x0)), np.atleast_1d(_f64(y0)), np.atleast_1d(_f64(theta0))
@@ -139,6 +151,18 @@ class BatchSim:
         if n > 1:
             x0, y0, t0 = (_f64(np.broadcast_to(a, (n,))) for a in (x0, y0, t0))
         self._ck(self._L.r2p2_reset(self._h, x0.ctypes.data, y0.ctypes.data, t0.ctypes.data, n, float(time_budget)))
+
+    def write_pose(self, first, x=None, y=None, theta=None, last_x=None, last_y=None):
+        """Overwrite pose attributes of robots [first, first + n) as host code does in the reference (set_position,
+        set_last_position, ``robot.orientation = ...``); odometry, fitness and flags are left alone."""
+        arrs = [None if a is None else np.atleast_1d(_f64(a)) for a in (x, y, theta, last_x, last_y)]
+        n = max(len(a) for a in arrs if a is not None)
+        assert all(a is None or len(a) == n for a in arrs)
+        self._ck(self._L.r2p2_write_pose(self._h, int(first), n, *[None if a is None else a.ctypes.data for a in arrs]))
+
+    def set_robot_index_offset(self, first):
+        """Index of robot 0 in the whole sharded population (keys the device noise generator)."""
+        self._ck(self._L.r2p2_set_robot_index_offset(self._h, int(first)))
 
     # ---- execution -----------------------------------------------------------------------------
     def run(self, T, delta=0.1, delta_ctrl=None, evolve=False):
@@ -154,7 +178,10 @@ class BatchSim:
 
     # ---- results ---------------------------------------------------------------------------------
     def fitness(self, out=None):
-        f = np.empty(self.P) if out is None else out
+        P = self.P
+        f = np.empty(P) if out is None else out
+        if f.size < P or f.dtype != np.float64 or not f.flags["C_CONTIGUOUS"]:
+            raise ValueError("fitness buffer must be a contiguous float64 array of at least %d elements" % P)
         self._ck(self._L.r2p2_read_fitness(self._h, f.ctypes.data))
         return f
 
@@ -189,9 +216,10 @@ class BatchSim:
     def set_trace(self, enable, T_max=1):
         self._ck(self._L.r2p2_set_trace(self._h, int(bool(enable)), int(T_max)))
         self._trace_T = int(T_max) if enable else 0
+        self._trace_P = self.P if enable else 0                # the library copies rows of THIS population size
 
     def trace(self, T):
-        P, R = self.P, self.R
+        P, R = self._trace_P, self.R
         out = {"pose": np.empty((T, P, 5)), "dst": np.empty((T, P, R)), "hitk": np.empty((T, P, R), dtype=np.int32),
                "hitpx": np.empty((T, P, R, 2), dtype=np.int32), "nsamp": np.empty((T, P, R), dtype=np.uint32),
                "ncoll": np.empty((T, P), dtype=np.uint32)}
@@ -217,6 +245,8 @@ class BatchSim:
         self._ck(self._L.r2p2_state_bytes(self._h, C.byref(n)))
         if b.size != n.value:
             raise ValueError("snapshot of %d bytes does not fit a population of %d robots (%d bytes)" % (b.size, self.P, n.value))
+        if b[:4].tobytes() != b"R2PS":
+            raise ValueError("not a state snapshot (bad magic)")
         self._ck(self._L.r2p2_load_state(self._h, b.ctypes.data))
 
     # ---- path planner's cost grid --------------------------------------------------------------------
