@@ -15,3 +15,6 @@ class Naive_controller(Controller):
 
     def device_spec(self, n_rays):
         return dict(kind="const", hidden_layer=None, activation="tanh", genome=list(self.command))
+
+
+Naive_Controller = Naive_controller      # the reference's spelling (conf/controller-naive.json: "naive_controller.Naive_Controller")

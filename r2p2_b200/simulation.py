@@ -1,8 +1,9 @@
 """Headless simulation driver: the reference's ``utils.load_simulation`` / ``create_robot(s)`` / ``update_loop``
 (r2p2/utils.py:118-234, 273-280, 302-303) without pygame, batched on the device.
 
-``Simulation`` groups the scenario's robots by (robot json, controller shape) and advances every group with one
-kernel launch per tick; ``run(ticks)`` advances all ticks in one launch.
+``Simulation`` groups the scenario's robots by (robot json, controller shape) -- ``group.RobotGroup`` -- and advances
+every group with one kernel launch (device controllers) or one sense + one move launch (host controllers) per tick and
+one read-back, instead of the reference's per-robot loop (utils.py:226-227, 233-234).
 """
 import json
 
@@ -10,8 +11,8 @@ import numpy as np
 
 from .config_manager import ConfigManager
 from .controllers.controllers import get_controllers
+from .group import RobotGroup, group_key
 from .robot import Robot
-from .sim import BatchSim
 
 
 def load_image(infilename):
@@ -51,11 +52,23 @@ class Simulation:
         for i, path in enumerate(paths):                       # utils.create_robots (utils.py:175-190)
             c = ctrls[i] if i < len(ctrls) else ctrls[0]
             self.robots.append(create_robot(self.cm.resolve(path), c, device=device))
+        self.device = device
+        self.groups = None
 
-    def update(self, delta):
-        """One pass of ``for r in robots: r.update(npdata, delta, True)`` (utils.py:226-227, 233-234)."""
+    def _make_groups(self):
+        """Robots in scenario order, grouped by what a launch has to share; a group keeps that order."""
+        buckets = {}
         for r in self.robots:
-            r.update(self.env, delta, True)
+            buckets.setdefault(group_key(r), []).append(r)
+        self.groups = [RobotGroup(rs, self.env, device=self.device) for rs in buckets.values()]
+
+    def update(self, delta, write_stats=True):
+        """One pass of ``for r in robots: r.update(npdata, delta, True)`` (utils.py:226-227, 233-234): one launch and one
+        read-back per group."""
+        if self.groups is None:
+            self._make_groups()
+        for g in self.groups:
+            g.update(delta, write_stats)
 
     def run(self, ticks, delta=0.1):
         for _ in range(ticks):

@@ -456,6 +456,59 @@ def gen_grids(E):
     np.savez_compressed(os.path.join(OUT, "grids.npz"), specs=json.dumps(specs), **out)
 
 
+def gen_host_controllers(E):
+    """Episodes driven by reference controllers that have no device form -- naive_controller.Naive_Controller (constant
+    command) and pid_controller.Sequential_PID_Controller (goal list, PID terms, obstacle-avoid state machine, backing
+    off after a collision; controller-PID.json and controller-PID2.json) -- run by the unmodified reference on stage.png
+    with robot.json (scenario-naive-test / scenario-PID).  Per tick: the distances handed to control(), the command it
+    returned, the pose after the tick, collide() calls, and the controller's own state -> tests/golden/host_controllers.npz."""
+    out, specs = {}, []
+
+    def run(name, ctrl, T, conf_name=None):
+        env = counting(E.load_env("stage.png"))
+        E.u.npdata = env                                   # utils.display_image publishes the transposed stage (utils.py:302-303)
+        with contextlib.redirect_stdout(io.StringIO()):
+            r = E.make_robot("robot.json", ctrl)
+        ncol = [0]
+        orig_oc, orig_ctl = ctrl.on_collision, ctrl.control
+        cmds = []
+
+        def oc(pos):
+            ncol[0] += 1
+            orig_oc(pos)
+
+        def ctl(dst):
+            c = orig_ctl(dst)
+            cmds.append((float(c[0]), float(c[1])))
+            return c
+        ctrl.on_collision, ctrl.control = oc, ctl
+        R = len(r.sensors)
+        pose = np.zeros((T, 5)); dst = np.zeros((T, R)); ncoll = np.zeros(T, dtype=np.int32); aux = np.zeros((T, 4))
+        start = (float(r.x), float(r.y), float(r.orientation))
+        for t in range(T):
+            r.update(env, 0.1, False)
+            pose[t] = (r.x, r.y, r.orientation, r.speed, r.angular_velocity)
+            dst[t] = [10000.0 if d == math.inf else d for d in ctrl.dst]
+            ncoll[t] = ncol[0]
+            aux[t] = (len(getattr(ctrl, "goal", [])), getattr(ctrl, "state", 0), float(getattr(ctrl, "backing", 0)), getattr(ctrl, "target_angle", 0.0))
+        out[name + "/pose"] = pose; out[name + "/dst"] = dst; out[name + "/ncoll"] = ncoll; out[name + "/aux"] = aux
+        out[name + "/cmd"] = np.asarray(cmds, dtype=np.float64); out[name + "/start"] = np.asarray(start)
+        specs.append({"name": name, "T": T, "stage": "stage.png", "robot": "robot.json", "conf": conf_name})
+        print("host controller", name, "T", T, "collides", ncol[0], "goals left", aux[-1, 0], "final pose", pose[-1, :3])
+
+    naive = E._import_controller("naive_controller")
+    run("naive", naive.Naive_Controller({}), 400)
+    pidm = E._import_controller("pid_controller")
+    import shutil
+    for conf_name in ("controller-PID.json", "controller-PID2.json"):
+        # the class reads a hard-coded ../conf/controller-PID.json (pid_controller.py:18)
+        if conf_name != "controller-PID.json":
+            shutil.copyfile(os.path.join(ref_harness.REF, "conf", conf_name), os.path.join(E.tmp, "conf", "controller-PID.json"))
+        run("pid_" + conf_name.replace("controller-", "").replace(".json", ""), pidm.Sequential_PID_Controller({}), 1500, conf_name)
+    shutil.copyfile(os.path.join(ref_harness.REF, "conf", "controller-PID.json"), os.path.join(E.tmp, "conf", "controller-PID.json"))
+    np.savez_compressed(os.path.join(OUT, "host_controllers.npz"), meta=meta(), specs=json.dumps(specs), **out)
+
+
 def gen_conf():
     """The reference's conf/*.json, byte for byte -> tests/golden/conf/ (robot / controller / scenario numbers are read
     from these copies by tests/common.py and bench.py instead of being typed in)."""
@@ -484,6 +537,9 @@ def main():
         if "--goal-only" in sys.argv:
             gen_goal(E)
             return
+        if "--host-controllers-only" in sys.argv:
+            gen_host_controllers(E)
+            return
         if "--logs-only" in sys.argv:
             gen_logs(E)
             return
@@ -499,6 +555,7 @@ def main():
         gen_logs(E)
         gen_goal(E)
         gen_grids(E)
+        gen_host_controllers(E)
         # stage bitmaps as the reference loads them (env[x, y], int32) -- fixtures for the GPU box
         for stage in STAGES:
             env = np.ascontiguousarray(E.load_env(stage)).astype(np.uint8)
