@@ -374,29 +374,29 @@ int launch_episode_s(r2p2_handle h, KParams& kp, bool smem_stage, int* occ_out) 
     if constexpr (LPR >= 16) if (!smem_stage) {
         if (net_matches<NetNeuro>(kp)) {
             kp.w_in_smem = 0;
-            return launch_episode<LPR, false, NetNeuro>(h, kp, episode_smem_bytes(LPR, false, kp.plane_bytes, kp.has50, kp.maxw, 0, kp.G, kp.win_ww * kp.win_wb), occ_out);
+            return launch_episode<LPR, false, NetNeuro>(h, kp, episode_smem_bytes(LPR, false, kp.plane_bytes, kp.has50, kp.maxw, 0, kp.G, kp.win_ww * kp.win_wb, kp.tanh_in_smem), occ_out);
         }
         if (net_matches<NetSimple>(kp)) {
             kp.w_in_smem = 0;
-            return launch_episode<LPR, false, NetSimple>(h, kp, episode_smem_bytes(LPR, false, kp.plane_bytes, kp.has50, kp.maxw, 0, kp.G, kp.win_ww * kp.win_wb), occ_out);
+            return launch_episode<LPR, false, NetSimple>(h, kp, episode_smem_bytes(LPR, false, kp.plane_bytes, kp.has50, kp.maxw, 0, kp.G, kp.win_ww * kp.win_wb, kp.tanh_in_smem), occ_out);
         }
     }
     // one lane per robot: compile-time shape over the transposed genome array
     if constexpr (LPR == 1) if (!smem_stage) {
-        const size_t sm = episode_smem_bytes(1, false, kp.plane_bytes, kp.has50, kp.maxw, 0, kp.G);
+        const size_t sm = episode_smem_bytes(1, false, kp.plane_bytes, kp.has50, kp.maxw, 0, kp.G, 0, kp.tanh_in_smem);
         if (net_matches<NetNeuro>(kp)) return launch_episode<1, false, SmemNet<NetNeuro>>(h, kp, sm, occ_out);
         if (net_matches<NetSimple>(kp)) return launch_episode<1, false, SmemNet<NetSimple>>(h, kp, sm, occ_out);
     }
     // 2..8 lanes: compile-time shape, weights read through one pointer per robot -- its genome's copy in shared memory
     // when the robots in flight fit there (w_in_smem), else the [P][G] array itself (L1/L2)
     if constexpr (LPR >= 2 && LPR <= 8) if (!smem_stage && ws_allowed(kp)) {
-        const size_t sm = episode_smem_bytes(LPR, false, kp.plane_bytes, kp.has50, kp.maxw, kp.w_in_smem, kp.G, kp.win_ww * kp.win_wb);
+        const size_t sm = episode_smem_bytes(LPR, false, kp.plane_bytes, kp.has50, kp.maxw, kp.w_in_smem, kp.G, kp.win_ww * kp.win_wb, kp.tanh_in_smem);
         if (net_matches<NetNeuro>(kp)) return launch_episode<LPR, false, SmemNet<NetNeuro>>(h, kp, sm, occ_out);
         if (net_matches<NetSimple>(kp)) return launch_episode<LPR, false, SmemNet<NetSimple>>(h, kp, sm, occ_out);
         if constexpr (LPR >= 4) if (net_matches<NetSweep>(kp) && !(kp.goal_on || kp.skip_sense))
             return launch_kernel<LPR>(h, episode_kernel_ws<LPR, SmemNet<NetSweep>, false>, kp, sm, occ_out);
     }
-    const size_t smem = episode_smem_bytes(LPR, smem_stage, kp.plane_bytes, kp.has50, kp.maxw, kp.w_in_smem, kp.G, kp.win_ww * kp.win_wb);
+    const size_t smem = episode_smem_bytes(LPR, smem_stage, kp.plane_bytes, kp.has50, kp.maxw, kp.w_in_smem, kp.G, kp.win_ww * kp.win_wb, kp.tanh_in_smem);
     return smem_stage ? launch_episode<LPR, true, GenericNet>(h, kp, smem, occ_out) : launch_episode<LPR, false, GenericNet>(h, kp, smem, occ_out);
 }
 
@@ -414,6 +414,11 @@ int dispatch_episode(r2p2_handle h, KParams& kp, int lpr, bool smem_stage, int* 
     // robots in flight stay in shared memory only if both fit (else they are read through L1/L2)
     if (kp.w_in_smem && kp.win_ww && episode_smem_bytes(lpr, false, kp.plane_bytes, kp.has50, kp.maxw, 1, kp.G, kp.win_ww * kp.win_wb) > 55 * 1024)
         kp.w_in_smem = 0;
+    // the tanh table (18 KB): rows are picked per lane, so a global read is up to 32 L1 lookups per instruction against a
+    // few shared-memory wavefronts -- staged whenever it still leaves room for four CTAs per SM
+    static const bool no_tanh_smem = [] { const char* e = getenv("R2P2_NO_TANH_SMEM"); return e && e[0] == '1'; }();
+    kp.tanh_in_smem = (!no_tanh_smem && !smem_stage && kp.ctrl_kind == R2P2_CTRL_NEURO && kp.activation == R2P2_ACT_TANH &&
+                       episode_smem_bytes(lpr, false, kp.plane_bytes, kp.has50, kp.maxw, kp.w_in_smem, kp.G, kp.win_ww * kp.win_wb, 1) <= 55 * 1024) ? 1 : 0;
     switch (lpr) {
         case 1: return launch_episode_s<1>(h, kp, smem_stage, occ_out);
         case 2: return launch_episode_s<2>(h, kp, smem_stage, occ_out);
@@ -740,6 +745,11 @@ static int fill_params(r2p2_handle h, KParams& kp, int32_t T, double delta, doub
     kp.P = h->P; kp.T = T; kp.evolve = evolve ? 1 : 0;
     kp.delta = delta; kp.delta_ctrl = delta_ctrl;
     kp.g_sincostab = h->d_sincostab; kp.g_crxy = h->d_crxy;
+    {
+        void* tt = nullptr;
+        CK(cudaGetSymbolAddress(&tt, r2p2_d_tanhtab));
+        kp.g_tanhtab = reinterpret_cast<const double*>(tt);
+    }
     StateArrays& s = h->st;
     kp.x = s.x; kp.y = s.y; kp.theta = s.theta; kp.speed = s.speed; kp.omega = s.omega; kp.last_x = s.last_x; kp.last_y = s.last_y;
     kp.dist = s.dist; kp.odom_x = s.odom_x; kp.odom_y = s.odom_y; kp.origin_x = s.origin_x; kp.origin_y = s.origin_y;

@@ -14,6 +14,9 @@
 
 #include "r2p2_kernels.cuh"
 
+#ifndef R2P2_WS_MINB
+#define R2P2_WS_MINB 4
+#endif
 namespace r2p2 {
 
 #ifdef R2P2_EXP_FETCH_ONLY      // experiment: windows are fetched but the marches read the global plane
@@ -57,7 +60,7 @@ template <int LPR> constexpr int kWsSonarOwn = (LPR <= 2 ? 8 : 4);
 template <int LPR> constexpr int kWsCollOwn = (LPR >= 16 ? 1 : LPR >= 8 ? 2 : 4);
 
 template <int LPR, class NET, bool EXTRA = false>
-__global__ void __launch_bounds__(kBlock, (NET::kLayers > 0 && !NET::kSmemWeights) ? 1 : 4) episode_kernel_ws(const __grid_constant__ KParams p) {
+__global__ void __launch_bounds__(kBlock, (NET::kLayers > 0 && !NET::kSmemWeights) ? 1 : R2P2_WS_MINB) episode_kernel_ws(const __grid_constant__ KParams p) {
     static_assert(LPR >= 2 && LPR <= 16, "warp-synchronous kernel: 2..16 lanes per robot");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NR = kBlock / LPR;                      // robots in flight per CTA
@@ -67,7 +70,10 @@ __global__ void __launch_bounds__(kBlock, (NET::kLayers > 0 && !NET::kSmemWeight
     double* s_tab = reinterpret_cast<double*>(smem_raw + 16);
     double* s_crx = s_tab + R2P2_SINCOSTAB_LEN;
     double* s_cry = s_crx + 360;
-    double* s_bufA = s_cry + 360;
+    const double* s_tanh = p.g_tanhtab;
+    double* s_after = s_cry + 360;
+    if (p.tanh_in_smem) { s_tanh = s_after; s_after += R2P2_TANH_NINT * R2P2_TANH_ROW; }
+    double* s_bufA = s_after;
     double* s_bufB = s_bufA + (size_t)p.maxw * NR;
     double* s_gen = s_bufB + (size_t)p.maxw * NR;         // [NR][G], only when p.w_in_smem
     // per-robot windows of the hot plane (see below)
@@ -77,9 +83,10 @@ __global__ void __launch_bounds__(kBlock, (NET::kLayers > 0 && !NET::kSmemWeight
     const uint32_t mb = smem_u32(mbar);
     if (threadIdx.x == 0) {
         mbar_init(mb, 1);
-        mbar_expect_tx(mb, R2P2_SINCOSTAB_LEN * 8 + 720 * 8);
+        mbar_expect_tx(mb, R2P2_SINCOSTAB_LEN * 8 + 720 * 8 + (p.tanh_in_smem ? R2P2_TANH_NINT * R2P2_TANH_ROW * 8 : 0));
         tma_load_1d(s_tab, p.g_sincostab, R2P2_SINCOSTAB_LEN * 8, mb);
         tma_load_1d(s_crx, p.g_crxy, 720 * 8, mb);
+        if (p.tanh_in_smem) tma_load_1d(const_cast<double*>(s_tanh), p.g_tanhtab, R2P2_TANH_NINT * R2P2_TANH_ROW * 8, mb);
     }
     __syncthreads();
     while (!mbar_try_wait(mb, 0)) { }
@@ -254,7 +261,7 @@ __global__ void __launch_bounds__(kBlock, (NET::kLayers > 0 && !NET::kSmemWeight
 #endif
                 for (int i = g.sub; i < NET::sz(0); i += LPR) bufA[i * NR] = R2P2_DIV(p.vr1, bufA[i * NR]);   // 25/dst (inf when dst == 0)
                 __syncwarp();
-                group_mlp<LPR, NET>(gen, bufA, bufB, NR, g.sub, p.activation, v, w);
+                group_mlp<LPR, NET>(gen, bufA, bufB, NR, g.sub, p.activation, s_tanh, v, w);
                 if (v > 180.0) v = R2P2_SUB(v, 360.0);
                 __syncwarp();
             } else if constexpr (NET::kLayers > 0) {
@@ -264,8 +271,8 @@ __global__ void __launch_bounds__(kBlock, (NET::kLayers > 0 && !NET::kSmemWeight
                     const int i = g.sub + s * LPR;
                     h[s] = (i < NET::sz(0)) ? R2P2_DIV(p.vr1, bufA[i * NR]) : 0.0;
                 }
-                if constexpr (NET::kSmemWeights) mlp.forward_smem(gen, FULL, g.sub, h, p.activation, v, w);
-                else mlp.forward(FULL, g.sub, h, p.activation, v, w);
+                if constexpr (NET::kSmemWeights) mlp.forward_smem(gen, FULL, g.sub, h, p.activation, s_tanh, v, w);
+                else mlp.forward(FULL, g.sub, h, p.activation, s_tanh, v, w);
                 if (v > 180.0) v = R2P2_SUB(v, 360.0);
                 __syncwarp();
             } else if (p.ctrl_kind == R2P2_CTRL_NEURO) {
@@ -292,7 +299,7 @@ __global__ void __launch_bounds__(kBlock, (NET::kLayers > 0 && !NET::kSmemWeight
                             for (int u = 0; u < 8; ++u)
                                 if (i0 + u < nin) acc = R2P2_FMA(hv[u], wv[u], acc);
                         }
-                        hout[j * NR] = last ? acc : activate(p.activation, acc);
+                        hout[j * NR] = last ? acc : activate(p.activation, acc, s_tanh);
                     }
                     __syncwarp();
                     double* tsw = hin; hin = hout; hout = tsw;

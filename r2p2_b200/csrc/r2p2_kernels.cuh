@@ -70,6 +70,8 @@ struct KParams {
     // controller
     int32_t ctrl_kind, n_layers, activation, G, maxw;
     int32_t w_in_smem;                 // LPR > 1: copy each robot's genome into shared memory at robot start
+    int32_t tanh_in_smem;              // the tanh table (18 KB) is staged in shared memory next to the sin/cos table
+    const double* g_tanhtab;           // its global copy
     int32_t layers[R2P2_MAX_LAYERS];
     const double* genomes;             // [P][G] (LPR > 1) or [G][P] (LPR == 1)
     // run
@@ -757,9 +759,10 @@ __device__ __forceinline__ SinCos sincos_call(double a, const double* tab) {
     return r;
 }
 
-__device__ __forceinline__ double activate(int kind, double v) {
+// tanhtab: the tanh table the kernel uses (its shared-memory copy when there is room for one, else the global one)
+__device__ __forceinline__ double activate(int kind, double v, const double* tanhtab) {
     switch (kind) {
-        case R2P2_ACT_TANH: return r2p2_tanh(v);
+        case R2P2_ACT_TANH: return r2p2_tanh_tab(v, tanhtab);
         case R2P2_ACT_RELU:
             if (v != v) return v;
             if (v > 1.7976931348623157e308) return 1.7976931348623157e308;
@@ -776,14 +779,16 @@ __device__ __forceinline__ double activate(int kind, double v) {
 //   [0,16)                         mbarrier
 //   [16, 16+3520)                  sin/cos table
 //   [.., +5760)                    crash-radius offsets (360 x, 360 y)
+//   [.., +18304)                   tanh table (tanh_in_smem only)
 //   [.., +plane_bytes)             wall plane      (SMEM_STAGE only)
 //   [.., +plane_bytes)             level-50 plane  (SMEM_STAGE and has50 only)
 //   [.., +2*maxw*NR*8)             MLP / sonar buffers A and B, element i of robot slot r at [i*NR + r]
 //   [.., +NR*G*8)                  genomes of the robots in flight (w_in_smem only), row r at [r*G]
 //   [.., +NR*win_words*4)          per-robot windows of the hot plane (warp-synchronous kernel)
 __host__ __device__ inline size_t episode_smem_bytes(int lpr, bool smem_stage, uint32_t plane_bytes, int has50, int maxw, int w_in_smem, int G,
-                                                     int win_words = 0) {
+                                                     int win_words = 0, int tanh_in_smem = 0) {
     size_t n = 16 + R2P2_SINCOSTAB_LEN * 8 + 720 * 8;
+    if (tanh_in_smem) n += (size_t)R2P2_TANH_NINT * R2P2_TANH_ROW * 8;
     if (smem_stage) n += (size_t)plane_bytes * (has50 ? 2 : 1);
     n += (size_t)2 * maxw * (kBlock / lpr) * 8;
     if (w_in_smem) n += (size_t)(kBlock / lpr) * G * 8;
@@ -857,7 +862,7 @@ struct FixedMlp {
         }
     }
     // h[s] on entry: input (s*LPR + sub) of layer 0 (unused slots ignored); returns outputs 0 and 1 in all lanes
-    __device__ __forceinline__ void forward(unsigned mask, int sub, double (&h)[kSlots], int activation, double& out0, double& out1) const {
+    __device__ __forceinline__ void forward(unsigned mask, int sub, double (&h)[kSlots], int activation, const double* tanhtab, double& out0, double& out1) const {
         int q = 0;
 #pragma unroll
         for (int l = 0; l + 1 < NET::kLayers; ++l) {
@@ -871,7 +876,7 @@ struct FixedMlp {
                     if (s * LPR < NET::sz(l + 1)) acc = R2P2_FMA(hi, w[q], acc);
                     ++q;
                 }
-                hn[s] = (s * LPR < NET::sz(l + 1)) ? ((l + 2 < NET::kLayers) ? activate(activation, acc) : acc) : 0.0;
+                hn[s] = (s * LPR < NET::sz(l + 1)) ? ((l + 2 < NET::kLayers) ? activate(activation, acc, tanhtab) : acc) : 0.0;
             }
 #pragma unroll
             for (int s = 0; s < kSlots; ++s) h[s] = hn[s];
@@ -881,7 +886,7 @@ struct FixedMlp {
     }
     // Same chains with the weights in shared memory (gs = this robot's genome copy): W_l[i][j] at gs[woff(l) + i*sz(l+1) + j],
     // compile-time i, lane-dependent j.
-    __device__ __forceinline__ void forward_smem(const double* gs, unsigned mask, int sub, double (&h)[kSlots], int activation,
+    __device__ __forceinline__ void forward_smem(const double* gs, unsigned mask, int sub, double (&h)[kSlots], int activation, const double* tanhtab,
                                                  double& out0, double& out1) const {
 #pragma unroll
         for (int l = 0; l + 1 < NET::kLayers; ++l) {
@@ -896,7 +901,7 @@ struct FixedMlp {
                     const double hi = (LPR == 1) ? h[i] : __shfl_sync(mask, h[i / LPR], i % LPR, LPR);
                     if (s * LPR < NET::sz(l + 1)) acc = R2P2_FMA(hi, gs[NET::woff(l) + i * NET::sz(l + 1) + jc], acc);
                 }
-                hn[s] = (s * LPR < NET::sz(l + 1)) ? ((l + 2 < NET::kLayers) ? activate(activation, acc) : acc) : 0.0;
+                hn[s] = (s * LPR < NET::sz(l + 1)) ? ((l + 2 < NET::kLayers) ? activate(activation, acc, tanhtab) : acc) : 0.0;
             }
 #pragma unroll
             for (int s = 0; s < kSlots; ++s) h[s] = hn[s];
@@ -907,7 +912,7 @@ struct FixedMlp {
     // One lane per robot: the whole net in this thread.  Activations stay in registers, every loop is unrolled, and
     // the weights stream from the transposed genome array (wt = genomes_t + robot, element q at wt[q * P]: one
     // coalesced line per warp and weight).  Same ordered FMA chains as everywhere else.
-    __device__ __forceinline__ void forward_global(const double* __restrict__ wt, size_t P, double (&h)[kSlots], int activation,
+    __device__ __forceinline__ void forward_global(const double* __restrict__ wt, size_t P, double (&h)[kSlots], int activation, const double* tanhtab,
                                                    double& out0, double& out1) const {
 #pragma unroll
         for (int l = 0; l + 1 < NET::kLayers; ++l) {
@@ -918,7 +923,7 @@ struct FixedMlp {
 #pragma unroll
                 for (int i = 0; i < NET::sz(l); ++i)
                     acc = R2P2_FMA(h[i], __ldg(wt + (size_t)(NET::woff(l) + i * NET::sz(l + 1) + j) * P), acc);
-                hn[j] = (l + 2 < NET::kLayers) ? activate(activation, acc) : acc;
+                hn[j] = (l + 2 < NET::kLayers) ? activate(activation, acc, tanhtab) : acc;
             }
 #pragma unroll
             for (int j = 0; j < NET::sz(l + 1); ++j) h[j] = hn[j];
@@ -931,7 +936,7 @@ struct FixedMlp {
 // loop unrolled so that a neuron's weight loads (coalesced over the warp's 32 robots in the transposed genome array
 // wt[q * P]) are all in flight ahead of its ordered FMA chain; one activation instance per layer.
 template <class NET, int L>
-__device__ __forceinline__ void lane_layer(const double* __restrict__ wt, size_t P, const double* hin, double* hout, int NR, int activation) {
+__device__ __forceinline__ void lane_layer(const double* __restrict__ wt, size_t P, const double* hin, double* hout, int NR, int activation, const double* tanhtab) {
     constexpr int nin = NET::sz(L), nout = NET::sz(L + 1);
     constexpr bool last = (L + 2 == NET::kLayers);
 #pragma unroll 1
@@ -945,17 +950,17 @@ __device__ __forceinline__ void lane_layer(const double* __restrict__ wt, size_t
         double acc = 0.0;
 #pragma unroll
         for (int i = 0; i < nin; ++i) acc = R2P2_FMA(hv[i], wv[i], acc);
-        hout[j * NR] = last ? acc : activate(activation, acc);
+        hout[j * NR] = last ? acc : activate(activation, acc, tanhtab);
     }
 }
 template <class NET>
-__device__ __forceinline__ void lane_mlp(const double* __restrict__ wt, size_t P, double* a, double* b, int NR, int activation,
+__device__ __forceinline__ void lane_mlp(const double* __restrict__ wt, size_t P, double* a, double* b, int NR, int activation, const double* tanhtab,
                                          double& out0, double& out1) {
-    lane_layer<NET, 0>(wt, P, a, b, NR, activation);
+    lane_layer<NET, 0>(wt, P, a, b, NR, activation, tanhtab);
     double* res = b;
-    if constexpr (NET::kLayers > 2) { lane_layer<NET, 1>(wt, P, b, a, NR, activation); res = a; }
-    if constexpr (NET::kLayers > 3) { lane_layer<NET, 2>(wt, P, a, b, NR, activation); res = b; }
-    if constexpr (NET::kLayers > 4) { lane_layer<NET, 3>(wt, P, b, a, NR, activation); res = a; }
+    if constexpr (NET::kLayers > 2) { lane_layer<NET, 1>(wt, P, b, a, NR, activation, tanhtab); res = a; }
+    if constexpr (NET::kLayers > 3) { lane_layer<NET, 2>(wt, P, a, b, NR, activation, tanhtab); res = b; }
+    if constexpr (NET::kLayers > 4) { lane_layer<NET, 3>(wt, P, b, a, NR, activation, tanhtab); res = a; }
     out0 = res[0];
     out1 = res[NR];
 }
@@ -967,7 +972,7 @@ __device__ __forceinline__ void lane_mlp(const double* __restrict__ wt, size_t P
 // (The first version exchanged activations with __shfl_sync: two SHFL per double and input were 11 % of the synthetic
 // sweep's instructions.)
 template <int LPR, class NET, int L>
-__device__ __forceinline__ void group_layer(const double* __restrict__ gs, const double* hin, double* hout, int NR, int sub, int activation) {
+__device__ __forceinline__ void group_layer(const double* __restrict__ gs, const double* hin, double* hout, int NR, int sub, int activation, const double* tanhtab) {
     constexpr int nin = NET::sz(L), nout = NET::sz(L + 1), slots = (nout + LPR - 1) / LPR;
     constexpr bool last = (L + 2 == NET::kLayers);
     const double* wp[slots];
@@ -987,19 +992,19 @@ __device__ __forceinline__ void group_layer(const double* __restrict__ gs, const
 #pragma unroll
     for (int q = 0; q < slots; ++q) {
         const int jn = sub + q * LPR;
-        if (jn < nout) hout[jn * NR] = last ? acc[q] : activate(activation, acc[q]);
+        if (jn < nout) hout[jn * NR] = last ? acc[q] : activate(activation, acc[q], tanhtab);
     }
 }
 // in: a[i * NR] = input i (already vr1 / dst); a and b are overwritten; returns outputs 0 and 1 in every lane of the group.
 // `sync` is the group-wide barrier (a __syncwarp in the warp-synchronous kernel).
 template <int LPR, class NET>
-__device__ __forceinline__ void group_mlp(const double* __restrict__ gs, double* a, double* b, int NR, int sub, int activation, double& out0, double& out1) {
-    group_layer<LPR, NET, 0>(gs, a, b, NR, sub, activation);
+__device__ __forceinline__ void group_mlp(const double* __restrict__ gs, double* a, double* b, int NR, int sub, int activation, const double* tanhtab, double& out0, double& out1) {
+    group_layer<LPR, NET, 0>(gs, a, b, NR, sub, activation, tanhtab);
     __syncwarp();
     double* res = b;
-    if constexpr (NET::kLayers > 2) { group_layer<LPR, NET, 1>(gs, b, a, NR, sub, activation); __syncwarp(); res = a; }
-    if constexpr (NET::kLayers > 3) { group_layer<LPR, NET, 2>(gs, a, b, NR, sub, activation); __syncwarp(); res = b; }
-    if constexpr (NET::kLayers > 4) { group_layer<LPR, NET, 3>(gs, b, a, NR, sub, activation); __syncwarp(); res = a; }
+    if constexpr (NET::kLayers > 2) { group_layer<LPR, NET, 1>(gs, b, a, NR, sub, activation, tanhtab); __syncwarp(); res = a; }
+    if constexpr (NET::kLayers > 3) { group_layer<LPR, NET, 2>(gs, a, b, NR, sub, activation, tanhtab); __syncwarp(); res = b; }
+    if constexpr (NET::kLayers > 4) { group_layer<LPR, NET, 3>(gs, b, a, NR, sub, activation, tanhtab); __syncwarp(); res = a; }
     out0 = res[0];
     out1 = res[NR];
 }
@@ -1020,6 +1025,8 @@ __global__ void __launch_bounds__(kBlock, (NET::kLayers > 0 && !NET::kSmemWeight
     double* s_crx = s_tab + R2P2_SINCOSTAB_LEN;
     double* s_cry = s_crx + 360;
     unsigned char* cur = reinterpret_cast<unsigned char*>(s_cry + 360);
+    const double* s_tanh = p.g_tanhtab;
+    if (p.tanh_in_smem) { s_tanh = reinterpret_cast<const double*>(cur); cur += R2P2_TANH_NINT * R2P2_TANH_ROW * 8; }
     uint32_t* s_wall = nullptr;
     uint32_t* s_l50 = nullptr;
     if (SMEM_STAGE) {
@@ -1036,9 +1043,11 @@ __global__ void __launch_bounds__(kBlock, (NET::kLayers > 0 && !NET::kSmemWeight
         mbar_init(mb, 1);
         uint32_t total = R2P2_SINCOSTAB_LEN * 8 + 720 * 8;
         if (SMEM_STAGE) total += p.plane_bytes * (p.has50 ? 2u : 1u);
+        if (p.tanh_in_smem) total += R2P2_TANH_NINT * R2P2_TANH_ROW * 8;
         mbar_expect_tx(mb, total);
         tma_load_1d(s_tab, p.g_sincostab, R2P2_SINCOSTAB_LEN * 8, mb);
         tma_load_1d(s_crx, p.g_crxy, 720 * 8, mb);
+        if (p.tanh_in_smem) tma_load_1d(const_cast<double*>(s_tanh), p.g_tanhtab, R2P2_TANH_NINT * R2P2_TANH_ROW * 8, mb);
         if (SMEM_STAGE) {
             for (uint32_t off = 0; off < p.plane_bytes; off += 32768u) {
                 const uint32_t n = min(32768u, p.plane_bytes - off);
@@ -1199,7 +1208,7 @@ __global__ void __launch_bounds__(kBlock, (NET::kLayers > 0 && !NET::kSmemWeight
             if constexpr (NET::kSmemWeights) {            // one lane per robot, compile-time shape (capi dispatches it for LPR == 1 only)
 #pragma unroll
                 for (int i = 0; i < NET::sz(0); ++i) bufA[i * NR] = R2P2_DIV(p.vr1, bufA[i * NR]);   // 25/dst (inf when dst == 0)
-                lane_mlp<NET>(p.genomes + rb, (size_t)p.P, bufA, bufB, NR, p.activation, v, w);
+                lane_mlp<NET>(p.genomes + rb, (size_t)p.P, bufA, bufB, NR, p.activation, s_tanh, v, w);
                 if (v > 180.0) v = R2P2_SUB(v, 360.0);
             } else if constexpr (NET::kLayers > 0) {
                 double h[FixedMlp<LPR, NET>::kSlots];
@@ -1208,8 +1217,8 @@ __global__ void __launch_bounds__(kBlock, (NET::kLayers > 0 && !NET::kSmemWeight
                     const int i = g.sub + s * LPR;
                     h[s] = (i < NET::sz(0)) ? R2P2_DIV(p.vr1, bufA[i * NR]) : 0.0;                     // 25/dst (inf when dst == 0)
                 }
-                if constexpr (LPR > 1) mlp.forward(g.mask, g.sub, h, p.activation, v, w);
-                else mlp.forward_global(p.genomes + rb, (size_t)p.P, h, p.activation, v, w);
+                if constexpr (LPR > 1) mlp.forward(g.mask, g.sub, h, p.activation, s_tanh, v, w);
+                else mlp.forward_global(p.genomes + rb, (size_t)p.P, h, p.activation, s_tanh, v, w);
                 if (v > 180.0) v = R2P2_SUB(v, 360.0);
                 g.sync();                                  // bufA is rewritten by the next tick's sense
             } else if (p.ctrl_kind == R2P2_CTRL_NEURO) {
@@ -1243,7 +1252,7 @@ __global__ void __launch_bounds__(kBlock, (NET::kLayers > 0 && !NET::kSmemWeight
                                     if (i0 + u < nin) acc = R2P2_FMA(hv[u], wv[u], acc);
                             }
                         }
-                        hout[j * NR] = last ? acc : activate(p.activation, acc);
+                        hout[j * NR] = last ? acc : activate(p.activation, acc, s_tanh);
                     }
                     g.sync();
                     double* tsw = hin; hin = hout; hout = tsw;

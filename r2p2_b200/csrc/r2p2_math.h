@@ -20,6 +20,16 @@
 //
 // Every operation is an explicitly rounded IEEE-754 double operation: no contraction is left to
 // the compiler (device: __dmul_rn/__dadd_rn/__fma_rn; host: build with -ffp-contract=off).
+//
+// Provenance and licence of the sin / cos part.  r2p2__do_sin, r2p2__do_cos, r2p2__reduce_sincos, r2p2__taylor_sin, r2p2_sin,
+// r2p2_cos and r2p2_sincos follow the algorithm of the GNU C Library's IBM Accurate Mathematical Library routines
+// (sysdeps/ieee754/dbl-64/s_sin.c, dosincos / branred helpers; Copyright (C) 2001-2024 Free Software Foundation, Inc.),
+// and the polynomial constants and the 440-entry table in r2p2_sincostab.h are the values of glibc 2.39's libm
+// (read out of libm.so.6 by tools/gen_sincostab.py).  The GNU C Library is free software; you can redistribute it
+// and/or modify it under the terms of the GNU Lesser General Public License as published by the Free Software
+// Foundation; either version 2.1 of the License, or (at your option) any later version.  These derived parts are
+// distributed under the same terms, WITHOUT ANY WARRANTY; see <https://www.gnu.org/licenses/> for the licence text.
+// Everything else in this file (atan2, exp, tanh, logistic, norm) is this project's own work.
 #pragma once
 
 #include <stdint.h>
@@ -409,7 +419,7 @@ R2P2_HD double r2p2_tanh_exp(double x) {
 // tanh by table: on [2^-6, 32) a degree-11 Taylor polynomial around the midpoint of the interval selected by the
 // exponent and the top four mantissa bits of |x| (tools/gen_tanhtab.py; t = |x| - mid is exact), evaluated with Estrin's
 // scheme -- no exp, no division, a 5-deep dependent chain.  Below 2^-6 the odd series at 0; from 20 on, +-1.
-R2P2_HD double r2p2_tanh(double x) {
+R2P2_HD double r2p2_tanh_tab(double x, const double* tanhtab) {
     const double ax = r2p2_fabs(x);
     if (x != x) return x;
     if (ax >= 20.0) return r2p2_copysign(1.0, x);
@@ -428,7 +438,7 @@ R2P2_HD double r2p2_tanh(double x) {
     const double t = R2P2_SUB(ax, mid);
     // row: c0 hi, c0 lo, c1..c11.  tanh = c0 + t * (c1 + c2 t + ... + c11 t^10): the bracket by Estrin, the dominant
     // term added last so that its rounding is the only one that matters (|t| <= mid/32)
-    const double* c = R2P2_TANHTAB + idx * R2P2_TANH_ROW;
+    const double* c = tanhtab + idx * R2P2_TANH_ROW;
     const double t2 = R2P2_MUL(t, t), t4 = R2P2_MUL(t2, t2), t8 = R2P2_MUL(t4, t4);
     const double a0 = R2P2_FMA(c[3], t, c[2]), a1 = R2P2_FMA(c[5], t, c[4]), a2 = R2P2_FMA(c[7], t, c[6]);
     const double a3 = R2P2_FMA(c[9], t, c[8]), a4 = R2P2_FMA(c[11], t, c[10]);
@@ -437,6 +447,8 @@ R2P2_HD double r2p2_tanh(double x) {
     const double r = R2P2_ADD(c[0], R2P2_FMA(t, inner, c[1]));
     return r2p2_copysign(r, x);
 }
+
+R2P2_HD double r2p2_tanh(double x) { return r2p2_tanh_tab(x, R2P2_TANHTAB); }
 
 // logistic(x) = 1 / (1 + exp(-x))   (sklearn 'logistic' activation = scipy.special.expit)
 R2P2_HD double r2p2_logistic(double x) {
