@@ -50,6 +50,8 @@ typedef struct r2p2_sim* r2p2_handle;
 #define R2P2_CTRL_CONST 0    /* genome = [speed, angular_velocity]: naive_controller.py generalised   */
 #define R2P2_CTRL_NEURO 1    /* neurocontroller.Neuro_controller: MLP, genome = flat C-order weights  */
 #define R2P2_CTRL_LINEAR 2   /* inspyred.Inspyred_controller: [l_1..l_n, a_1..a_n, vmaxlin, vmaxang]  */
+#define R2P2_CTRL_PID 3      /* pid_controller.Sequential_PID_Controller: genome = [ap, ai, ad, lp, li, ld]; goals: r2p2_set_pid */
+#define R2P2_PID_MAX_GOALS 64 /* goal stack per robot: configured goals + temporary obstacle-avoid goals */
 
 /* activations (sklearn names) */
 #define R2P2_ACT_IDENTITY 0
@@ -102,6 +104,18 @@ int r2p2_set_robot(r2p2_handle h, double vr0, double vr1, double radius, double 
 /* kind = R2P2_CTRL_*; NEURO: layers = [n_rays, hidden..., 2] (n_layers entries), activation = R2P2_ACT_*.
  * For CONST / LINEAR pass layers = NULL, n_layers = 0. */
 int r2p2_set_controller(r2p2_handle h, int32_t kind, const int32_t* layers, int32_t n_layers, int32_t activation);
+
+/* Sequential_PID_Controller on the device (r2p2/controllers/pid_controller.py:8-262): goal list, PID terms on heading and
+ * distance, the obstacle-avoid state machine, backing off for ten ticks after a collision -- evaluated inside the step
+ * kernel for every robot of the population; a robot's genome holds its six gains.  goals: [n_goals][2] (x, y), the same
+ * list for every robot (per_robot = 0) or [P][n_goals][2] (per_robot = 1, P = the population size at the next reset).
+ * max_acceleration: the controller's clamp (5 in the reference); acceleration: Robot.acceleration, which nothing in the
+ * reference's tick changes (0).  The reference's register_robot moves the robot to goal[0]: pass that as the start pose
+ * to r2p2_reset.  Goals are (re)loaded by r2p2_reset.  Needs at least three sonar rays. */
+int r2p2_set_pid(r2p2_handle h, const double* goals, int32_t n_goals, int32_t per_robot, double max_acceleration, double acceleration);
+/* Controller state per robot (any pointer may be NULL; arrays of P): goals left, state (0 advancing, 1 avoiding, 2 advancing
+ * after avoiding), ticks of backing off left, target angle, and the current goal (NaN when the list is empty). */
+int r2p2_read_pid(r2p2_handle h, int32_t* goals_left, int32_t* state, int32_t* backing, double* target_angle, double* goal_x, double* goal_y);
 
 /* Sensor noise, Robot.has_noise / __generate_noise = np.random.normal(0, 0.5) (r2p2/robot.py:96,139-140,308-310): one draw
  * per unclamped sonar ray, in ray order.

@@ -13,7 +13,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _BUILD = os.path.join(_HERE, "_build")
 
 MAX_RAYS, MAX_LAYERS = 64, 8
-CTRL = {"const": 0, "neuro": 1, "linear": 2}
+CTRL = {"const": 0, "neuro": 1, "linear": 2, "pid": 3}
+PID_GCAP = 64
 ACT = {"identity": 0, "tanh": 1, "relu": 2, "logistic": 3}
 F_COLLIDED, F_FAULT, F_DONE, F_TRIGRANGE = 1, 2, 4, 8
 
@@ -25,7 +26,8 @@ class _Cfg(C.Structure):
                 ("ctrl_kind", C.c_int32), ("n_layers", C.c_int32), ("layers", C.c_int32 * MAX_LAYERS),
                 ("activation", C.c_int32), ("G", C.c_int32), ("evolve", C.c_int32),
                 ("delta", C.c_double), ("delta_ctrl", C.c_double), ("time_budget", C.c_double),
-                ("noise", C.c_void_p), ("noise_len", C.c_int32), ("goal_on", C.c_int32), ("goal_x", C.c_double), ("goal_y", C.c_double)]
+                ("noise", C.c_void_p), ("noise_len", C.c_int32), ("goal_on", C.c_int32), ("goal_x", C.c_double), ("goal_y", C.c_double),
+                ("pid_max_acc", C.c_double), ("pid_accel", C.c_double), ("pid_state", C.c_void_p)]
 
 
 class _Robot(C.Structure):
@@ -40,6 +42,24 @@ ROBOT_DTYPE = np.dtype([(n, "<f8") for n in ("x", "y", "theta", "speed", "omega"
                                              "odom_x", "odom_y", "origin_x", "origin_y", "time", "fitness")] +
                        [("flags", "<u4"), ("ncollide", "<u4"), ("ticks", "<u4"), ("_pad", "<u4"),
                         ("nsamp_sonar", "<u8"), ("nsamp_coll", "<u8"), ("npixel", "<u8"), ("ndraws", "<u4"), ("goal_tick", "<u4")])
+
+
+PID_DTYPE = np.dtype([(n, "<f8") for n in ("acc_ang", "acc_dist", "last_ang", "last_dist", "target_angle")] +
+                     [("state", "<i4"), ("backing", "<i4"), ("ngoals", "<i4"), ("pad", "<i4"), ("gx", "<f8", (PID_GCAP,)), ("gy", "<f8", (PID_GCAP,))])
+
+
+def pid_initial_state(P, goals):
+    """Controller state of P fresh Sequential_PID_Controllers with the goal list `goals` ([n][2], shared, or [P][n][2])."""
+    g = np.asarray(goals, dtype=np.float64)
+    if g.ndim == 2:
+        g = np.broadcast_to(g, (P,) + g.shape)
+    n = g.shape[1]
+    assert n <= PID_GCAP
+    ps = np.zeros(P, dtype=PID_DTYPE)
+    ps["ngoals"] = n
+    ps["gx"][:, :n] = g[:, ::-1, 0]                   # a stack: the last slot in use is goal[0]
+    ps["gy"][:, :n] = g[:, ::-1, 1]
+    return ps
 
 
 def build(force=False):
@@ -68,6 +88,7 @@ class Oracle:
         assert L.orc_sizeof_cfg() == C.sizeof(_Cfg), (L.orc_sizeof_cfg(), C.sizeof(_Cfg))
         assert L.orc_sizeof_robot() == C.sizeof(_Robot) == ROBOT_DTYPE.itemsize
         assert L.orc_is_portmath() == int(self.port)
+        assert L.orc_sizeof_pid() == PID_DTYPE.itemsize, (L.orc_sizeof_pid(), PID_DTYPE.itemsize)
         L.orc_ray.restype = C.c_int
         L.orc_ray.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_double,
                               C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_uint32)]
@@ -90,7 +111,7 @@ class Oracle:
 
     def run(self, env, *, rays, vr, radius, max_speed, ctrl, genomes, x0, y0, theta0, T, delta=0.1,
             layers=None, activation="tanh", evolve=False, delta_ctrl=None, time_budget=20000.0,
-            noise=None, trace=False, threads=1, goal=None, state=None):
+            noise=None, trace=False, threads=1, goal=None, state=None, pid_goals=None, pid_state=None, pid_max_acc=5.0, pid_accel=0.0):
         """Run P robots for T ticks.  Returns dict(state=structured array [P], plus traces [T,P,...]).
         state: continue from this structured array (a copy is advanced) instead of starting at x0 / y0 / theta0."""
         env = self._env(env)
@@ -115,6 +136,10 @@ class Oracle:
         cfg.time_budget = float(time_budget)
         if goal is not None:
             cfg.goal_on, cfg.goal_x, cfg.goal_y = 1, float(goal[0]), float(goal[1])
+        ps = None
+        if ctrl == "pid":                                   # genomes = [P][6] PID gains (ap, ai, ad, lp, li, ld)
+            ps = np.array(pid_state, dtype=PID_DTYPE, copy=True) if pid_state is not None else pid_initial_state(P, pid_goals)
+            cfg.pid_max_acc, cfg.pid_accel, cfg.pid_state = float(pid_max_acc), float(pid_accel), ps.ctypes.data
         if noise is not None:
             noise = np.ascontiguousarray(noise, dtype=np.float64)
             assert noise.ndim == 2 and noise.shape[0] == P      # per-robot stream of N(0, 0.5) draws, consumed sequentially
@@ -152,6 +177,8 @@ class Oracle:
             raise ValueError("oracle: unsupported configuration")
         out["state"] = st
         out["fitness"] = st["fitness"].copy()
+        if ps is not None:
+            out["pid"] = ps
         return out
 
 

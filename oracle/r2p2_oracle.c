@@ -59,7 +59,7 @@
 #define ORC_MAX_LAYERS 8
 #define ORC_MAX_WIDTH 64
 
-enum { ORC_CTRL_CONST = 0, ORC_CTRL_NEURO = 1, ORC_CTRL_LINEAR = 2 };
+enum { ORC_CTRL_CONST = 0, ORC_CTRL_NEURO = 1, ORC_CTRL_LINEAR = 2, ORC_CTRL_PID = 3 };
 enum { ORC_ACT_IDENTITY = 0, ORC_ACT_TANH = 1, ORC_ACT_RELU = 2, ORC_ACT_LOGISTIC = 3 };
 
 /* per-robot flag bits (same meaning as include/r2p2_b200.h) */
@@ -90,7 +90,18 @@ typedef struct {
     int32_t noise_len;
     int32_t goal_on;           /* goal flagging: Sequential_PID_Controller.is_at_goal (controllers/pid_controller.py:207-213) as a */
     double goal_x, goal_y;     /* per-run predicate on the pose after each tick; a flag only, the dynamics never see it          */
+    /* Sequential_PID_Controller (controllers/pid_controller.py:8-262): genome = [ap, ai, ad, lp, li, ld] per robot */
+    double pid_max_acc;        /* self.max_acceleration (5)  */
+    double pid_accel;          /* robot.acceleration (0: nothing in the tick changes it, robot.py:398 is commented out) */
+    void* pid_state;           /* orc_pid[P]: PID terms, obstacle-avoid state, goal stack */
 } orc_cfg;
+
+#define ORC_PID_GCAP 64        /* goal stack capacity (configured goals + temporary avoid goals); overflow = fault */
+typedef struct {
+    double acc_ang, acc_dist, last_ang, last_dist, target_angle;
+    int32_t state, backing, ngoals, pad;
+    double gx[ORC_PID_GCAP], gy[ORC_PID_GCAP];   /* a stack: slot ngoals-1 is goal[0] of the reference's list */
+} orc_pid;
 
 typedef struct {
     double x, y, theta, speed, omega;
@@ -212,9 +223,11 @@ static inline double orc_fitness(const orc_robot* rb) {   /* neurocontroller.py:
 }
 
 /* controller.control(dst).  returns 0 when the episode ended on this call (evolve). */
-static int orc_control(const orc_cfg* c, orc_robot* rb, const double* genome, const double* dst, double* v_out, double* w_out) {
+static int orc_control_pid(const orc_cfg* c, orc_robot* rb, orc_pid* ps, const double* k, const double* dst, double* v_out, double* w_out);
+static int orc_control(const orc_cfg* c, orc_robot* rb, const double* genome, const double* dst, double* v_out, double* w_out, orc_pid* ps) {
     rb->dist += orc_norm2(rb->x - rb->odom_x, rb->y - rb->odom_y);
     rb->odom_x = rb->x; rb->odom_y = rb->y;
+    if (c->ctrl_kind == ORC_CTRL_PID) return orc_control_pid(c, rb, ps, genome, dst, v_out, w_out);
     if (c->ctrl_kind != ORC_CTRL_CONST) {
         if (c->evolve) rb->time -= c->delta_ctrl;
         if (rb->time <= 0 && c->evolve) {
@@ -257,6 +270,98 @@ static int orc_control(const orc_cfg* c, orc_robot* rb, const double* genome, co
 }
 
 static inline void orc_collide(orc_robot* rb) { rb->ncollide++; rb->flags |= ORC_F_COLLIDED; rb->time = 0; }
+
+/* ---- Sequential_PID_Controller.control (controllers/pid_controller.py:40-262) ----------------------------------- */
+static inline double orc_pymod360(double a) {          /* Python float % 360 */
+    double m = fmod(a, 360.0);
+    if (m != 0) { if (m < 0) m += 360.0; } else m = 0.0;
+    return m;
+}
+/* Robot.brake (robot.py:354-363) */
+static inline double orc_brake(const orc_cfg* c, orc_robot* rb) {
+    const int neg = rb->speed < 0;
+    const double new_speed = rb->speed - c->pid_accel - rb->speed / 3;
+    if ((neg && new_speed > 0) || (!neg && new_speed < 0)) { rb->speed = 0; return -c->pid_accel / 5; }
+    return -c->pid_accel - rb->speed / 3;
+}
+static inline double orc_pid_angle_variation(orc_robot* rb, orc_pid* ps, const double* k) {   /* :235-243 */
+    const double e = ps->target_angle - rb->theta;
+    ps->acc_ang += e;
+    const double de = e - ps->last_ang;
+    ps->last_ang = e;
+    return k[0] * e + k[1] * ps->acc_ang + k[2] * de;
+}
+/* returns 0 on a fault (IndexError at the goal pixel, goal stack overflow) */
+static int orc_control_pid(const orc_cfg* c, orc_robot* rb, orc_pid* ps, const double* k, const double* dst, double* v_out, double* w_out) {
+    const int R = c->R;
+    if (ps->backing) { ps->backing -= 1; *v_out = rb->theta; *w_out = -c->max_speed; return 1; }      /* :50-53 */
+    {   /* manage_state :215-229 */
+        const double rng = c->vr1, tol = c->vr0 / rng * 13;
+        if ((dst[R - 1] / rng < tol && dst[R - 2] / rng < tol) || (dst[1] / rng < tol && dst[2] / rng < tol) || dst[0] / rng < tol)
+            ps->state = (ps->state == 0) ? 1 : 2;
+        else ps->state = 0;
+    }
+    if (ps->state == 0 || ps->state == 2) {             /* control_advance :60-72 */
+        if (ps->ngoals == 0) { *v_out = 0; *w_out = 0; return 1; }
+        const double gx = ps->gx[ps->ngoals - 1], gy = ps->gy[ps->ngoals - 1];
+        ps->target_angle = ORC_ATAN2(gy - rb->y, gx - rb->x) * ORC_DEG;                               /* :245-250 */
+        const double angle = orc_pid_angle_variation(rb, ps, k);
+        const double speed0 = rb->speed;
+        double var;                                      /* calculate_acceleration_variation :219-233 */
+        if (fabs(ps->target_angle - rb->theta) > 45) {
+            ps->acc_dist += orc_brake(c, rb);
+            var = orc_brake(c, rb);
+        } else {
+            const double e = orc_norm2(gx - rb->x, gy - rb->y);
+            if (c->pid_accel < c->pid_max_acc) ps->acc_dist += e;
+            const double de = e - ps->last_dist;
+            ps->last_dist = e;
+            var = k[3] * e + k[4] * ps->acc_dist + k[5] * de;
+        }
+        double acc = c->pid_accel + var;                 /* choose_acceleration :143-155 */
+        if (acc > c->pid_max_acc) acc = c->pid_max_acc;
+        else if (-acc < c->pid_max_acc) acc = -c->pid_max_acc;
+        const double speed = speed0 + acc;
+        {   /* is_at_goal :207-213 */
+            int64_t ix, iy; int32_t v = 1;
+            rb->npixel++;
+            if (!orc_pyint(gx, &ix) || !orc_pyint(gy, &iy) || !orc_px(c, ix, iy, &v)) { rb->flags |= ORC_F_FAULT; return 0; }
+            int at = (v == 0);
+            if (!at) at = orc_norm2(gx - rb->x, gy - rb->y) <= c->radius * 1.85;
+            if (at) { ps->ngoals--; if (ps->state == 2) ps->state = 0; }
+        }
+        *v_out = speed; *w_out = angle;
+        return 1;
+    }
+    /* control_avoid :73-124 */
+    const double far = c->vr1;
+    double risk = 1;
+    for (int i = 0; i < R; ++i) risk *= (dst[i] / far);
+    if (dst[1] + dst[2] < dst[R - 1] + dst[R - 2]) risk /= (far / dst[R - 1]) * (far / dst[R - 2]);
+    else risk /= (far / dst[1]) * (far / dst[2]);
+    if (dst[0] / far < 0.45) risk *= dst[0] / far;
+    double safety = (far + c->radius) * risk * 2;
+    if (safety <= c->vr0) safety = c->vr0 * 2;
+    double a;
+    if ((dst[1] + dst[2]) > (dst[R - 1] + dst[R - 2])) a = orc_pymod360(ps->target_angle) + 90;
+    else a = orc_pymod360(ps->target_angle) - 90;
+    int ok = 1;
+    const double arg = (ps->target_angle - a) * ORC_RAD;
+    double x_var = safety * ORC_COS(arg, &ok), y_var = safety * ORC_SIN(arg, &ok);
+    if (!ok) { rb->flags |= ORC_F_TRIGRANGE | ORC_F_FAULT; return 0; }
+    const double am = orc_pymod360(a);
+    if (am > 90 && am < 270) x_var *= -1;
+    if (am > 180) y_var *= -1;
+    if (ps->ngoals >= ORC_PID_GCAP) { rb->flags |= ORC_F_FAULT; return 0; }
+    ps->gx[ps->ngoals] = rb->x + x_var; ps->gy[ps->ngoals] = rb->y + y_var; ps->ngoals++;             /* goal.insert(0, ...) */
+    (void)orc_pid_angle_variation(rb, ps, k);
+    ps->target_angle = a;
+    int must_retreat = 0;
+    for (int i = 0; i < R; ++i) if (dst[i] / far < c->vr0 / far * 12) { must_retreat = 1; break; }
+    *v_out = must_retreat ? -c->max_speed : rb->speed;
+    *w_out = 0;
+    return 1;
+}
 
 /* robot.py:181-186 ; returns 1 crashing, 0 clear, -1 fault */
 static int orc_crashing(const orc_cfg* c, orc_robot* rb, const double* crx, const double* cry) {
@@ -343,15 +448,21 @@ static int orc_move(const orc_cfg* c, orc_robot* rb, const double* crx, const do
 
 /* Robot.update (robot.py:389-402).  returns 1 if the robot keeps running. */
 static int orc_tick(const orc_cfg* c, orc_robot* rb, const double* genome, const double* crx, const double* cry,
-                    const orc_trace_row* tr, const double* noise_stream) {
+                    const orc_trace_row* tr, const double* noise_stream, orc_pid* ps) {
     double dst[ORC_MAX_RAYS];
     if (!orc_sense(c, rb, dst, tr, noise_stream)) return 0;
     double v, w;
-    if (!orc_control(c, rb, genome, dst, &v, &w)) { rb->speed = 0; rb->omega = 0; return 0; }
+    const uint32_t ncoll_before = rb->ncollide;
+    if (!orc_control(c, rb, genome, dst, &v, &w, ps)) {
+        if (c->ctrl_kind != ORC_CTRL_PID) { rb->speed = 0; rb->omega = 0; }
+        return 0;
+    }
     if (fabs(v) > c->max_speed) v = v / fabs(v) * c->max_speed;
     rb->speed = v; rb->omega = w;
     rb->theta = rb->theta + rb->omega * c->delta;
-    if (!orc_move(c, rb, crx, cry, tr ? tr->cinfo : NULL)) return 0;
+    const int moved = orc_move(c, rb, crx, cry, tr ? tr->cinfo : NULL);
+    if (ps && rb->ncollide != ncoll_before) ps->backing = 10;          /* on_collision (pid_controller.py:166-167) */
+    if (!moved) return 0;
     rb->ticks++;
     if (c->goal_on && !(rb->flags & ORC_F_GOAL)) {
         /* pid_controller.py:210-213: `npdata.item((int(gx), int(gy))) is 0` or norm(goal - pos) <= radius * 1.85 */
@@ -417,7 +528,8 @@ static void* orc_worker(void* arg) {
             int alive = 0;
             if (!(rb->flags & (ORC_F_FAULT | ORC_F_DONE))) {
                 const double* nz = c->noise ? c->noise + (size_t)p * (size_t)c->noise_len : NULL;
-                alive = orc_tick(c, rb, genome, crx, cry, &tr, nz);
+                orc_pid* ps = (c->ctrl_kind == ORC_CTRL_PID) ? ((orc_pid*)c->pid_state) + p : NULL;
+                alive = orc_tick(c, rb, genome, crx, cry, &tr, nz, ps);
             }
             if (j->tr_pose) {
                 double* q = j->tr_pose + row * 5;
@@ -435,6 +547,7 @@ static void* orc_worker(void* arg) {
 int orc_run(const orc_cfg* c, orc_robot* robots, const double* genomes, int32_t P, int32_t T, int32_t n_threads,
             double* tr_pose, double* tr_dst, int32_t* tr_hitk, int32_t* tr_hitpx, uint32_t* tr_nsamp, uint32_t* tr_ncoll, double* tr_cinfo) {
     if (c->R > ORC_MAX_RAYS || c->n_layers > ORC_MAX_LAYERS) return -1;
+    if (c->ctrl_kind == ORC_CTRL_PID && (c->R < 3 || c->G != 6 || !c->pid_state)) return -1;
     for (int l = 0; l < c->n_layers; ++l) if (c->layers[l] > ORC_MAX_WIDTH) return -1;
     if (n_threads < 1) n_threads = 1;
     if (n_threads > P) n_threads = P > 0 ? P : 1;
@@ -454,6 +567,7 @@ int orc_run(const orc_cfg* c, orc_robot* robots, const double* genomes, int32_t 
 }
 
 int orc_sizeof_cfg(void) { return (int)sizeof(orc_cfg); }
+int orc_sizeof_pid(void) { return (int)sizeof(orc_pid); }
 int orc_sizeof_robot(void) { return (int)sizeof(orc_robot); }
 int orc_is_portmath(void) {
 #ifdef ORC_PORTMATH

@@ -46,6 +46,8 @@ _SIGS = {
     "r2p2_set_stage_i32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
     "r2p2_set_robot": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_int32]),
     "r2p2_set_controller": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32]),
+    "r2p2_set_pid": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.c_double]),
+    "r2p2_read_pid": (C.c_int, [C.c_void_p] + [C.c_void_p] * 6),
     "r2p2_set_noise": (C.c_int, [C.c_void_p, C.c_int32, C.c_uint64, C.c_void_p, C.c_int32, C.c_int32]),
     "r2p2_read_noise_draws": (C.c_int, [C.c_void_p, C.c_void_p]),
     "r2p2_set_robot_index_offset": (C.c_int, [C.c_void_p, C.c_uint32]),

@@ -91,6 +91,14 @@ struct r2p2_sim {
     // goal flagging
     int goal_on = 0, goal_is_wall = 0;
     double goal_x = 0, goal_y = 0;
+    // Sequential_PID_Controller on the device (r2p2_set_pid): goals as given, per-robot controller state
+    bool have_pid = false;
+    int pid_n_goals = 0, pid_per_robot = 0, pid_goals_P = 0, pid_cap = 0;
+    double pid_max_acc = 5.0, pid_accel = 0.0;
+    double* d_pid_goals = nullptr;      // [n_goals][2] or [P][n_goals][2]
+    double *pid_acc_ang = nullptr, *pid_acc_dist = nullptr, *pid_last_ang = nullptr, *pid_last_dist = nullptr, *pid_target = nullptr;
+    int32_t *pid_state = nullptr, *pid_backing = nullptr, *pid_ngoals = nullptr;
+    double *pid_gx = nullptr, *pid_gy = nullptr;      // goal stacks [R2P2_PID_MAX_GOALS][pid_cap]
     // host-controller bridge (r2p2_sense / r2p2_move)
     double* d_sense_dst = nullptr;      // [P][R]
     int32_t* d_sense_px = nullptr;      // [P][R][2]
@@ -188,6 +196,16 @@ int ensure_genomes(r2p2_handle h, int P, int G) {
     h->P = P; h->G = G;
     h->genomes_t_valid = false;
     return ensure_state(h, P);
+}
+
+int ensure_pid(r2p2_handle h, int P) {
+    if (P <= h->pid_cap) return R2P2_OK;
+    double** dbl[] = {&h->pid_acc_ang, &h->pid_acc_dist, &h->pid_last_ang, &h->pid_last_dist, &h->pid_target};
+    for (double** p : dbl) CK(dalloc(p, (size_t)P));
+    CK(dalloc(&h->pid_state, (size_t)P)); CK(dalloc(&h->pid_backing, (size_t)P)); CK(dalloc(&h->pid_ngoals, (size_t)P));
+    CK(dalloc(&h->pid_gx, (size_t)P * R2P2_PID_MAX_GOALS)); CK(dalloc(&h->pid_gy, (size_t)P * R2P2_PID_MAX_GOALS));
+    h->pid_cap = P;
+    return R2P2_OK;
 }
 
 void free_trace(r2p2_handle h) {
@@ -341,7 +359,7 @@ template <int LPR, bool SMEM, class NET>
 int launch_episode(r2p2_handle h, const KParams& kp, size_t smem, int* occ_out) {
     // 2..16 lanes per robot: the warp-synchronous kernel (r2p2_kernel_ws.cuh), same results, one instruction stream per
     // warp.  R2P2_WS=0 in the environment selects the per-group kernel for A/B measurements.
-    const bool extra = kp.goal_on || kp.skip_sense;     // rarely used switches live in their own instances
+    const bool extra = kp.goal_on || kp.skip_sense || kp.ctrl_kind == R2P2_CTRL_PID;     // rarely used switches live in their own instances
     if constexpr (LPR >= 2 && LPR <= 16 && !SMEM) {
         if (ws_allowed(kp))
             return extra ? launch_kernel<LPR>(h, episode_kernel_ws<LPR, NET, true>, kp, smem, occ_out)
@@ -501,7 +519,9 @@ int r2p2_destroy(r2p2_handle h) {
     void* ptrs[] = {s.x, s.y, s.theta, s.speed, s.omega, s.last_x, s.last_y, s.dist, s.odom_x, s.odom_y, s.origin_x, s.origin_y,
                     s.time, s.fitness, s.flags, s.ncollide, s.ticks, s.ndraws, s.goal_tick, s.nsamp_sonar, s.nsamp_coll, h->d_noise, h->d_x0, h->d_y0, h->d_t0,
                     h->d_wall, h->d_l50, h->d_dist, h->d_crxy, h->d_sincostab, h->d_genomes, h->d_genomes_t, h->d_work, h->d_cnt3,
-                    h->d_ga_pop[0], h->d_ga_pop[1], h->d_ga_fit, h->d_ga_elite, h->d_sense_dst, h->d_sense_px, h->d_cmd, h->d_levels, h->d_hot};
+                    h->d_ga_pop[0], h->d_ga_pop[1], h->d_ga_fit, h->d_ga_elite, h->d_sense_dst, h->d_sense_px, h->d_cmd, h->d_levels, h->d_hot,
+                    h->d_pid_goals, h->pid_acc_ang, h->pid_acc_dist, h->pid_last_ang, h->pid_last_dist, h->pid_target, h->pid_state, h->pid_backing,
+                    h->pid_ngoals, h->pid_gx, h->pid_gy};
     for (void* p : ptrs) cudaFree(p);
     free_trace(h);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -584,7 +604,7 @@ int r2p2_set_robot(r2p2_handle h, double vr0, double vr1, double radius, double 
 
 int r2p2_set_controller(r2p2_handle h, int32_t kind, const int32_t* layers, int32_t n_layers, int32_t activation) {
     if (!h) return R2P2_E_ARG;
-    if (kind < R2P2_CTRL_CONST || kind > R2P2_CTRL_LINEAR) return fail(h, R2P2_E_ARG, "unknown controller kind %d", kind);
+    if (kind < R2P2_CTRL_CONST || kind > R2P2_CTRL_PID) return fail(h, R2P2_E_ARG, "unknown controller kind %d", kind);
     if (activation < 0 || activation > R2P2_ACT_LOGISTIC) return fail(h, R2P2_E_ARG, "unknown activation %d", activation);
     h->maxw = 1;
     if (kind == R2P2_CTRL_NEURO) {
@@ -710,6 +730,19 @@ int r2p2_reset(r2p2_handle h, const double* x0, const double* y0, const double* 
     reset_kernel<<<(h->P + 255) / 256, 256, 0, h->stream>>>(r);
     h->launches++;
     CK(cudaGetLastError());
+    if (h->have_pid) {                                 // fresh controllers: the goal list as configured, PID terms zero
+        if (h->pid_per_robot && h->pid_goals_P != h->P)
+            return fail(h, R2P2_E_ARG, "r2p2_set_pid gave goals for %d robots, the population is %d", h->pid_goals_P, h->P);
+        const int rc = ensure_pid(h, h->P);
+        if (rc) return rc;
+        PidResetParams q;
+        q.P = h->P; q.cap = h->P; q.n_goals = h->pid_n_goals; q.per_robot = h->pid_per_robot; q.goals = h->d_pid_goals;
+        q.acc_ang = h->pid_acc_ang; q.acc_dist = h->pid_acc_dist; q.last_ang = h->pid_last_ang; q.last_dist = h->pid_last_dist; q.target = h->pid_target;
+        q.state = h->pid_state; q.backing = h->pid_backing; q.ngoals = h->pid_ngoals; q.gx = h->pid_gx; q.gy = h->pid_gy;
+        pid_reset_kernel<<<(h->P + 255) / 256, 256, 0, h->stream>>>(q);
+        h->launches++;
+        CK(cudaGetLastError());
+    }
     if (n > 1) CK(cudaStreamSynchronize(h->stream));   // host arrays may be pageable and reused by the caller
     h->have_reset = true;
     if (n == 1) { h->have_pose1 = true; h->rx0 = x0[0]; h->ry0 = y0[0]; h->rt0 = theta0[0]; h->rbudget = time_budget; }
@@ -731,7 +764,7 @@ static int fill_params(r2p2_handle h, KParams& kp, int32_t T, double delta, doub
     if (!(h->radius >= 0.0 && h->radius < 250.0)) kp.crash_clear = 1 << 20;   // never skip the ring
     kp.R = h->R;
     memcpy(kp.ray_deg, h->ray_deg, sizeof(double) * (size_t)h->R);
-    kp.vr1 = h->vr1; kp.radius = h->radius; kp.max_speed = h->max_speed;
+    kp.vr0 = h->vr0; kp.vr1 = h->vr1; kp.radius = h->radius; kp.max_speed = h->max_speed;
     kp.L = h->vr1 + h->radius;
     {
         const volatile double m = h->vr0 * 0.125;   // two roundings, as Python evaluates vr0*0.125 + radius
@@ -764,7 +797,9 @@ static int fill_params(r2p2_handle h, KParams& kp, int32_t T, double delta, doub
     kp.goal_on = h->goal_on; kp.goal_is_wall = h->goal_is_wall; kp.goal_x = h->goal_x; kp.goal_y = h->goal_y;
     kp.goal_r = h->radius * 1.85;                  // pid_controller.py:213
     kp.goal_tick = s.goal_tick;
-
+    kp.pid_acc_ang = h->pid_acc_ang; kp.pid_acc_dist = h->pid_acc_dist; kp.pid_last_ang = h->pid_last_ang; kp.pid_last_dist = h->pid_last_dist;
+    kp.pid_target = h->pid_target; kp.pid_state = h->pid_state; kp.pid_backing = h->pid_backing; kp.pid_ngoals = h->pid_ngoals;
+    kp.pid_gx = h->pid_gx; kp.pid_gy = h->pid_gy; kp.pid_max_acc = h->pid_max_acc; kp.pid_accel = h->pid_accel;
     return R2P2_OK;
 }
 
@@ -783,6 +818,11 @@ int r2p2_run(r2p2_handle h, int32_t T, double delta, double delta_ctrl, int32_t 
         if (g != h->G) return fail(h, R2P2_E_ARG, "genome length %d != MLP weight count %d", h->G, g);
     } else if (h->kind == R2P2_CTRL_LINEAR) {
         if (h->G < 4 || (h->G & 1)) return fail(h, R2P2_E_ARG, "linear chromosome length must be even and >= 4 (got %d)", h->G);
+    } else if (h->kind == R2P2_CTRL_PID) {
+        if (h->G != 6) return fail(h, R2P2_E_ARG, "PID genome must be the six gains [ap, ai, ad, lp, li, ld] (got %d)", h->G);
+        if (h->R < 3) return fail(h, R2P2_E_ARG, "the PID controller reads sonar rays 0, 1, 2, -1 and -2: at least three rays");
+        if (!h->have_pid) return fail(h, R2P2_E_ARG, "r2p2_run: no goal list (call r2p2_set_pid, then r2p2_reset)");
+        if (h->pid_cap < h->P) return fail(h, R2P2_E_ARG, "r2p2_run: controller state not initialised (call r2p2_reset after r2p2_set_pid)");
     } else if (h->G != 2) {
         return fail(h, R2P2_E_ARG, "constant-command genome must be [speed, angular_velocity]");
     }
@@ -848,6 +888,51 @@ int r2p2_cost_grid(r2p2_handle h, int32_t div_x, int32_t div_y, int32_t* values,
     if (e == cudaSuccess && costs) e = cudaMemcpyAsync(costs, d_c, n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
     if (e != cudaSuccess) return fail(h, R2P2_E_CUDA, "r2p2_cost_grid: %s", cudaGetErrorString(e));
+    return R2P2_OK;
+}
+
+/* ---- Sequential_PID_Controller on the device ---- */
+int r2p2_set_pid(r2p2_handle h, const double* goals, int32_t n_goals, int32_t per_robot, double max_acceleration, double acceleration) {
+    if (!h) return R2P2_E_ARG;
+    if (!goals || n_goals < 0) return fail(h, R2P2_E_ARG, "r2p2_set_pid: goals is NULL");
+    if (n_goals > R2P2_PID_MAX_GOALS) return fail(h, R2P2_E_LIMIT, "at most %d goals", R2P2_PID_MAX_GOALS);
+    if (per_robot && h->P < 1) return fail(h, R2P2_E_ARG, "r2p2_set_pid: per-robot goals need the population size (upload genomes first)");
+    ON_DEVICE(h);
+    const size_t n = (size_t)(per_robot ? h->P : 1) * (size_t)n_goals * 2;
+    CK(cudaStreamSynchronize(h->stream));
+    CK(dalloc(&h->d_pid_goals, n));
+    if (n) CK(cudaMemcpyAsync(h->d_pid_goals, goals, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->pid_n_goals = n_goals; h->pid_per_robot = per_robot ? 1 : 0; h->pid_goals_P = per_robot ? h->P : 0;
+    h->pid_max_acc = max_acceleration; h->pid_accel = acceleration;
+    h->have_pid = true;
+    h->have_reset = false;                               // the goal lists are loaded by r2p2_reset
+    return R2P2_OK;
+}
+
+int r2p2_read_pid(r2p2_handle h, int32_t* goals_left, int32_t* state, int32_t* backing, double* target_angle, double* goal_x, double* goal_y) {
+    if (!h) return R2P2_E_ARG;
+    if (!h->have_pid || h->P < 1 || h->pid_cap < h->P) return fail(h, R2P2_E_ARG, "r2p2_read_pid: no PID controller state (r2p2_set_pid, r2p2_reset)");
+    ON_DEVICE(h);
+    const size_t P = (size_t)h->P;
+    std::vector<int32_t> ng(P);
+    CK(cudaMemcpyAsync(ng.data(), h->pid_ngoals, P * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    if (state) CK(cudaMemcpyAsync(state, h->pid_state, P * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    if (backing) CK(cudaMemcpyAsync(backing, h->pid_backing, P * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    if (target_angle) CK(cudaMemcpyAsync(target_angle, h->pid_target, P * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    std::vector<double> gx, gy;
+    if (goal_x || goal_y) {
+        gx.resize(P * R2P2_PID_MAX_GOALS); gy.resize(P * R2P2_PID_MAX_GOALS);
+        CK(cudaMemcpyAsync(gx.data(), h->pid_gx, gx.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(gy.data(), h->pid_gy, gy.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    for (size_t i = 0; i < P; ++i) {
+        if (goals_left) goals_left[i] = ng[i];
+        const bool any = ng[i] > 0 && ng[i] <= R2P2_PID_MAX_GOALS;
+        if (goal_x) goal_x[i] = any ? gx[(size_t)(ng[i] - 1) * P + i] : std::nan("");
+        if (goal_y) goal_y[i] = any ? gy[(size_t)(ng[i] - 1) * P + i] : std::nan("");
+    }
     return R2P2_OK;
 }
 

@@ -154,6 +154,10 @@ __global__ void __launch_bounds__(kBlock, (NET::kLayers > 0 && !NET::kSmemWeight
         }
 
         unsigned goal_tick = (EXTRA && p.goal_on) ? p.goal_tick[rb] : 0xffffffffu;
+        const bool pid = EXTRA && p.ctrl_kind == R2P2_CTRL_PID;      // Sequential_PID_Controller on the device
+        PidState ps;
+        ps.acc_ang = ps.acc_dist = ps.last_ang = ps.last_dist = ps.target = 0.0; ps.state = ps.backing = ps.ngoals = 0;
+        if (pid) pid_load(p, rb, ps);
         bool alive = valid && !(flags & (R2P2_F_FAULT | R2P2_F_DONE));
         StageView svw = sv;                               // the robot's view: its window instead of the global plane
         svw.win_ww = p.win_ww;
@@ -243,7 +247,7 @@ __global__ void __launch_bounds__(kBlock, (NET::kLayers > 0 && !NET::kSmemWeight
             if (live) {
                 dist = R2P2_ADD(dist, r2p2_norm2(R2P2_SUB(x, odom_x), R2P2_SUB(y, odom_y)));
                 odom_x = x; odom_y = y;
-                if (p.ctrl_kind != R2P2_CTRL_CONST) {
+                if (p.ctrl_kind != R2P2_CTRL_CONST && !pid) {
                     if (p.evolve) tmr = R2P2_SUB(tmr, p.delta_ctrl);
                     if (tmr <= 0.0 && p.evolve) {         // episode over: fitness is frozen here
                         fitness = R2P2_ADD(dist, r2p2_norm2(R2P2_SUB(odom_x, origin_x), R2P2_SUB(odom_y, origin_y)));
@@ -317,6 +321,13 @@ __global__ void __launch_bounds__(kBlock, (NET::kLayers > 0 && !NET::kSmemWeight
                 for (int i = 0; i < m; ++i) angv = R2P2_ADD(angv, R2P2_MUL(gen[n + i], bufA[i * NR]));
                 v = lin; w = angv;
                 __syncwarp();
+            } else if (pid) {
+                // scalar per robot, no collectives inside: robots that have stopped skip it; lane 0 of a group writes the goal stack
+                bool ok = true;
+                v = 0.0; w = 0.0;
+                if (live) ok = pid_control(p, sv, ps, rb, g.sub == 0, x, y, theta, speed, bufA, NR, gen, (size_t)1, s_tab, flags, v, w);
+                __syncwarp();                              // bufA is rewritten by the next tick's sense; a pushed goal is visible to the group
+                if (!ok) { flags |= R2P2_F_FAULT; live = false; }
             } else {
                 v = gen[0]; w = gen[1];
             }
@@ -435,9 +446,10 @@ __global__ void __launch_bounds__(kBlock, (NET::kLayers > 0 && !NET::kSmemWeight
                     }
                 }
             }
+            if (live && crash) { x = last_x; y = last_y; ncollide++; tmr = 0.0; ccode |= 1u << 5; }
+            if (pid && ncollide != ncollide0) ps.backing = 10;      // on_collision (pid_controller.py:166-167), also in a tick the reference raised in
             if (live) {
-                if (crash) { x = last_x; y = last_y; ncollide++; tmr = 0.0; ccode |= 1u << 5; }
-                else { last_x = x; last_y = y; }
+                if (!crash) { last_x = x; last_y = y; }
                 ticks++; tdone++;
                 if (ncollide != ncollide0) flags |= R2P2_F_COLLIDED;
                 if ((EXTRA && p.goal_on) && !(flags & R2P2_F_GOAL)) {   // Sequential_PID_Controller.is_at_goal (pid_controller.py:207-213), flag only
@@ -477,6 +489,7 @@ __global__ void __launch_bounds__(kBlock, (NET::kLayers > 0 && !NET::kSmemWeight
             p.nsamp_sonar[rb] += ns_sonar; p.nsamp_coll[rb] += ns_coll;
             if (p.noise_mode) p.ndraws[rb] = ndraws;
             if ((EXTRA && p.goal_on)) p.goal_tick[rb] = goal_tick;
+            if (pid) pid_store(p, rb, ps);
         }
         __syncwarp();
     }

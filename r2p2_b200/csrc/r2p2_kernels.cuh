@@ -64,7 +64,7 @@ struct KParams {
     // robot
     int32_t R;
     double ray_deg[R2P2_MAX_RAYS];
-    double vr1, radius, max_speed;
+    double vr0, vr1, radius, max_speed;
     double L, db_lo, db_hi;            // vr1 + radius, vr0*0.125 + radius, vr0 + radius
     double rad_p1;                     // radius + 1
     // controller
@@ -99,6 +99,11 @@ struct KParams {
     uint32_t* goal_tick;        //   [P] ticks completed when the predicate first held, 0xffffffff = never
     int skip_sense;             // r2p2_move: the tick starts at the controller output (command in `genomes`), no sensor sweep
     double* tr_cinfo;           // [T][P][4]: collide() calls of the tick (code, wall spot x, y, border coordinate), see r2p2_read_trace_collisions
+    // Sequential_PID_Controller (R2P2_CTRL_PID): per-robot controller state, SoA [P]; the goal stack [R2P2_PID_MAX_GOALS][P]
+    double *pid_acc_ang, *pid_acc_dist, *pid_last_ang, *pid_last_dist, *pid_target;
+    int32_t *pid_state, *pid_backing, *pid_ngoals;
+    double *pid_gx, *pid_gy;
+    double pid_max_acc, pid_accel;
     // scheduling
     unsigned int* work_counter;
 };
@@ -773,6 +778,121 @@ __device__ __forceinline__ double activate(int kind, double v, const double* tan
 }
 
 // ---------------------------------------------------------------------------------------------
+// Sequential_PID_Controller.control (r2p2/controllers/pid_controller.py:40-262), one robot, scalar: every lane of a group
+// evaluates it redundantly on the same values.  The arithmetic keeps the reference's evaluation order; its quirks are the
+// reference's (see r2p2_b200/controllers/pid_controller.py for the list).  atan2 is r2p2_atan2 (<= 3 ulp from libm), the
+// avoid state's cos / sin of +-90 degrees (+ turns) are the restated glibc ones.
+// ---------------------------------------------------------------------------------------------
+struct PidState {
+    double acc_ang, acc_dist, last_ang, last_dist, target;
+    int state, backing, ngoals;
+};
+__device__ __forceinline__ void pid_load(const KParams& p, unsigned rb, PidState& ps) {
+    ps.acc_ang = p.pid_acc_ang[rb]; ps.acc_dist = p.pid_acc_dist[rb]; ps.last_ang = p.pid_last_ang[rb]; ps.last_dist = p.pid_last_dist[rb];
+    ps.target = p.pid_target[rb]; ps.state = p.pid_state[rb]; ps.backing = p.pid_backing[rb]; ps.ngoals = p.pid_ngoals[rb];
+}
+__device__ __forceinline__ void pid_store(const KParams& p, unsigned rb, const PidState& ps) {
+    p.pid_acc_ang[rb] = ps.acc_ang; p.pid_acc_dist[rb] = ps.acc_dist; p.pid_last_ang[rb] = ps.last_ang; p.pid_last_dist[rb] = ps.last_dist;
+    p.pid_target[rb] = ps.target; p.pid_state[rb] = ps.state; p.pid_backing[rb] = ps.backing; p.pid_ngoals[rb] = ps.ngoals;
+}
+__device__ __forceinline__ double pymod360(double a) {      // Python float % 360
+    double m = fmod(a, 360.0);
+    if (m != 0.0) { if (m < 0.0) m = R2P2_ADD(m, 360.0); } else m = 0.0;
+    return m;
+}
+__device__ __forceinline__ double pid_brake(const KParams& p, double& speed) {   // Robot.brake (robot.py:354-363)
+    const bool neg = speed < 0.0;
+    const double third = R2P2_DIV(speed, 3.0);
+    const double new_speed = R2P2_SUB(R2P2_SUB(speed, p.pid_accel), third);
+    if ((neg && new_speed > 0.0) || (!neg && new_speed < 0.0)) { speed = 0.0; return R2P2_DIV(r2p2_neg(p.pid_accel), 5.0); }
+    return R2P2_SUB(r2p2_neg(p.pid_accel), third);
+}
+__device__ __forceinline__ double pid_angle_variation(PidState& ps, double theta, double ap, double ai, double ad) {
+    const double e = R2P2_SUB(ps.target, theta);
+    ps.acc_ang = R2P2_ADD(ps.acc_ang, e);
+    const double de = R2P2_SUB(e, ps.last_ang);
+    ps.last_ang = e;
+    return R2P2_ADD(R2P2_ADD(R2P2_MUL(ap, e), R2P2_MUL(ai, ps.acc_ang)), R2P2_MUL(ad, de));
+}
+// dst: the robot's sonar distances (element i at dst[i * stride]); k: its six gains (element i at k[i * kstride]).
+// returns false when the reference would raise (IndexError at the goal pixel) or the goal stack is full.
+__device__ __forceinline__ bool pid_control(const KParams& p, const StageView& sv, PidState& ps, unsigned rb, bool writer, double x, double y,
+                                            double theta, double& speed, const double* dst, int stride, const double* k, size_t kstride,
+                                            const double* s_tab, unsigned& flags, double& v_out, double& w_out) {
+    const int R = p.R;
+    if (ps.backing) { ps.backing -= 1; v_out = theta; w_out = r2p2_neg(p.max_speed); return true; }
+    const double rng = p.vr1;
+    const double d0 = dst[0], d1 = dst[stride], d2 = dst[2 * stride], dm1 = dst[(R - 1) * stride], dm2 = dst[(R - 2) * stride];
+    {
+        const double tol = R2P2_MUL(R2P2_DIV(p.vr0, rng), 13.0);
+        const bool danger = (R2P2_DIV(dm1, rng) < tol && R2P2_DIV(dm2, rng) < tol) || (R2P2_DIV(d1, rng) < tol && R2P2_DIV(d2, rng) < tol) ||
+                            R2P2_DIV(d0, rng) < tol;
+        ps.state = danger ? ((ps.state == 0) ? 1 : 2) : 0;
+    }
+    if (ps.state != 1) {                                   // control_advance
+        if (ps.ngoals == 0) { v_out = 0.0; w_out = 0.0; return true; }
+        const size_t slot = (size_t)(ps.ngoals - 1) * (size_t)p.P + rb;
+        const double gx = p.pid_gx[slot], gy = p.pid_gy[slot];
+        ps.target = R2P2_MUL(r2p2_atan2(R2P2_SUB(gy, y), R2P2_SUB(gx, x)), kDeg);
+        const double angle = pid_angle_variation(ps, theta, k[0], k[kstride], k[2 * kstride]);
+        const double speed0 = speed;
+        double var;
+        if (r2p2_fabs(R2P2_SUB(ps.target, theta)) > 45.0) {
+            ps.acc_dist = R2P2_ADD(ps.acc_dist, pid_brake(p, speed));
+            var = pid_brake(p, speed);
+        } else {
+            const double e = r2p2_norm2(R2P2_SUB(gx, x), R2P2_SUB(gy, y));
+            if (p.pid_accel < p.pid_max_acc) ps.acc_dist = R2P2_ADD(ps.acc_dist, e);
+            const double de = R2P2_SUB(e, ps.last_dist);
+            ps.last_dist = e;
+            var = R2P2_ADD(R2P2_ADD(R2P2_MUL(k[3 * kstride], e), R2P2_MUL(k[4 * kstride], ps.acc_dist)), R2P2_MUL(k[5 * kstride], de));
+        }
+        double acc = R2P2_ADD(p.pid_accel, var);
+        if (acc > p.pid_max_acc) acc = p.pid_max_acc;
+        else if (r2p2_neg(acc) < p.pid_max_acc) acc = r2p2_neg(p.pid_max_acc);
+        v_out = R2P2_ADD(speed0, acc);
+        w_out = angle;
+        // is_at_goal: the goal pixel is a wall, or the robot is within 1.85 radii
+        if (!(isfinite(gx) && isfinite(gy))) return false;                      // int(nan / inf) raises
+        bool f = false;
+        const bool wall = px_probe(sv.wall, sv, dtrunc(gx), dtrunc(gy), f);
+        if (f) return false;
+        if (wall || r2p2_norm2(R2P2_SUB(gx, x), R2P2_SUB(gy, y)) <= p.goal_r) { ps.ngoals -= 1; if (ps.state == 2) ps.state = 0; }
+        return true;
+    }
+    // control_avoid
+    double risk = 1.0;
+    for (int i = 0; i < R; ++i) risk = R2P2_MUL(risk, R2P2_DIV(dst[i * stride], rng));
+    if (R2P2_ADD(d1, d2) < R2P2_ADD(dm1, dm2)) risk = R2P2_DIV(risk, R2P2_MUL(R2P2_DIV(rng, dm1), R2P2_DIV(rng, dm2)));
+    else risk = R2P2_DIV(risk, R2P2_MUL(R2P2_DIV(rng, d1), R2P2_DIV(rng, d2)));
+    if (R2P2_DIV(d0, rng) < 0.45) risk = R2P2_MUL(risk, R2P2_DIV(d0, rng));
+    double safety = R2P2_MUL(R2P2_MUL(R2P2_ADD(rng, p.radius), risk), 2.0);
+    if (safety <= p.vr0) safety = R2P2_MUL(p.vr0, 2.0);
+    const double tm = pymod360(ps.target);
+    const double a = (R2P2_ADD(d1, d2) > R2P2_ADD(dm1, dm2)) ? R2P2_ADD(tm, 90.0) : R2P2_SUB(tm, 90.0);
+    const SinCos sc = sincos_call(R2P2_MUL(R2P2_SUB(ps.target, a), kRad), s_tab);
+    if (!sc.ok) { flags |= R2P2_F_TRIGRANGE; return false; }
+    double x_var = R2P2_MUL(safety, sc.c), y_var = R2P2_MUL(safety, sc.s);
+    const double am = pymod360(a);
+    if (am > 90.0 && am < 270.0) x_var = r2p2_neg(x_var);
+    if (am > 180.0) y_var = r2p2_neg(y_var);
+    if (ps.ngoals >= R2P2_PID_MAX_GOALS) return false;
+    if (writer) {
+        const size_t slot = (size_t)ps.ngoals * (size_t)p.P + rb;
+        p.pid_gx[slot] = R2P2_ADD(x, x_var); p.pid_gy[slot] = R2P2_ADD(y, y_var);
+    }
+    ps.ngoals += 1;
+    (void)pid_angle_variation(ps, theta, k[0], k[kstride], k[2 * kstride]);
+    ps.target = a;
+    bool must_retreat = false;
+    const double lim = R2P2_MUL(R2P2_DIV(p.vr0, rng), 12.0);
+    for (int i = 0; i < R; ++i) must_retreat |= R2P2_DIV(dst[i * stride], rng) < lim;
+    v_out = must_retreat ? r2p2_neg(p.max_speed) : speed;
+    w_out = 0.0;
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------
 // the episode kernel
 // ---------------------------------------------------------------------------------------------
 // dynamic shared memory layout (bytes):
@@ -1112,6 +1232,10 @@ __global__ void __launch_bounds__(kBlock, (NET::kLayers > 0 && !NET::kSmemWeight
         }
 
         unsigned goal_tick = (EXTRA && p.goal_on) ? p.goal_tick[rb] : 0xffffffffu;
+        const bool pid = EXTRA && p.ctrl_kind == R2P2_CTRL_PID;      // Sequential_PID_Controller on the device
+        PidState ps;
+        ps.acc_ang = ps.acc_dist = ps.last_ang = ps.last_dist = ps.target = 0.0; ps.state = ps.backing = ps.ngoals = 0;
+        if (pid) pid_load(p, rb, ps);
         PT_DECL
         int t = 0;
         unsigned ncollide0 = ncollide;
@@ -1194,7 +1318,7 @@ __global__ void __launch_bounds__(kBlock, (NET::kLayers > 0 && !NET::kSmemWeight
             // ---- control: Neuro_controller.control / Inspyred_controller.control -----------------
             dist = R2P2_ADD(dist, r2p2_norm2(R2P2_SUB(x, odom_x), R2P2_SUB(y, odom_y)));
             odom_x = x; odom_y = y;
-            if (p.ctrl_kind != R2P2_CTRL_CONST) {
+            if (p.ctrl_kind != R2P2_CTRL_CONST && !pid) {
                 if (p.evolve) tmr = R2P2_SUB(tmr, p.delta_ctrl);
                 if (tmr <= 0.0 && p.evolve) {             // episode over: fitness is frozen here
                     fitness = R2P2_ADD(dist, r2p2_norm2(R2P2_SUB(odom_x, origin_x), R2P2_SUB(odom_y, origin_y)));
@@ -1275,6 +1399,12 @@ __global__ void __launch_bounds__(kBlock, (NET::kLayers > 0 && !NET::kSmemWeight
                 }
                 v = lin; w = angv;
                 g.sync();
+            } else if (pid) {
+                // every lane of the group evaluates the controller on the same values; lane 0 writes the goal stack
+                const bool ok = (LPR == 1) ? pid_control(p, sv, ps, rb, true, x, y, theta, speed, bufA, NR, p.genomes + rb, (size_t)p.P, s_tab, flags, v, w)
+                                           : pid_control(p, sv, ps, rb, g.sub == 0, x, y, theta, speed, bufA, NR, gen, (size_t)1, s_tab, flags, v, w);
+                g.sync();                                  // bufA is rewritten by the next tick's sense; a pushed goal is visible to the group
+                if (!ok) { flags |= R2P2_F_FAULT; break; }
             } else {
                 if (LPR == 1) { v = __ldg(p.genomes + rb); w = __ldg(p.genomes + (size_t)p.P + rb); }
                 else { v = gen[0]; w = gen[1]; }
@@ -1405,6 +1535,7 @@ __global__ void __launch_bounds__(kBlock, (NET::kLayers > 0 && !NET::kSmemWeight
             PT(7)
             ticks++;
             if (ncollide != ncollide0) flags |= R2P2_F_COLLIDED;
+            if (pid && ncollide != ncollide0) ps.backing = 10;      // on_collision (pid_controller.py:166-167)
             if ((EXTRA && p.goal_on) && !(flags & R2P2_F_GOAL)) {   // Sequential_PID_Controller.is_at_goal (pid_controller.py:207-213), flag only
                 if (p.goal_is_wall || r2p2_norm2(R2P2_SUB(p.goal_x, x), R2P2_SUB(p.goal_y, y)) <= p.goal_r) { flags |= R2P2_F_GOAL; goal_tick = ticks; }
             }
@@ -1418,6 +1549,7 @@ __global__ void __launch_bounds__(kBlock, (NET::kLayers > 0 && !NET::kSmemWeight
         }
         PT_FLUSH(rb == 0 && g.sub == 0)
         if (ncollide != p.ncollide[rb]) flags |= R2P2_F_COLLIDED;
+        if (pid && ncollide != ncollide0) ps.backing = 10;          // collide() calls of a tick the reference raised in
         if (tracing && g.sub == 0) {     // rows of ticks that did not complete: frozen pose (as the oracle records them)
             for (int t2 = t; t2 < p.T; ++t2) {
                 const size_t trow = (size_t)t2 * (size_t)p.P + rb;
@@ -1439,6 +1571,7 @@ __global__ void __launch_bounds__(kBlock, (NET::kLayers > 0 && !NET::kSmemWeight
             p.nsamp_sonar[rb] += ns_sonar; p.nsamp_coll[rb] += ns_coll;
             if (p.noise_mode) p.ndraws[rb] = ndraws;
             if ((EXTRA && p.goal_on)) p.goal_tick[rb] = goal_tick;
+            if (pid) pid_store(p, rb, ps);
         }
         g.sync();
     }
@@ -1563,6 +1696,26 @@ __global__ void reset_kernel(const ResetParams r) {
     r.nsamp_sonar[i] = 0ull; r.nsamp_coll[i] = 0ull;
     r.ndraws[i] = 0u;
     r.goal_tick[i] = 0xffffffffu;
+}
+
+// Fresh Sequential_PID_Controllers: zero PID terms, state 0, the configured goal list on the stack (slot n-1 = goal[0]).
+struct PidResetParams {
+    int P, cap, n_goals, per_robot;
+    const double* goals;             // [n_goals][2] or [P][n_goals][2]
+    double *acc_ang, *acc_dist, *last_ang, *last_dist, *target;
+    int32_t *state, *backing, *ngoals;
+    double *gx, *gy;                 // [R2P2_PID_MAX_GOALS][cap]
+};
+__global__ void pid_reset_kernel(const PidResetParams q) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= q.P) return;
+    q.acc_ang[i] = 0.0; q.acc_dist[i] = 0.0; q.last_ang[i] = 0.0; q.last_dist[i] = 0.0; q.target[i] = 0.0;
+    q.state[i] = 0; q.backing[i] = 0; q.ngoals[i] = q.n_goals;
+    const double* gl = q.goals + (q.per_robot ? (size_t)i * q.n_goals * 2 : 0);
+    for (int s = 0; s < q.n_goals; ++s) {
+        q.gx[(size_t)s * q.cap + i] = gl[(q.n_goals - 1 - s) * 2];
+        q.gy[(size_t)s * q.cap + i] = gl[(q.n_goals - 1 - s) * 2 + 1];
+    }
 }
 
 __global__ void sum_counters_kernel(const unsigned long long* __restrict__ a, const unsigned long long* __restrict__ b,

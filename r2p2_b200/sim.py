@@ -10,7 +10,7 @@ import numpy as np
 from . import _lib
 from ._lib import R2P2Error, check
 
-CTRL = {"const": 0, "neuro": 1, "linear": 2}
+CTRL = {"const": 0, "neuro": 1, "linear": 2, "pid": 3}
 ACT = {"identity": 0, "tanh": 1, "relu": 2, "logistic": 3}
 F_COLLIDED, F_FAULT, F_DONE, F_TRIGRANGE = 1, 2, 4, 8
 
@@ -109,6 +109,26 @@ class BatchSim:
             self._ck(self._L.r2p2_set_controller(self._h, CTRL[kind], layers.ctypes.data, len(layers), ACT[activation]))
         else:
             self._ck(self._L.r2p2_set_controller(self._h, CTRL[kind], None, 0, 0))
+
+    def set_pid(self, goals, max_acceleration=5.0, acceleration=0.0):
+        """Goal list(s) of the device Sequential_PID_Controller (controller kind "pid", genome = [ap, ai, ad, lp, li, ld]):
+        [n, 2] shared by every robot, or [P, n, 2].  Loaded by the next ``reset``; the reference's register_robot starts
+        the robot at goals[0] -- pass that as the start pose."""
+        g = _f64(goals)
+        if g.ndim not in (2, 3) or g.shape[-1] != 2:
+            raise ValueError("goals must be [n, 2] or [P, n, 2]")
+        if g.ndim == 3 and g.shape[0] != self.P:
+            raise ValueError("per-robot goals: %d lists for a population of %d" % (g.shape[0], self.P))
+        self._ck(self._L.r2p2_set_pid(self._h, g.ctypes.data, g.shape[-2], int(g.ndim == 3), float(max_acceleration), float(acceleration)))
+
+    def pid_state(self):
+        """Controller state per robot: goals left, state (0 advancing, 1 avoiding, 2 advancing after avoiding), ticks of
+        backing off left, target angle, current goal (NaN when the list is empty)."""
+        P = self.P
+        out = {k: np.empty(P, dtype=np.int32) for k in ("goals_left", "state", "backing")}
+        out.update({k: np.empty(P) for k in ("target_angle", "goal_x", "goal_y")})
+        self._ck(self._L.r2p2_read_pid(self._h, *[out[k].ctypes.data for k in ("goals_left", "state", "backing", "target_angle", "goal_x", "goal_y")]))
+        return out
 
     def set_noise(self, mode="off", seed=0, stream=None):
         """Sensor noise (Robot.has_noise): "off", "replay" (stream[P, len] of N(0, 0.5) draws, bit-exact with the
