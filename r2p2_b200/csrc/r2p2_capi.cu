@@ -293,7 +293,7 @@ int upload_crxy(r2p2_handle h) {
 }
 
 // occ_out != NULL: only report how many CTAs of the kernel this configuration selects fit on an SM (no launch)
-struct OccEntry { const void* fn; int device; size_t smem; int occ; };
+struct OccEntry { const void* fn; int device; size_t smem; int block; int occ; };
 std::vector<OccEntry> g_occ_cache;      // per kernel instance: dynamic shared memory it was sized for, CTAs per SM
 std::mutex g_occ_mutex;                 // handles of different host threads share the cache
 
@@ -302,22 +302,22 @@ int launch_kernel(r2p2_handle h, KERN kern, const KParams& kp, size_t smem, int*
     int occ = -1;
     std::lock_guard<std::mutex> lock(g_occ_mutex);
     for (const OccEntry& e : g_occ_cache)
-        if (e.fn == (const void*)kern && e.device == h->device && e.smem == smem) { occ = e.occ; break; }
+        if (e.fn == (const void*)kern && e.device == h->device && e.smem == smem && e.block == kp.block) { occ = e.occ; break; }
     if (occ < 0) {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kBlock, smem));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kp.block, smem));
         // one entry per (kernel, device): a new size replaces the old one, the attribute is the last one set
         g_occ_cache.erase(std::remove_if(g_occ_cache.begin(), g_occ_cache.end(), [&](const OccEntry& e) { return e.fn == (const void*)kern && e.device == h->device; }), g_occ_cache.end());
-        g_occ_cache.push_back({(const void*)kern, h->device, smem, occ});
+        g_occ_cache.push_back({(const void*)kern, h->device, smem, kp.block, occ});
     }
     if (occ_out) { *occ_out = occ; return R2P2_OK; }
     if (occ < 1) return fail(h, R2P2_E_LIMIT, "episode kernel does not fit on an SM (smem %zu bytes)", smem);
-    const int robots_per_cta = kBlock / LPR;
+    const int robots_per_cta = kp.block / LPR;
     long long ctas = ((long long)kp.P + robots_per_cta - 1) / robots_per_cta;
     ctas = std::min<long long>(ctas, (long long)occ * h->sm_count);   // persistent: the work counter feeds the rest
     CK(cudaMemsetAsync(h->d_work, 0, sizeof(unsigned int), h->stream));
     CK(cudaEventRecord(h->ev0, h->stream));
-    kern<<<(unsigned)ctas, kBlock, smem, h->stream>>>(kp);
+    kern<<<(unsigned)ctas, kp.block, smem, h->stream>>>(kp);
     CK(cudaEventRecord(h->ev1, h->stream));
     h->ev_valid = true;
     h->launches++;
@@ -342,7 +342,7 @@ void window_geometry(KParams& kp, int lpr) {
     if (lpr < 2 || lpr > 16 || !kp.g_hot || no_win || !(kp.L > -1.0 && kp.L < 30000.0)) return;
     int tl = 1;
     while (tl * 2 * kp.R <= lpr && tl < kMaxSonarTeam) tl *= 2;
-    const int own_s = sonar_nown(tl, lpr <= 2 ? 8 : 4), own_c = (lpr >= 16 ? 1 : lpr >= 8 ? 2 : 4);
+    const int own_s = sonar_nown(tl, kWsSonarOwn<2> == kWsSonarOwn<8> ? 8 : (lpr <= 2 ? 8 : 4)), own_c = (lpr >= 16 ? 1 : lpr >= 8 ? 2 : 4);
     const int kB_s = (int)std::ceil(kp.L + 1e-6);
     const double climit = std::fabs(kp.max_speed * kp.delta) + std::fabs(kp.radius);
     if (!(climit < 4096.0)) return;
@@ -351,7 +351,7 @@ void window_geometry(KParams& kp, int lpr) {
     const int slack = 8;                                   // a fetched window is kept until the robot has moved this far
     const int ww = (((2 * (half + slack) + 32 + 7) / 8) + 3) / 4 * 4, wb = (2 * (half + slack) + 4 + 3) / 4;
     if (half + slack + 96 > kp.hpad) return;                                             // the window must stay inside the plane's margin
-    if ((size_t)(kBlock / lpr) * ww * wb * 4 > 64 * 1024) return;                 // too fat: the per-group kernel reads the plane through L1
+    if ((size_t)(kp.block / lpr) * ww * wb * 4 > (size_t)64 * 1024 * (kp.block / 128)) return;                 // too fat: the per-group kernel reads the plane through L1
     kp.win_ww = ww; kp.win_wb = wb; kp.win_half = half; kp.win_slack = slack;
 }
 
@@ -392,51 +392,82 @@ int launch_episode_s(r2p2_handle h, KParams& kp, bool smem_stage, int* occ_out) 
     if constexpr (LPR >= 16) if (!smem_stage) {
         if (net_matches<NetNeuro>(kp)) {
             kp.w_in_smem = 0;
-            return launch_episode<LPR, false, NetNeuro>(h, kp, episode_smem_bytes(LPR, false, kp.plane_bytes, kp.has50, kp.maxw, 0, kp.G, kp.win_ww * kp.win_wb, kp.tanh_in_smem), occ_out);
+            return launch_episode<LPR, false, NetNeuro>(h, kp, episode_smem_bytes(kp.block, LPR, false, kp.plane_bytes, kp.has50, kp.maxw, 0, kp.G, kp.win_ww * kp.win_wb, kp.tanh_in_smem), occ_out);
         }
         if (net_matches<NetSimple>(kp)) {
             kp.w_in_smem = 0;
-            return launch_episode<LPR, false, NetSimple>(h, kp, episode_smem_bytes(LPR, false, kp.plane_bytes, kp.has50, kp.maxw, 0, kp.G, kp.win_ww * kp.win_wb, kp.tanh_in_smem), occ_out);
+            return launch_episode<LPR, false, NetSimple>(h, kp, episode_smem_bytes(kp.block, LPR, false, kp.plane_bytes, kp.has50, kp.maxw, 0, kp.G, kp.win_ww * kp.win_wb, kp.tanh_in_smem), occ_out);
         }
     }
     // one lane per robot: compile-time shape over the transposed genome array
     if constexpr (LPR == 1) if (!smem_stage) {
-        const size_t sm = episode_smem_bytes(1, false, kp.plane_bytes, kp.has50, kp.maxw, 0, kp.G, 0, kp.tanh_in_smem);
+        const size_t sm = episode_smem_bytes(kp.block, 1, false, kp.plane_bytes, kp.has50, kp.maxw, 0, kp.G, 0, kp.tanh_in_smem);
         if (net_matches<NetNeuro>(kp)) return launch_episode<1, false, SmemNet<NetNeuro>>(h, kp, sm, occ_out);
         if (net_matches<NetSimple>(kp)) return launch_episode<1, false, SmemNet<NetSimple>>(h, kp, sm, occ_out);
     }
     // 2..8 lanes: compile-time shape, weights read through one pointer per robot -- its genome's copy in shared memory
     // when the robots in flight fit there (w_in_smem), else the [P][G] array itself (L1/L2)
     if constexpr (LPR >= 2 && LPR <= 8) if (!smem_stage && ws_allowed(kp)) {
-        const size_t sm = episode_smem_bytes(LPR, false, kp.plane_bytes, kp.has50, kp.maxw, kp.w_in_smem, kp.G, kp.win_ww * kp.win_wb, kp.tanh_in_smem);
+        const size_t sm = episode_smem_bytes(kp.block, LPR, false, kp.plane_bytes, kp.has50, kp.maxw, kp.w_in_smem, kp.G, kp.win_ww * kp.win_wb, kp.tanh_in_smem);
         if (net_matches<NetNeuro>(kp)) return launch_episode<LPR, false, SmemNet<NetNeuro>>(h, kp, sm, occ_out);
         if (net_matches<NetSimple>(kp)) return launch_episode<LPR, false, SmemNet<NetSimple>>(h, kp, sm, occ_out);
         if constexpr (LPR >= 4) if (net_matches<NetSweep>(kp) && !(kp.goal_on || kp.skip_sense))
             return launch_kernel<LPR>(h, episode_kernel_ws<LPR, SmemNet<NetSweep>, false>, kp, sm, occ_out);
     }
-    const size_t smem = episode_smem_bytes(LPR, smem_stage, kp.plane_bytes, kp.has50, kp.maxw, kp.w_in_smem, kp.G, kp.win_ww * kp.win_wb, kp.tanh_in_smem);
+    const size_t smem = episode_smem_bytes(kp.block, LPR, smem_stage, kp.plane_bytes, kp.has50, kp.maxw, kp.w_in_smem, kp.G, kp.win_ww * kp.win_wb, kp.tanh_in_smem);
     return smem_stage ? launch_episode<LPR, true, GenericNet>(h, kp, smem, occ_out) : launch_episode<LPR, false, GenericNet>(h, kp, smem, occ_out);
 }
 
 // genomes of the robots in flight live in shared memory when the group mapping leaves room for them
-int w_in_smem_for(int lpr, int G) {
+int w_in_smem_for(int block, int lpr, int G) {
     // R2P2_WSMEM_KB (experiments): largest genome block a CTA may hold in shared memory; two CTAs per SM must still fit
     static const size_t lim = [] { const char* e = getenv("R2P2_WSMEM_KB"); return (size_t)(e ? atoi(e) : 48) * 1024; }();
-    return (lpr > 1 && (size_t)(kBlock / lpr) * G * 8 <= lim) ? 1 : 0;
+    return (lpr > 1 && (size_t)(block / lpr) * G * 8 <= lim * (block / 128)) ? 1 : 0;
+}
+
+// Shared-memory plan of one launch for a given CTA size: windows first, then the genomes of the robots in flight, then
+// the tanh table -- each only while 16 warps per SM (512 / block CTAs of the 128-register instances) still fit.
+void plan_smem(KParams& kp, int lpr, bool smem_stage) {
+    const size_t per_cta = (size_t)55 * 1024 * (kp.block / 128);
+    kp.w_in_smem = w_in_smem_for(kp.block, lpr, kp.G);
+    window_geometry(kp, lpr);
+    if (kp.w_in_smem && kp.win_ww && episode_smem_bytes(kp.block, lpr, false, kp.plane_bytes, kp.has50, kp.maxw, 1, kp.G, kp.win_ww * kp.win_wb) > per_cta)
+        kp.w_in_smem = 0;
+    // the tanh table (18 KB): rows are picked per lane, so a global read is up to 32 L1 lookups per instruction against a
+    // few shared-memory wavefronts
+    static const bool no_tanh_smem = [] { const char* e = getenv("R2P2_NO_TANH_SMEM"); return e && e[0] == '1'; }();
+    kp.tanh_in_smem = (!no_tanh_smem && !smem_stage && kp.ctrl_kind == R2P2_CTRL_NEURO && kp.activation == R2P2_ACT_TANH &&
+                       episode_smem_bytes(kp.block, lpr, false, kp.plane_bytes, kp.has50, kp.maxw, kp.w_in_smem, kp.G, kp.win_ww * kp.win_wb, 1) <= per_cta) ? 1 : 0;
+}
+
+// Threads per CTA.  The register-weight instances run 128.  The others hold 16 warps per SM whatever the split, so the
+// choice is about (a) how the population spreads over the SMs -- the run lasts as long as its fullest SM, so the split
+// with the fewest warps on the fullest SM wins -- and (b) at equal spread, the largest CTA: its tables are staged once
+// per SM and the shared memory that saves is L1 for the genomes (R2P2_BLOCK in the environment forces a size).
+int choose_block(r2p2_handle h, const KParams& kp, int lpr, bool smem_stage) {
+    const bool regw = lpr >= 16 && !smem_stage && (net_matches<NetNeuro>(kp) || net_matches<NetSimple>(kp));
+    if (regw) return kRegBlock;
+    static const int forced = [] { const char* e = getenv("R2P2_BLOCK"); const int v = e ? atoi(e) : 0; return (v == 128 || v == 256 || v == 512) ? v : 0; }();
+    if (forced) return forced;
+    int best = 128;
+    long long best_warps = -1;
+    for (int block = kMaxBlock; block >= 128; block >>= 1) {
+        KParams k2 = kp;
+        k2.block = block;
+        plan_smem(k2, lpr, smem_stage);
+        const size_t smem = episode_smem_bytes(block, lpr, smem_stage, k2.plane_bytes, k2.has50, k2.maxw, k2.w_in_smem, k2.G, k2.win_ww * k2.win_wb, k2.tanh_in_smem);
+        if (smem > h->smem_optin || smem * (kMaxBlock / block) > (size_t)225 * 1024) continue;   // 16 warps per SM must fit
+        const long long ctas = ((long long)kp.P * lpr + block - 1) / block;
+        const long long per_sm = std::min<long long>((ctas + h->sm_count - 1) / h->sm_count, kMaxBlock / block);
+        const long long warps = per_sm * (block / 32);
+        if (best_warps < 0 || warps < best_warps) { best_warps = warps; best = block; }
+    }
+    return best;
 }
 
 int dispatch_episode(r2p2_handle h, KParams& kp, int lpr, bool smem_stage, int* occ_out) {
-    kp.w_in_smem = w_in_smem_for(lpr, kp.G);
-    window_geometry(kp, lpr);
-    // four CTAs per SM (what the register budget allows) need <= ~55 KB each: the windows come first, the genomes of the
-    // robots in flight stay in shared memory only if both fit (else they are read through L1/L2)
-    if (kp.w_in_smem && kp.win_ww && episode_smem_bytes(lpr, false, kp.plane_bytes, kp.has50, kp.maxw, 1, kp.G, kp.win_ww * kp.win_wb) > 55 * 1024)
-        kp.w_in_smem = 0;
-    // the tanh table (18 KB): rows are picked per lane, so a global read is up to 32 L1 lookups per instruction against a
-    // few shared-memory wavefronts -- staged whenever it still leaves room for four CTAs per SM
-    static const bool no_tanh_smem = [] { const char* e = getenv("R2P2_NO_TANH_SMEM"); return e && e[0] == '1'; }();
-    kp.tanh_in_smem = (!no_tanh_smem && !smem_stage && kp.ctrl_kind == R2P2_CTRL_NEURO && kp.activation == R2P2_ACT_TANH &&
-                       episode_smem_bytes(lpr, false, kp.plane_bytes, kp.has50, kp.maxw, kp.w_in_smem, kp.G, kp.win_ww * kp.win_wb, 1) <= 55 * 1024) ? 1 : 0;
+    kp.block = choose_block(h, kp, lpr, smem_stage);
+    plan_smem(kp, lpr, smem_stage);
     switch (lpr) {
         case 1: return launch_episode_s<1>(h, kp, smem_stage, occ_out);
         case 2: return launch_episode_s<2>(h, kp, smem_stage, occ_out);
@@ -456,7 +487,7 @@ int choose_lpr(r2p2_handle h, const KParams& kp) {
         KParams k2 = kp;
         int occ = 0;
         if (dispatch_episode(h, k2, lpr, false, &occ) != R2P2_OK) continue;
-        const long long ctas = ((long long)h->P * lpr + kBlock - 1) / kBlock;
+        const long long ctas = ((long long)h->P * lpr + k2.block - 1) / k2.block;
         if (ctas <= (long long)occ * h->sm_count) return lpr;
     }
     // more robots than fit at once.  Many rays per robot (config E: 32 rays, 262144 robots): eight lanes split the fan, the
@@ -862,10 +893,9 @@ int r2p2_run(r2p2_handle h, int32_t T, double delta, double delta_ctrl, int32_t 
         kp.tr_nsamp = h->tr_nsamp; kp.tr_ncoll = h->tr_ncoll; kp.tr_cinfo = h->tr_cinfo;
     }
 
-    kp.w_in_smem = w_in_smem_for(lpr, kp.G);
     bool smem_stage = h->smem_req == 1;   // default off: measured on B200, L1-cached global reads of the planes are as fast as the shared copy
     if (smem_stage) {
-        const size_t with_stage = episode_smem_bytes(lpr, true, kp.plane_bytes, kp.has50, kp.maxw, kp.w_in_smem, kp.G);
+        const size_t with_stage = episode_smem_bytes(128, lpr, true, kp.plane_bytes, kp.has50, kp.maxw, w_in_smem_for(128, lpr, kp.G), kp.G);
         if (with_stage > h->smem_optin) return fail(h, R2P2_E_LIMIT, "stage planes (%zu bytes with tables) exceed shared memory", with_stage);
     }
     return dispatch_episode(h, kp, lpr, smem_stage, nullptr);

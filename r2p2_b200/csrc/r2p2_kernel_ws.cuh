@@ -14,9 +14,6 @@
 
 #include "r2p2_kernels.cuh"
 
-#ifndef R2P2_WS_MINB
-#define R2P2_WS_MINB 4
-#endif
 namespace r2p2 {
 
 #ifdef R2P2_EXP_FETCH_ONLY      // experiment: windows are fetched but the marches read the global plane
@@ -56,14 +53,18 @@ struct WGroup {
 
 // own samples per pass of the sonar teams (below 8 lanes per ray) and of the collision team (the whole group, 16 samples
 // per pass: collision rays are speed * delta + radius long); the host sizes the windows with the same numbers
+#ifdef R2P2_EXP_SONAR_OWN8
+template <int LPR> constexpr int kWsSonarOwn = 8;
+#else
 template <int LPR> constexpr int kWsSonarOwn = (LPR <= 2 ? 8 : 4);
+#endif
 template <int LPR> constexpr int kWsCollOwn = (LPR >= 16 ? 1 : LPR >= 8 ? 2 : 4);
 
 template <int LPR, class NET, bool EXTRA = false>
-__global__ void __launch_bounds__(kBlock, (NET::kLayers > 0 && !NET::kSmemWeights) ? 1 : R2P2_WS_MINB) episode_kernel_ws(const __grid_constant__ KParams p) {
+__global__ void __launch_bounds__((NET::kLayers > 0 && !NET::kSmemWeights) ? kRegBlock : kMaxBlock, 1) episode_kernel_ws(const __grid_constant__ KParams p) {
     static_assert(LPR >= 2 && LPR <= 16, "warp-synchronous kernel: 2..16 lanes per robot");
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int NR = kBlock / LPR;                      // robots in flight per CTA
+    const int NR = (int)blockDim.x / LPR;                 // robots in flight per CTA
     constexpr int RPW = 32 / LPR;                         // robots per warp
     constexpr unsigned FULL = 0xffffffffu;
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw);

@@ -42,7 +42,12 @@ __device__ unsigned long long g_robot_cycles[65536 * 12];   // per robot, per ph
 #ifndef R2P2_RING_T
 #define R2P2_RING_T 8           // one-lane mapping: above this many rings per converged warp every lane scans its own (measured: 4, 8, 12, 16)
 #endif
-constexpr int kBlock = 128;                    // threads per CTA
+// Threads per CTA are chosen per launch (128, 256 or 512; blockDim.x): the 128-register instances hold 16 warps per SM
+// whatever the split, and one large CTA stages the read-only tables once per SM instead of four times -- the shared
+// memory that frees goes to L1, where the genomes of the robots in flight live (measured: config E 130 -> 122 ms per 200
+// ticks, scenario-track 62 -> 57 ms).  The register-weight instances (up to 242 registers) run 128 threads.
+constexpr int kMaxBlock = 512;
+constexpr int kRegBlock = 128;
 constexpr double kRad = 3.14159265358979323846 / 180.0;   // CPython math.radians multiplier
 constexpr double kDeg = 180.0 / 3.14159265358979323846;   // CPython math.degrees multiplier
 constexpr double kNormSlack = 1e-6;            // |norm(p_k - o) - k| bound used to skip the norm test (see march)
@@ -106,6 +111,7 @@ struct KParams {
     double pid_max_acc, pid_accel;
     // scheduling
     unsigned int* work_counter;
+    int32_t block;                     // threads per CTA of this launch (host side; the kernels read blockDim.x)
 };
 
 struct StageView {
@@ -420,14 +426,14 @@ __device__ __forceinline__ Hit team_march_t(const StageView& s, const Team& tm, 
         // lane per ray: re-walked from the pass start with the same additions (at most NOWN - 1 of them; no registers
         // held across the pass).  Teams: kept per sample -- a re-walk of up to TL * (NOWN - 1) dependent additions would
         // sit on the critical path of the latency-bound mappings (config B: +7 %).
-        constexpr int NKEEP = (TL > 1) ? NOWN : 1;
+        constexpr int NKEEP = (TL > 1 || WIN) ? NOWN : 1;
         double xs[NKEEP], ys[NKEEP];
         xs[0] = x; ys[0] = y;                               // this lane's first sample of the pass
         unsigned w[NOWN];
         int sh[NOWN];
 #pragma unroll
         for (int m = 0; m < NOWN; ++m) {
-            if constexpr (TL > 1) { xs[m] = x; ys[m] = y; }
+            if constexpr (NKEEP > 1) { xs[m] = x; ys[m] = y; }
             const int ix = floor_lo(x), iy = floor_lo(y);
             if constexpr (WIN) w[m] = lds_u32(s.win_sb + 4u * (unsigned)hot_word(ix, iy, hwpr));
             else w[m] = __ldg(hot + hot_word(ix, iy, hwpr));
@@ -446,7 +452,7 @@ __device__ __forceinline__ Hit team_march_t(const StageView& s, const Team& tm, 
             if (rem < TL * NOWN) evm &= (1u << ((rem + TL - 1) / TL)) - 1u;   // own samples at or beyond kB do not count
             if (win_owner) {                                // the knife-edge sample, if any, is the last one of the ray
                 xw = xs[0]; yw = ys[0];
-                if constexpr (TL > 1) {
+                if constexpr (NKEEP > 1) {
                     const int mw = (kA - k0) / TL;
 #pragma unroll
                     for (int m = 1; m < NOWN; ++m) if (mw == m) { xw = xs[m]; yw = ys[m]; }
@@ -458,7 +464,7 @@ __device__ __forceinline__ Hit team_march_t(const StageView& s, const Team& tm, 
         if (evm) {                                          // this lane's first event: its position, its kind
             const int me = __ffs((int)evm) - 1;
             hx = xs[0]; hy = ys[0];
-            if constexpr (TL > 1) {
+            if constexpr (NKEEP > 1) {
 #pragma unroll
                 for (int m = 1; m < NOWN; ++m) if (me == m) { hx = xs[m]; hy = ys[m]; }
             } else {
@@ -757,7 +763,11 @@ struct SinCos {
     double s, c;
     int ok;
 };
+#ifdef R2P2_EXP_SINCOS_NOINLINE
+__device__ __noinline__ SinCos sincos_call(double a, const double* tab) {
+#else
 __device__ __forceinline__ SinCos sincos_call(double a, const double* tab) {
+#endif
     SinCos r;
     r.ok = 1;
     r2p2_sincos(a, tab, &r.s, &r.c, &r.ok);
@@ -902,17 +912,17 @@ __device__ __forceinline__ bool pid_control(const KParams& p, const StageView& s
 //   [.., +18304)                   tanh table (tanh_in_smem only)
 //   [.., +plane_bytes)             wall plane      (SMEM_STAGE only)
 //   [.., +plane_bytes)             level-50 plane  (SMEM_STAGE and has50 only)
-//   [.., +2*maxw*NR*8)             MLP / sonar buffers A and B, element i of robot slot r at [i*NR + r]
+//   [.., +2*maxw*NR*8)             MLP / sonar buffers A and B, element i of robot slot r at [i*NR + r]; NR = blockDim.x / LPR
 //   [.., +NR*G*8)                  genomes of the robots in flight (w_in_smem only), row r at [r*G]
 //   [.., +NR*win_words*4)          per-robot windows of the hot plane (warp-synchronous kernel)
-__host__ __device__ inline size_t episode_smem_bytes(int lpr, bool smem_stage, uint32_t plane_bytes, int has50, int maxw, int w_in_smem, int G,
+__host__ __device__ inline size_t episode_smem_bytes(int block, int lpr, bool smem_stage, uint32_t plane_bytes, int has50, int maxw, int w_in_smem, int G,
                                                      int win_words = 0, int tanh_in_smem = 0) {
     size_t n = 16 + R2P2_SINCOSTAB_LEN * 8 + 720 * 8;
     if (tanh_in_smem) n += (size_t)R2P2_TANH_NINT * R2P2_TANH_ROW * 8;
     if (smem_stage) n += (size_t)plane_bytes * (has50 ? 2 : 1);
-    n += (size_t)2 * maxw * (kBlock / lpr) * 8;
-    if (w_in_smem) n += (size_t)(kBlock / lpr) * G * 8;
-    if (win_words) n += (size_t)(kBlock / lpr) * (size_t)win_words * 4;
+    n += (size_t)2 * maxw * (block / lpr) * 8;
+    if (w_in_smem) n += (size_t)(block / lpr) * G * 8;
+    if (win_words) n += (size_t)(block / lpr) * (size_t)win_words * 4;
     return n;
 }
 
@@ -1137,9 +1147,9 @@ struct FixedMlp<LPR, GenericNet> {
 // EXTRA: goal flagging / r2p2_move's skip_sense compiled in.  The plain instance is what evaluations run; keeping the
 // rarely used switches out of it is worth 2-3 % on config B (register allocation of the latency-bound chain).
 template <int LPR, bool SMEM_STAGE, class NET, bool EXTRA = false>
-__global__ void __launch_bounds__(kBlock, (NET::kLayers > 0 && !NET::kSmemWeights) ? 1 : 4) episode_kernel(const __grid_constant__ KParams p) {
+__global__ void __launch_bounds__((NET::kLayers > 0 && !NET::kSmemWeights) ? kRegBlock : kMaxBlock, 1) episode_kernel(const __grid_constant__ KParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int NR = kBlock / LPR;                      // robots in flight per CTA
+    const int NR = (int)blockDim.x / LPR;                 // robots in flight per CTA
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw);
     double* s_tab = reinterpret_cast<double*>(smem_raw + 16);
     double* s_crx = s_tab + R2P2_SINCOSTAB_LEN;
