@@ -348,7 +348,8 @@ void window_geometry(KParams& kp, int lpr) {
     if (!(climit < 4096.0)) return;
     const int kB_c = (int)std::ceil(climit + 1e-6) + 1;
     const int half = std::max(std::max(kB_s + tl * own_s + 1, kB_c + lpr * own_c + 3), (int)std::ceil(std::fabs(kp.radius)) + 4) + 1;
-    const int slack = 8;                                   // a fetched window is kept until the robot has moved this far
+    static const int slack_env = [] { const char* e = getenv("R2P2_WIN_SLACK"); return e ? atoi(e) : 0; }();   // experiments
+    const int slack = slack_env > 0 ? slack_env : 8;       // a fetched window is kept until the robot has moved this far
     const int ww = (((2 * (half + slack) + 32 + 7) / 8) + 3) / 4 * 4, wb = (2 * (half + slack) + 4 + 3) / 4;
     if (half + slack + 96 > kp.hpad) return;                                             // the window must stay inside the plane's margin
     if ((size_t)(kp.block / lpr) * ww * wb * 4 > (size_t)64 * 1024 * (kp.block / 128)) return;                 // too fat: the per-group kernel reads the plane through L1
