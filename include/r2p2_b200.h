@@ -164,6 +164,16 @@ int r2p2_write_pose(r2p2_handle h, int32_t first, int32_t count, const double* x
  * semantics -- a robot stops at the control() call where its timer is <= 0 (a collision zeroes the
  * timer) and its fitness is frozen there.  evolve == 0: free run for T ticks.  Asynchronous. */
 int r2p2_run(r2p2_handle h, int32_t T, double delta, double delta_ctrl, int32_t evolve);
+/* evolution.evaluate_ann for a whole population (r2p2/evolution.py:29-52: one candidate per call through weights.json /
+ * fitness.txt) as ONE call: r2p2_upload_genomes + r2p2_reset + r2p2_run + r2p2_read_fitness, with the upload pipelined
+ * when the population runs in three or more waves (a wave = as many robots as are resident at once): the first waves'
+ * genomes go up, then the rest on a copy stream while the episode kernel already runs; the second piece has its own
+ * launch on a second stream, so its CTAs move in as the first launch's retire.  Give
+ * page-locked host memory for `genomes` to get the overlap (pageable memory works, the copies then serialise).
+ * Arguments as for the four calls it replaces; fitness: [P], written before the call returns.  Results are identical
+ * to the separate calls. */
+int r2p2_evaluate(r2p2_handle h, const double* genomes, int32_t P, int32_t G, const double* x0, const double* y0, const double* theta0,
+                  int32_t n, double time_budget, int32_t T, double delta, double delta_ctrl, int32_t evolve, double* fitness);
 int r2p2_sync(r2p2_handle h);
 /* Device time of the most recent r2p2_run kernel in milliseconds (CUDA events on the handle's stream). */
 int r2p2_last_run_ms(r2p2_handle h, float* ms);

@@ -61,6 +61,8 @@ _SIGS = {
     "r2p2_set_genomes_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
     "r2p2_reset": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_double]),
     "r2p2_run": (C.c_int, [C.c_void_p, C.c_int32, C.c_double, C.c_double, C.c_int32]),
+    "r2p2_evaluate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_double,
+                                C.c_int32, C.c_double, C.c_double, C.c_int32, C.c_void_p]),
     "r2p2_sync": (C.c_int, [C.c_void_p]),
     "r2p2_last_run_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "r2p2_read_fitness": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -37,6 +37,10 @@ struct r2p2_sim {
     cudaStream_t own_stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool ev_valid = false;
+    bool timing_off = false;         // r2p2_evaluate brackets its chunk launches itself
+    cudaStream_t copy_stream = nullptr, aux_stream = nullptr;   // r2p2_evaluate: genome upload in two chunks; the second chunk's kernel
+    cudaEvent_t ev_chunk[2] = {nullptr, nullptr}, ev_idle = nullptr, ev_aux = nullptr;
+    int slot = 0;                    // launches go to (stream, d_work) [slot 0] or (aux_stream, d_work + 1) [slot 1]
     std::string err;
     int sm_count = 0;
     size_t smem_optin = 0;
@@ -313,13 +317,13 @@ int launch_kernel(r2p2_handle h, KERN kern, const KParams& kp, size_t smem, int*
     if (occ_out) { *occ_out = occ; return R2P2_OK; }
     if (occ < 1) return fail(h, R2P2_E_LIMIT, "episode kernel does not fit on an SM (smem %zu bytes)", smem);
     const int robots_per_cta = kp.block / LPR;
-    long long ctas = ((long long)kp.P + robots_per_cta - 1) / robots_per_cta;
-    ctas = std::min<long long>(ctas, (long long)occ * h->sm_count);   // persistent: the work counter feeds the rest
-    CK(cudaMemsetAsync(h->d_work, 0, sizeof(unsigned int), h->stream));
-    CK(cudaEventRecord(h->ev0, h->stream));
-    kern<<<(unsigned)ctas, kp.block, smem, h->stream>>>(kp);
-    CK(cudaEventRecord(h->ev1, h->stream));
-    h->ev_valid = true;
+    long long ctas = ((long long)(kp.rb_end - kp.rb_begin) + robots_per_cta - 1) / robots_per_cta;
+    ctas = std::max<long long>(1, std::min<long long>(ctas, (long long)occ * h->sm_count));   // persistent: the work counter feeds the rest
+    cudaStream_t st = h->slot ? h->aux_stream : h->stream;
+    CK(cudaMemsetAsync(kp.work_counter, 0, sizeof(unsigned int), st));
+    if (!h->timing_off) CK(cudaEventRecord(h->ev0, st));
+    kern<<<(unsigned)ctas, kp.block, smem, st>>>(kp);
+    if (!h->timing_off) { CK(cudaEventRecord(h->ev1, st)); h->ev_valid = true; }
     h->launches++;
     CK(cudaGetLastError());
     return R2P2_OK;
@@ -458,7 +462,7 @@ int choose_block(r2p2_handle h, const KParams& kp, int lpr, bool smem_stage) {
         plan_smem(k2, lpr, smem_stage);
         const size_t smem = episode_smem_bytes(block, lpr, smem_stage, k2.plane_bytes, k2.has50, k2.maxw, k2.w_in_smem, k2.G, k2.win_ww * k2.win_wb, k2.tanh_in_smem);
         if (smem > h->smem_optin || smem * (kMaxBlock / block) > (size_t)225 * 1024) continue;   // 16 warps per SM must fit
-        const long long ctas = ((long long)kp.P * lpr + block - 1) / block;
+        const long long ctas = ((long long)(kp.rb_end - kp.rb_begin) * lpr + block - 1) / block;
         const long long per_sm = std::min<long long>((ctas + h->sm_count - 1) / h->sm_count, kMaxBlock / block);
         const long long warps = per_sm * (block / 32);
         if (best_warps < 0 || warps < best_warps) { best_warps = warps; best = block; }
@@ -529,7 +533,7 @@ int r2p2_create(int device, r2p2_handle* out) {
     s->stream = s->own_stream;
     if (e == cudaSuccess) e = cudaEventCreate(&s->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&s->ev1);
-    if (e == cudaSuccess) e = cudaMalloc(&s->d_work, sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_work, 2 * sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaMalloc(&s->d_cnt3, 3 * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMalloc(&s->d_sincostab, R2P2_SINCOSTAB_LEN * sizeof(double));
     if (e == cudaSuccess) e = cudaMemcpy(s->d_sincostab, r2p2_h_sincostab, R2P2_SINCOSTAB_LEN * sizeof(double), cudaMemcpyHostToDevice);
@@ -556,6 +560,11 @@ int r2p2_destroy(r2p2_handle h) {
                     h->pid_ngoals, h->pid_gx, h->pid_gy};
     for (void* p : ptrs) cudaFree(p);
     free_trace(h);
+    for (cudaEvent_t e : h->ev_chunk) if (e) cudaEventDestroy(e);
+    if (h->ev_idle) cudaEventDestroy(h->ev_idle);
+    if (h->ev_aux) cudaEventDestroy(h->ev_aux);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -808,6 +817,7 @@ static int fill_params(r2p2_handle h, KParams& kp, int32_t T, double delta, doub
     kp.maxw = std::max(h->maxw, h->R);
     memcpy(kp.layers, h->layers, sizeof(int) * R2P2_MAX_LAYERS);
     kp.P = h->P; kp.T = T; kp.evolve = evolve ? 1 : 0;
+    kp.rb_begin = 0u; kp.rb_end = (uint32_t)h->P;
     kp.delta = delta; kp.delta_ctrl = delta_ctrl;
     kp.g_sincostab = h->d_sincostab; kp.g_crxy = h->d_crxy;
     {
@@ -824,7 +834,7 @@ static int fill_params(r2p2_handle h, KParams& kp, int32_t T, double delta, doub
     kp.noise_mode = h->noise_mode; kp.noise_len = h->noise_len; kp.noise_seed = h->noise_seed; kp.noise_stream = h->d_noise;
     kp.robot_index0 = h->robot_index0;
     if (h->noise_mode == 1 && h->noise_P != h->P) return fail(h, R2P2_E_ARG, "noise stream was uploaded for %d robots, population is %d", h->noise_P, h->P);
-    kp.work_counter = h->d_work;
+    kp.work_counter = h->d_work + h->slot;
     kp.genomes = h->d_genomes;
     kp.goal_on = h->goal_on; kp.goal_is_wall = h->goal_is_wall; kp.goal_x = h->goal_x; kp.goal_y = h->goal_y;
     kp.goal_r = h->radius * 1.85;                  // pid_controller.py:213
@@ -835,7 +845,7 @@ static int fill_params(r2p2_handle h, KParams& kp, int32_t T, double delta, doub
     return R2P2_OK;
 }
 
-int r2p2_run(r2p2_handle h, int32_t T, double delta, double delta_ctrl, int32_t evolve) {
+static int run_check(r2p2_handle h, int32_t T) {
     if (!h) return R2P2_E_ARG;
     if (!h->d_wall) return fail(h, R2P2_E_ARG, "r2p2_run: no stage (call r2p2_set_stage)");
     if (!h->have_robot) return fail(h, R2P2_E_ARG, "r2p2_run: no robot (call r2p2_set_robot)");
@@ -859,21 +869,33 @@ int r2p2_run(r2p2_handle h, int32_t T, double delta, double delta_ctrl, int32_t 
         return fail(h, R2P2_E_ARG, "constant-command genome must be [speed, angular_velocity]");
     }
     if (h->trace && (T > h->trace_T)) return fail(h, R2P2_E_ARG, "trace enabled for at most %d ticks per run", h->trace_T);
-    ON_DEVICE(h);
+    return R2P2_OK;
+}
 
+// One episode-kernel launch over robots [lo, hi) (the whole population for r2p2_run; a chunk of it for r2p2_evaluate,
+// whose later genomes are still on their way).  cap_out != NULL: no launch, only the number of robots resident at once.
+static int run_range(r2p2_handle h, int32_t T, double delta, double delta_ctrl, int32_t evolve, int lo, int hi, long long* cap_out) {
     KParams kp;
     int rc0 = fill_params(h, kp, T, delta, delta_ctrl, evolve);
     if (rc0) return rc0;
-
     if (h->lpr_epoch != h->cfg_epoch) { h->lpr_cached = choose_lpr(h, kp); h->lpr_epoch = h->cfg_epoch; }
     const int lpr = h->lpr_cached;
+    const bool smem_stage = h->smem_req == 1;   // default off: measured on B200, L1-cached global reads of the planes are as fast as the shared copy
+    if (cap_out) {
+        int occ = 0;
+        rc0 = dispatch_episode(h, kp, lpr, smem_stage, &occ);
+        if (rc0) return rc0;
+        *cap_out = (long long)std::max(occ, 1) * h->sm_count * (kp.block / lpr);
+        return R2P2_OK;
+    }
+    const bool whole = lo == 0 && hi == h->P;
     if (lpr == 1) {
-        if (!h->genomes_t_valid) {
-            dim3 grid((h->P + 31) / 32, (h->G + 31) / 32), block(32, 8);
-            transpose_genomes_kernel<<<grid, block, 0, h->stream>>>(h->d_genomes, h->d_genomes_t, h->P, h->G);
+        if (!whole || !h->genomes_t_valid) {
+            dim3 grid((hi - lo + 31) / 32, (h->G + 31) / 32), block(32, 8);
+            transpose_genomes_kernel<<<grid, block, 0, h->slot ? h->aux_stream : h->stream>>>(h->d_genomes, h->d_genomes_t, lo, hi, h->P, h->G);
             h->launches++;
             CK(cudaGetLastError());
-            h->genomes_t_valid = true;
+            if (whole) h->genomes_t_valid = true;
         }
         kp.genomes = h->d_genomes_t;
     } else {
@@ -882,24 +904,100 @@ int r2p2_run(r2p2_handle h, int32_t T, double delta, double delta_ctrl, int32_t 
 
     if (h->trace) {
         if (h->trace_P != h->P || h->trace_R != h->R) return fail(h, R2P2_E_ARG, "trace buffers were sized for another population; call r2p2_set_trace again");
-        const size_t rows = (size_t)T * h->P;
-        CK(cudaMemsetAsync(h->tr_pose, 0, rows * 5 * sizeof(double), h->stream));
-        CK(cudaMemsetAsync(h->tr_dst, 0, rows * h->R * sizeof(double), h->stream));
-        CK(cudaMemsetAsync(h->tr_hitk, 0xff, rows * h->R * sizeof(int32_t), h->stream));
-        CK(cudaMemsetAsync(h->tr_hitpx, 0xff, rows * h->R * 2 * sizeof(int32_t), h->stream));
-        CK(cudaMemsetAsync(h->tr_nsamp, 0, rows * h->R * sizeof(uint32_t), h->stream));
-        CK(cudaMemsetAsync(h->tr_ncoll, 0, rows * sizeof(uint32_t), h->stream));
-        CK(cudaMemsetAsync(h->tr_cinfo, 0, rows * 4 * sizeof(double), h->stream));
+        if (lo == 0) {
+            const size_t rows = (size_t)T * h->P;
+            CK(cudaMemsetAsync(h->tr_pose, 0, rows * 5 * sizeof(double), h->stream));
+            CK(cudaMemsetAsync(h->tr_dst, 0, rows * h->R * sizeof(double), h->stream));
+            CK(cudaMemsetAsync(h->tr_hitk, 0xff, rows * h->R * sizeof(int32_t), h->stream));
+            CK(cudaMemsetAsync(h->tr_hitpx, 0xff, rows * h->R * 2 * sizeof(int32_t), h->stream));
+            CK(cudaMemsetAsync(h->tr_nsamp, 0, rows * h->R * sizeof(uint32_t), h->stream));
+            CK(cudaMemsetAsync(h->tr_ncoll, 0, rows * sizeof(uint32_t), h->stream));
+            CK(cudaMemsetAsync(h->tr_cinfo, 0, rows * 4 * sizeof(double), h->stream));
+        }
         kp.tr_pose = h->tr_pose; kp.tr_dst = h->tr_dst; kp.tr_hitk = h->tr_hitk; kp.tr_hitpx = h->tr_hitpx;
         kp.tr_nsamp = h->tr_nsamp; kp.tr_ncoll = h->tr_ncoll; kp.tr_cinfo = h->tr_cinfo;
     }
 
-    bool smem_stage = h->smem_req == 1;   // default off: measured on B200, L1-cached global reads of the planes are as fast as the shared copy
     if (smem_stage) {
         const size_t with_stage = episode_smem_bytes(128, lpr, true, kp.plane_bytes, kp.has50, kp.maxw, w_in_smem_for(128, lpr, kp.G), kp.G);
         if (with_stage > h->smem_optin) return fail(h, R2P2_E_LIMIT, "stage planes (%zu bytes with tables) exceed shared memory", with_stage);
     }
+    kp.rb_begin = (uint32_t)lo; kp.rb_end = (uint32_t)hi;
     return dispatch_episode(h, kp, lpr, smem_stage, nullptr);
+}
+
+int r2p2_run(r2p2_handle h, int32_t T, double delta, double delta_ctrl, int32_t evolve) {
+    const int rc = run_check(h, T);
+    if (rc) return rc;
+    ON_DEVICE(h);
+    return run_range(h, T, delta, delta_ctrl, evolve, 0, h->P, nullptr);
+}
+
+/* evolution.evaluate_ann for a whole population (r2p2/evolution.py:29-52) as one call: upload, reset, run, read back.  When
+ * the population runs in three or more waves (a wave = as many robots as are resident at once) the genomes go up in two
+ * pieces on a copy stream: the first few waves' worth, then the rest while the episode kernel already runs the first
+ * piece.  The second piece gets its own launch on a second stream, so its CTAs move in as the first launch's CTAs retire
+ * (one stream would put a full drain between the two). */
+int r2p2_evaluate(r2p2_handle h, const double* genomes, int32_t P, int32_t G, const double* x0, const double* y0, const double* theta0,
+                  int32_t n, double time_budget, int32_t T, double delta, double delta_ctrl, int32_t evolve, double* fitness) {
+    if (!h) return R2P2_E_ARG;
+    if (!genomes || P < 1 || G < 1) return fail(h, R2P2_E_ARG, "genomes: need P >= 1, G >= 1");
+    if (!fitness) return fail(h, R2P2_E_ARG, "fitness is NULL");
+    ON_DEVICE(h);
+    int rc = ensure_genomes(h, P, G);
+    if (rc) return rc;
+    if (!h->copy_stream) {
+        CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
+        for (cudaEvent_t& e : h->ev_chunk) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->ev_idle, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->ev_aux, cudaEventDisableTiming));
+    }
+    h->have_genomes = true;
+    rc = r2p2_reset(h, x0, y0, theta0, n, time_budget);
+    if (rc) return rc;
+    rc = run_check(h, T);
+    if (rc) return rc;
+    long long cap = 0;
+    rc = run_range(h, T, delta, delta_ctrl, evolve, 0, P, &cap);
+    if (rc) return rc;
+    const long long waves = ((long long)P + cap - 1) / cap;
+    const bool split = waves >= 3 && (size_t)P * G * sizeof(double) >= ((size_t)8 << 20) && !h->trace;
+    const int cut = split ? (int)std::min<long long>(P, std::max<long long>(1, waves / 8) * cap) : P;
+    // earlier launches on the compute stream may still read the genome buffer; the reset must be done before either launch
+    CK(cudaEventRecord(h->ev_idle, h->stream));
+    CK(cudaStreamWaitEvent(h->copy_stream, h->ev_idle, 0));
+    CK(cudaMemcpyAsync(h->d_genomes, genomes, (size_t)cut * G * sizeof(double), cudaMemcpyHostToDevice, h->copy_stream));
+    CK(cudaEventRecord(h->ev_chunk[0], h->copy_stream));
+    if (split) {
+        CK(cudaMemcpyAsync(h->d_genomes + (size_t)cut * G, genomes + (size_t)cut * G, (size_t)(P - cut) * G * sizeof(double), cudaMemcpyHostToDevice, h->copy_stream));
+        CK(cudaEventRecord(h->ev_chunk[1], h->copy_stream));
+    }
+    h->genomes_t_valid = false;
+    h->timing_off = true;
+    cudaError_t e = cudaStreamWaitEvent(h->stream, h->ev_chunk[0], 0);
+    if (e == cudaSuccess) e = cudaEventRecord(h->ev0, h->stream);
+    if (e == cudaSuccess) rc = run_range(h, T, delta, delta_ctrl, evolve, 0, cut, nullptr);
+    if (e == cudaSuccess && rc == R2P2_OK && split) {
+        e = cudaStreamWaitEvent(h->aux_stream, h->ev_idle, 0);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(h->aux_stream, h->ev_chunk[1], 0);
+        if (e == cudaSuccess) {
+            h->slot = 1;
+            rc = run_range(h, T, delta, delta_ctrl, evolve, cut, P, nullptr);
+            h->slot = 0;
+        }
+        if (e == cudaSuccess) e = cudaEventRecord(h->ev_aux, h->aux_stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(h->stream, h->ev_aux, 0);
+    }
+    h->timing_off = false;
+    if (e != cudaSuccess) rc = fail(h, R2P2_E_CUDA, "r2p2_evaluate: %s", cudaGetErrorString(e));
+    if (rc) { cudaStreamSynchronize(h->copy_stream); cudaStreamSynchronize(h->aux_stream); cudaStreamSynchronize(h->stream); return rc; }
+    CK(cudaEventRecord(h->ev1, h->stream));
+    h->ev_valid = true;
+    h->genomes_t_valid = (h->lpr_cached == 1);
+    CK(cudaMemcpyAsync(fitness, h->st.fitness, (size_t)P * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return R2P2_OK;
 }
 
 /* ---- path planner's cost grid ---- */

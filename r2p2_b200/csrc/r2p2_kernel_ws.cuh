@@ -126,12 +126,12 @@ __global__ void __launch_bounds__((NET::kLayers > 0 && !NET::kSmemWeights) ? kRe
     for (;;) {
         // ---- the warp fetches its next 32/LPR robots ---------------------------------------------------
         unsigned base = 0;
-        if (lane == 0) base = atomicAdd(p.work_counter, (unsigned)RPW);
+        if (lane == 0) base = atomicAdd(p.work_counter, (unsigned)RPW) + p.rb_begin;
         base = __shfl_sync(FULL, base, 0);
-        if (base >= (unsigned)p.P) break;
+        if (base >= p.rb_end) break;
         const unsigned rb_raw = base + lane / LPR;
-        const bool valid = rb_raw < (unsigned)p.P;
-        const unsigned rb = valid ? rb_raw : (unsigned)p.P - 1u;          // lanes without a robot read a valid one, commit nothing
+        const bool valid = rb_raw < p.rb_end;
+        const unsigned rb = valid ? rb_raw : p.rb_end - 1u;              // lanes without a robot read a valid one, commit nothing
 
         double x = p.x[rb], y = p.y[rb], theta = p.theta[rb], speed = p.speed[rb], omega = p.omega[rb];
         double last_x = p.last_x[rb], last_y = p.last_y[rb];

@@ -112,6 +112,8 @@ struct KParams {
     // scheduling
     unsigned int* work_counter;
     int32_t block;                     // threads per CTA of this launch (host side; the kernels read blockDim.x)
+    uint32_t rb_begin, rb_end;         // robots [rb_begin, rb_end) are this launch's work (the whole population, or one chunk of a
+                                       // pipelined evaluation whose later genomes are still being uploaded)
 };
 
 struct StageView {
@@ -1226,9 +1228,9 @@ __global__ void __launch_bounds__((NET::kLayers > 0 && !NET::kSmemWeights) ? kRe
     for (;;) {
         // ---- fetch the next robot --------------------------------------------------------------
         unsigned rb = 0;
-        if (g.sub == 0) rb = atomicAdd(p.work_counter, 1u);
+        if (g.sub == 0) rb = atomicAdd(p.work_counter, 1u) + p.rb_begin;
         rb = g.bcast_u(rb);
-        if (rb >= (unsigned)p.P) break;
+        if (rb >= p.rb_end) break;
 
         double x = p.x[rb], y = p.y[rb], theta = p.theta[rb], speed = p.speed[rb], omega = p.omega[rb];
         double last_x = p.last_x[rb], last_y = p.last_y[rb];
@@ -1678,10 +1680,11 @@ __global__ void i32_to_u8_kernel(const int32_t* __restrict__ in, uint8_t* __rest
     out[i] = (uint8_t)v;
 }
 
-// [P][G] -> [G][P]
-__global__ void transpose_genomes_kernel(const double* __restrict__ in, double* __restrict__ out, int P, int G) {
+// [P][G] -> [G][P], rows lo .. P-1 of `in` (lo a multiple of 32 or 0; P = the end of the range and the stride of `out`'s rows
+// is P_total)
+__global__ void transpose_genomes_kernel(const double* __restrict__ in, double* __restrict__ out, int lo, int P, int P_total, int G) {
     __shared__ double tile[32][33];
-    const int p0 = blockIdx.x * 32, g0 = blockIdx.y * 32;
+    const int p0 = lo + blockIdx.x * 32, g0 = blockIdx.y * 32;
     for (int r = threadIdx.y; r < 32; r += blockDim.y) {
         const int pp = p0 + r, gg = g0 + threadIdx.x;
         if (pp < P && gg < G) tile[r][threadIdx.x] = in[(size_t)pp * G + gg];
@@ -1689,7 +1692,7 @@ __global__ void transpose_genomes_kernel(const double* __restrict__ in, double* 
     __syncthreads();
     for (int r = threadIdx.y; r < 32; r += blockDim.y) {
         const int gg = g0 + r, pp = p0 + threadIdx.x;
-        if (pp < P && gg < G) out[(size_t)gg * P + pp] = tile[threadIdx.x][r];
+        if (pp < P && gg < G) out[(size_t)gg * P_total + pp] = tile[threadIdx.x][r];
     }
 }
 

@@ -36,18 +36,20 @@ class PopulationEvaluator:
     # -- whole evaluation from host memory (the e2e path) --
     def evaluate(self, genomes, out=None):
         g = np.ascontiguousarray(genomes, dtype=np.float64)
-        self.sim.upload_genomes(g)
-        self.sim.reset(self.x0, self.y0, self.th0, self.time_budget)
-        self.sim.run(self.ticks, self.delta, self.delta_ctrl, self.evolve)
-        return self.sim.fitness(out)
+        if g.ndim != 2:
+            raise ValueError("genomes must be [P, G]")
+        f = np.empty(g.shape[0]) if out is None else out
+        if f.size < g.shape[0] or f.dtype != np.float64 or not f.flags["C_CONTIGUOUS"]:
+            raise ValueError("fitness buffer must be a contiguous float64 array of at least %d elements" % g.shape[0])
+        self.evaluate_ptr(g.ctypes.data, g.shape[0], g.shape[1], f.ctypes.data)
+        return f
 
     # -- pieces, for callers that keep genomes on the device or use pinned buffers --
     def evaluate_ptr(self, genomes_host_ptr, P, G, fitness_host_ptr):
-        """Same as evaluate() with raw host pointers (e.g. pinned torch tensors): no numpy temporaries."""
-        self.sim.upload_genomes_ptr(genomes_host_ptr, P, G)
-        self.sim.reset(self.x0, self.y0, self.th0, self.time_budget)
-        self.sim.run(self.ticks, self.delta, self.delta_ctrl, self.evolve)
-        self.sim.read_fitness_ptr(fitness_host_ptr)
+        """Same as evaluate() with raw host pointers (e.g. pinned torch tensors): no numpy temporaries.  One library call
+        (r2p2_evaluate): the genome upload is pipelined against the episode kernel chunk by chunk."""
+        self.sim.evaluate_ptr(genomes_host_ptr, P, G, self.x0, self.y0, self.th0, self.time_budget, self.ticks, self.delta,
+                              self.delta_ctrl, self.evolve, fitness_host_ptr)
 
     def launch_resident(self):
         """Reset + run with the genomes already on the device (asynchronous)."""

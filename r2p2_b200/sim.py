@@ -188,6 +188,17 @@ class BatchSim:
     def run(self, T, delta=0.1, delta_ctrl=None, evolve=False):
         self._ck(self._L.r2p2_run(self._h, int(T), float(delta), float(delta if delta_ctrl is None else delta_ctrl), int(bool(evolve))))
 
+    def evaluate_ptr(self, genomes_host_ptr, P, G, x0, y0, theta0, time_budget, T, delta, delta_ctrl, evolve, fitness_host_ptr):
+        """upload + reset + run + read fitness as one call with the genome upload pipelined against the kernel
+        (r2p2_evaluate); raw host pointers, page-locked for the overlap."""
+        x0, y0, t0 = np.atleast_1d(_f64(x0)), np.atleast_1d(_f64(y0)), np.atleast_1d(_f64(theta0))
+        n = max(len(x0), len(y0), len(t0))
+        if n > 1:
+            x0, y0, t0 = (_f64(np.broadcast_to(a, (n,))) for a in (x0, y0, t0))
+        self._ck(self._L.r2p2_evaluate(self._h, C.c_void_p(int(genomes_host_ptr)), int(P), int(G), x0.ctypes.data, y0.ctypes.data, t0.ctypes.data,
+                                       n, float(time_budget), int(T), float(delta), float(delta_ctrl), int(bool(evolve)),
+                                       C.c_void_p(int(fitness_host_ptr))))
+
     def sync(self):
         self._ck(self._L.r2p2_sync(self._h))
 

@@ -199,3 +199,53 @@ def test_current_device_is_left_alone():
     assert rt.cudaGetDevice(C.byref(cur)) == 0 and cur.value == 0
     sim.close()
     assert rt.cudaGetDevice(C.byref(cur)) == 0 and cur.value == 0
+
+
+def test_evaluate_call_equals_the_four_calls_and_pipelines_the_upload():
+    """r2p2_evaluate (upload + reset + run + read; populations of three or more waves go up in two pieces, the second one
+    while the first already runs, each with its own launch) against the separate calls: identical fitness, state and
+    counters -- the 8-lane window kernel (config E's shape, 5 waves) and the one-lane kernel with its piece-wise
+    transposition (250 000 linear robots, 4 waves), from pinned and pageable memory."""
+    import torch
+    import bench
+    import r2p2_b200
+    from r2p2_b200.evaluator import PopulationEvaluator
+    cases = []
+    w = bench.WORKLOADS["E"]
+    rob = bench.ROBOTS[w["robot"]]
+    P = 40000
+    cases.append((bench.synthetic_stage(), rob, "neuro", w["hidden"], bench.slice_poses(bench.start_poses(w, P), 0, P), bench.make_genomes(w, 11, 0, P), 30, 2))
+    w1 = bench.WORKLOADS["C1"]
+    rob1 = bench.ROBOTS[w1["robot"]]
+    P1 = 250000
+    g1 = np.random.RandomState(3).uniform(-1, 1, (P1, 18)) * 0.05
+    cases.append((bench.load_stage(w1["stage"]), rob1, "linear", None, (float(rob1["x"]), float(rob1["y"]), np.random.RandomState(4).uniform(0, 360, P1)), g1, 40, 2))
+    for stage, rb, ctrl, hidden, (px, py, pt), genomes, T, min_launches in cases:
+        P, G = genomes.shape
+        ev = PopulationEvaluator(stage, sonar_range=rb["sonar_range"], radius=rb["radius"], max_speed=rb["max_speed"], sonars=rb["sonars"],
+                                 controller=ctrl, hidden_layer=hidden, x=px, y=py, orientation=pt, ticks=T)
+        sim = ev.sim
+        sim.upload_genomes(genomes)
+        sim.reset(px, py, pt)
+        sim.run(T)
+        ref = (sim.fitness().copy(), sim.state(), sim.counters())
+        # pinned host buffers (the overlap case)
+        gp = torch.from_numpy(genomes).pin_memory()
+        fp = torch.empty(P, dtype=torch.float64).pin_memory()
+        n0 = sim.launch_count()
+        ev.evaluate_ptr(gp.data_ptr(), P, G, fp.data_ptr())
+        launches = sim.launch_count() - n0
+        assert launches >= 1 + min_launches, launches            # reset + one episode launch per chunk (+ transpositions)
+        assert np.array_equal(fp.numpy(), ref[0])
+        st, c = sim.state(), sim.counters()
+        for k in st:
+            assert np.array_equal(st[k], ref[1][k]), k
+        assert c == ref[2]
+        # pageable numpy memory, and a second evaluation of other genomes on the same handle
+        g2 = genomes[::-1].copy()
+        f2 = ev.evaluate(g2)
+        assert f2.shape == (P,)                               # (start poses are per robot: only the next evaluation is comparable)
+        f3 = ev.evaluate(genomes)
+        assert np.array_equal(f3, ref[0])
+        assert sim.last_run_ms() > 0
+        ev.close()
