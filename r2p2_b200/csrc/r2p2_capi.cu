@@ -67,7 +67,7 @@ struct r2p2_sim {
     // population
     int P = 0, G = 0;
     double* d_genomes = nullptr;     // [P][G]
-    double* d_genomes_t = nullptr;   // [G][P], built lazily for the 1-lane mapping
+    double* d_genomes_t = nullptr;   // [ceil(P/32)][G][32] (see transpose_genomes_kernel), built lazily for the 1-lane mapping
     size_t genomes_cap = 0;
     bool genomes_t_valid = false;
     bool have_genomes = false, have_reset = false;
@@ -189,7 +189,7 @@ int ensure_state(r2p2_handle h, int P) {
 }
 
 int ensure_genomes(r2p2_handle h, int P, int G) {
-    const size_t need = (size_t)P * (size_t)G;
+    const size_t need = (size_t)((P + 31) / 32 * 32) * (size_t)G;      // whole tiles of 32 robots for the one-lane copy
     if (need > h->genomes_cap) {
         CK(dalloc(&h->d_genomes, need));
         CK(dalloc(&h->d_genomes_t, need));
@@ -356,7 +356,7 @@ void window_geometry(KParams& kp, int lpr) {
     const int slack = slack_env > 0 ? slack_env : 8;       // a fetched window is kept until the robot has moved this far
     const int ww = (((2 * (half + slack) + 32 + 7) / 8) + 3) / 4 * 4, wb = (2 * (half + slack) + 4 + 3) / 4;
     if (half + slack + 96 > kp.hpad) return;                                             // the window must stay inside the plane's margin
-    if ((size_t)(kp.block / lpr) * ww * wb * 4 > (size_t)64 * 1024 * (kp.block / 128)) return;                 // too fat: the per-group kernel reads the plane through L1
+    if ((size_t)(kp.block / lpr) * ww * wb * 4 * 128 > (size_t)64 * 1024 * kp.block) return;                 // too fat: the per-group kernel reads the plane through L1
     kp.win_ww = ww; kp.win_wb = wb; kp.win_half = half; kp.win_slack = slack;
 }
 
@@ -427,13 +427,13 @@ int launch_episode_s(r2p2_handle h, KParams& kp, bool smem_stage, int* occ_out) 
 int w_in_smem_for(int block, int lpr, int G) {
     // R2P2_WSMEM_KB (experiments): largest genome block a CTA may hold in shared memory; two CTAs per SM must still fit
     static const size_t lim = [] { const char* e = getenv("R2P2_WSMEM_KB"); return (size_t)(e ? atoi(e) : 48) * 1024; }();
-    return (lpr > 1 && (size_t)(block / lpr) * G * 8 <= lim * (block / 128)) ? 1 : 0;
+    return (lpr > 1 && (size_t)(block / lpr) * G * 8 * 128 <= lim * block) ? 1 : 0;
 }
 
 // Shared-memory plan of one launch for a given CTA size: windows first, then the genomes of the robots in flight, then
 // the tanh table -- each only while 16 warps per SM (512 / block CTAs of the 128-register instances) still fit.
 void plan_smem(KParams& kp, int lpr, bool smem_stage) {
-    const size_t per_cta = (size_t)55 * 1024 * (kp.block / 128);
+    const size_t per_cta = (size_t)55 * 1024 * kp.block / 128;
     kp.w_in_smem = w_in_smem_for(kp.block, lpr, kp.G);
     window_geometry(kp, lpr);
     if (kp.w_in_smem && kp.win_ww && episode_smem_bytes(kp.block, lpr, false, kp.plane_bytes, kp.has50, kp.maxw, 1, kp.G, kp.win_ww * kp.win_wb) > per_cta)
@@ -449,24 +449,35 @@ void plan_smem(KParams& kp, int lpr, bool smem_stage) {
 // choice is about (a) how the population spreads over the SMs -- the run lasts as long as its fullest SM, so the split
 // with the fewest warps on the fullest SM wins -- and (b) at equal spread, the largest CTA: its tables are staged once
 // per SM and the shared memory that saves is L1 for the genomes (R2P2_BLOCK in the environment forces a size).
+// A population that is resident all at once is a static partition (every robot runs its T ticks on the SM it landed on):
+// 65,536 one-lane robots are 2,048 warps = 13.8 per SM, and 128 CTAs of 512 threads would leave 20 SMs idle with 16 warps
+// on each of the others.  One CTA per SM of 32 * ceil(warps / SMs) threads (here 448: 14 warps on 147 SMs) spreads them
+// evenly and still stages the tables once per SM.
 int choose_block(r2p2_handle h, const KParams& kp, int lpr, bool smem_stage) {
     const bool regw = lpr >= 16 && !smem_stage && (net_matches<NetNeuro>(kp) || net_matches<NetSimple>(kp));
     if (regw) return kRegBlock;
-    static const int forced = [] { const char* e = getenv("R2P2_BLOCK"); const int v = e ? atoi(e) : 0; return (v == 128 || v == 256 || v == 512) ? v : 0; }();
+    static const int forced = [] { const char* e = getenv("R2P2_BLOCK"); const int v = e ? atoi(e) : 0; return (v >= 128 && v <= 512 && v % 32 == 0) ? v : 0; }();
     if (forced) return forced;
     int best = 128;
     long long best_warps = -1;
-    for (int block = kMaxBlock; block >= 128; block >>= 1) {
+    auto smem_of = [&](int block) {
         KParams k2 = kp;
         k2.block = block;
         plan_smem(k2, lpr, smem_stage);
-        const size_t smem = episode_smem_bytes(block, lpr, smem_stage, k2.plane_bytes, k2.has50, k2.maxw, k2.w_in_smem, k2.G, k2.win_ww * k2.win_wb, k2.tanh_in_smem);
+        return episode_smem_bytes(block, lpr, smem_stage, k2.plane_bytes, k2.has50, k2.maxw, k2.w_in_smem, k2.G, k2.win_ww * k2.win_wb, k2.tanh_in_smem);
+    };
+    for (int block = kMaxBlock; block >= 128; block >>= 1) {
+        const size_t smem = smem_of(block);
         if (smem > h->smem_optin || smem * (kMaxBlock / block) > (size_t)225 * 1024) continue;   // 16 warps per SM must fit
         const long long ctas = ((long long)(kp.rb_end - kp.rb_begin) * lpr + block - 1) / block;
         const long long per_sm = std::min<long long>((ctas + h->sm_count - 1) / h->sm_count, kMaxBlock / block);
         const long long warps = per_sm * (block / 32);
         if (best_warps < 0 || warps < best_warps) { best_warps = warps; best = block; }
     }
+    static const bool no_bal = [] { const char* e = getenv("R2P2_NO_BALANCE"); return e && e[0] == '1'; }();   // A/B measurements
+    const long long total_warps = ((long long)(kp.rb_end - kp.rb_begin) * lpr + 31) / 32;
+    const long long bal = 32 * ((total_warps + h->sm_count - 1) / h->sm_count);        // one CTA per SM, everything resident
+    if (!no_bal && bal >= 128 && bal < kMaxBlock && (best_warps < 0 || bal / 32 < best_warps) && smem_of((int)bal) <= h->smem_optin) best = (int)bal;
     return best;
 }
 
@@ -892,7 +903,7 @@ static int run_range(r2p2_handle h, int32_t T, double delta, double delta_ctrl, 
     if (lpr == 1) {
         if (!whole || !h->genomes_t_valid) {
             dim3 grid((hi - lo + 31) / 32, (h->G + 31) / 32), block(32, 8);
-            transpose_genomes_kernel<<<grid, block, 0, h->slot ? h->aux_stream : h->stream>>>(h->d_genomes, h->d_genomes_t, lo, hi, h->P, h->G);
+            transpose_genomes_kernel<<<grid, block, 0, h->slot ? h->aux_stream : h->stream>>>(h->d_genomes, h->d_genomes_t, lo, hi, h->G);
             h->launches++;
             CK(cudaGetLastError());
             if (whole) h->genomes_t_valid = true;

@@ -79,7 +79,7 @@ __global__ void __launch_bounds__((NET::kLayers > 0 && !NET::kSmemWeights) ? kRe
     double* s_gen = s_bufB + (size_t)p.maxw * NR;         // [NR][G], only when p.w_in_smem
     // per-robot windows of the hot plane (see below)
     const int win_words = p.win_ww * p.win_wb;
-    uint32_t* s_win = reinterpret_cast<uint32_t*>(s_gen + (p.w_in_smem ? (size_t)NR * p.G : 0));
+    uint32_t* s_win = reinterpret_cast<uint32_t*>(s_gen + (p.w_in_smem ? (size_t)NR * smem_gstride(LPR, p.G) : 0));
 
     const uint32_t mb = smem_u32(mbar);
     if (threadIdx.x == 0) {
@@ -148,7 +148,7 @@ __global__ void __launch_bounds__((NET::kLayers > 0 && !NET::kSmemWeights) ? kRe
         if constexpr (NET::kLayers > 0 && !NET::kSmemWeights) {
             mlp.load(gen, g.sub);
         } else if (p.w_in_smem) {
-            double* dst_g = s_gen + (size_t)slot * p.G;
+            double* dst_g = s_gen + (size_t)slot * smem_gstride(LPR, p.G);
             for (int i = g.sub; i < p.G; i += LPR) dst_g[i] = __ldg(gen + i);
             __syncwarp();
             gen = dst_g;

@@ -78,7 +78,7 @@ struct KParams {
     int32_t tanh_in_smem;              // the tanh table (18 KB) is staged in shared memory next to the sin/cos table
     const double* g_tanhtab;           // its global copy
     int32_t layers[R2P2_MAX_LAYERS];
-    const double* genomes;             // [P][G] (LPR > 1) or [G][P] (LPR == 1)
+    const double* genomes;             // [P][G] (LPR > 1) or tiles [ceil(P/32)][G][32] (LPR == 1, see transpose_genomes_kernel)
     // run
     int32_t P, T, evolve;
     double delta, delta_ctrl;
@@ -151,6 +151,10 @@ __host__ __device__ __forceinline__ int hot_word(int ix, int iy, int hwpr) { ret
 __host__ __device__ __forceinline__ int hot_shift(int ix, int iy) { return ix + 8 * iy; }
 // floor(v) for |v| < 2^31 (negative values too) from the low word of RD(v + 1.5 * 2^52); no validity check
 __device__ __forceinline__ int floor_lo(double v) { return __double2loint(__dadd_rd(v, 6755399441055744.0)); }
+
+// one-lane genome tiles (see transpose_genomes_kernel)
+__host__ __device__ __forceinline__ size_t tiled_base(unsigned rb, int G) { return (size_t)(rb >> 5) * (size_t)G * 32u + (rb & 31u); }
+constexpr int kTileStride = 32;       // doubles between consecutive genes of one robot
 
 // ---------------------------------------------------------------------------------------------
 // TMA (1-D bulk copy) + mbarrier helpers
@@ -916,15 +920,21 @@ __device__ __forceinline__ bool pid_control(const KParams& p, const StageView& s
 //   [.., +plane_bytes)             wall plane      (SMEM_STAGE only)
 //   [.., +plane_bytes)             level-50 plane  (SMEM_STAGE and has50 only)
 //   [.., +2*maxw*NR*8)             MLP / sonar buffers A and B, element i of robot slot r at [i*NR + r]; NR = blockDim.x / LPR
-//   [.., +NR*G*8)                  genomes of the robots in flight (w_in_smem only), row r at [r*G]
+//   [.., +NR*GS*8)                 genomes of the robots in flight (w_in_smem only), row r at [r*GS], GS = smem_gstride(LPR, G)
 //   [.., +NR*win_words*4)          per-robot windows of the hot plane (warp-synchronous kernel)
+// Row stride (doubles) of the genome copies in shared memory.  The groups of a warp read the same weight columns of
+// different robots in one instruction (LPR consecutive doubles each); with a stride that is a multiple of 16 doubles all
+// of them would hit the same banks (config E: G = 656 -> 4-way conflicts on every weight load).  A stride congruent to
+// LPR modulo 16 spreads the 32 / LPR groups evenly over the 32 banks.
+__host__ __device__ inline int smem_gstride(int lpr, int G) { return G + ((lpr - G) % 16 + 16) % 16; }
+
 __host__ __device__ inline size_t episode_smem_bytes(int block, int lpr, bool smem_stage, uint32_t plane_bytes, int has50, int maxw, int w_in_smem, int G,
                                                      int win_words = 0, int tanh_in_smem = 0) {
     size_t n = 16 + R2P2_SINCOSTAB_LEN * 8 + 720 * 8;
     if (tanh_in_smem) n += (size_t)R2P2_TANH_NINT * R2P2_TANH_ROW * 8;
     if (smem_stage) n += (size_t)plane_bytes * (has50 ? 2 : 1);
     n += (size_t)2 * maxw * (block / lpr) * 8;
-    if (w_in_smem) n += (size_t)(block / lpr) * G * 8;
+    if (w_in_smem) n += (size_t)(block / lpr) * smem_gstride(lpr, G) * 8;
     if (win_words) n += (size_t)(block / lpr) * (size_t)win_words * 4;
     return n;
 }
@@ -1043,9 +1053,9 @@ struct FixedMlp {
         out1 = (LPR == 1) ? h[1] : __shfl_sync(mask, h[(1 / LPR)], 1 % LPR, LPR);
     }
     // One lane per robot: the whole net in this thread.  Activations stay in registers, every loop is unrolled, and
-    // the weights stream from the transposed genome array (wt = genomes_t + robot, element q at wt[q * P]: one
-    // coalesced line per warp and weight).  Same ordered FMA chains as everywhere else.
-    __device__ __forceinline__ void forward_global(const double* __restrict__ wt, size_t P, double (&h)[kSlots], int activation, const double* tanhtab,
+    // the weights stream from the robot's tile of the genome array (element q at wt[q * 32]: one coalesced line per warp
+    // and weight).  Same ordered FMA chains as everywhere else.
+    __device__ __forceinline__ void forward_global(const double* __restrict__ wt, double (&h)[kSlots], int activation, const double* tanhtab,
                                                    double& out0, double& out1) const {
 #pragma unroll
         for (int l = 0; l + 1 < NET::kLayers; ++l) {
@@ -1055,7 +1065,7 @@ struct FixedMlp {
                 double acc = 0.0;
 #pragma unroll
                 for (int i = 0; i < NET::sz(l); ++i)
-                    acc = R2P2_FMA(h[i], __ldg(wt + (size_t)(NET::woff(l) + i * NET::sz(l + 1) + j) * P), acc);
+                    acc = R2P2_FMA(h[i], __ldg(wt + (NET::woff(l) + i * NET::sz(l + 1) + j) * kTileStride), acc);
                 hn[j] = (l + 2 < NET::kLayers) ? activate(activation, acc, tanhtab) : acc;
             }
 #pragma unroll
@@ -1066,24 +1076,23 @@ struct FixedMlp {
     }
 };
 // One lane per robot, compile-time shape: activations in shared memory (stride NR), weights from the transposed genome
-// array (wt[q * P]: weight q of the warp's 32 robots is one coalesced 256-byte read); one activation instance per layer.
+// tiles (wt[q * 32]: weight q of the warp's 32 robots is one coalesced 256-byte read); one activation instance per layer.
 template <class NET, int L>
-__device__ __forceinline__ void lane_layer(const double* __restrict__ wt, size_t P, const double* hin, double* hout, int NR, int activation, const double* tanhtab) {
+__device__ __forceinline__ void lane_layer(const double* __restrict__ wt, const double* hin, double* hout, int NR, int activation, const double* tanhtab) {
     constexpr int nin = NET::sz(L), nout = NET::sz(L + 1);
     constexpr bool last = (L + 2 == NET::kLayers);
-    // Input-major: row i of the layer (W[i][0 .. nout-1] = nout consecutive rows of the transposed genome array, one
-    // running pointer) feeds all nout neurons at once.  Every neuron keeps the reference's ordered chain
+    // Input-major: row i of the layer (W[i][0 .. nout-1] = nout consecutive genes of the robot, compile-time offsets from
+    // its tile pointer) feeds all nout neurons at once.  Every neuron keeps the reference's ordered chain
     // acc_j = fma(h_i, w_ij, acc_j), i ascending, but the nout chains are independent: the FMA latency and the L2 latency
     // of the next row's loads overlap instead of being paid once per neuron.
     double acc[nout];
 #pragma unroll
     for (int j = 0; j < nout; ++j) acc[j] = 0.0;
-    const double* wp = wt + (size_t)NET::woff(L) * P;
 #pragma unroll
     for (int i = 0; i < nin; ++i) {
         double wv[nout];
 #pragma unroll
-        for (int j = 0; j < nout; ++j) { wv[j] = __ldcg(wp); wp += P; }   // L2 only: the stream of weight rows must not evict the hot plane from L1
+        for (int j = 0; j < nout; ++j) wv[j] = __ldcg(wt + (NET::woff(L) + i * nout + j) * 32);   // L2 only: the stream of weight rows must not evict the hot plane from L1
         const double hi = hin[i * NR];
 #pragma unroll
         for (int j = 0; j < nout; ++j) acc[j] = R2P2_FMA(hi, wv[j], acc[j]);
@@ -1096,13 +1105,13 @@ __device__ __forceinline__ void lane_layer(const double* __restrict__ wt, size_t
     }
 }
 template <class NET>
-__device__ __forceinline__ void lane_mlp(const double* __restrict__ wt, size_t P, double* a, double* b, int NR, int activation, const double* tanhtab,
+__device__ __forceinline__ void lane_mlp(const double* __restrict__ wt, double* a, double* b, int NR, int activation, const double* tanhtab,
                                          double& out0, double& out1) {
-    lane_layer<NET, 0>(wt, P, a, b, NR, activation, tanhtab);
+    lane_layer<NET, 0>(wt, a, b, NR, activation, tanhtab);
     double* res = b;
-    if constexpr (NET::kLayers > 2) { lane_layer<NET, 1>(wt, P, b, a, NR, activation, tanhtab); res = a; }
-    if constexpr (NET::kLayers > 3) { lane_layer<NET, 2>(wt, P, a, b, NR, activation, tanhtab); res = b; }
-    if constexpr (NET::kLayers > 4) { lane_layer<NET, 3>(wt, P, b, a, NR, activation, tanhtab); res = a; }
+    if constexpr (NET::kLayers > 2) { lane_layer<NET, 1>(wt, b, a, NR, activation, tanhtab); res = a; }
+    if constexpr (NET::kLayers > 3) { lane_layer<NET, 2>(wt, a, b, NR, activation, tanhtab); res = b; }
+    if constexpr (NET::kLayers > 4) { lane_layer<NET, 3>(wt, b, a, NR, activation, tanhtab); res = a; }
     out0 = res[0];
     out1 = res[NR];
 }
@@ -1242,12 +1251,12 @@ __global__ void __launch_bounds__((NET::kLayers > 0 && !NET::kSmemWeights) ? kRe
         unsigned ndraws = p.noise_mode ? p.ndraws[rb] : 0u;
         unsigned my_ns_sonar = 0u, ns_coll = 0u;          // my_ns_sonar: this lane's rays only
         // the genome is read every tick for T ticks: keep it next to the SM
-        const double* gen = p.genomes + (size_t)rb * (size_t)p.G;
+        const double* gen = (LPR == 1) ? p.genomes + tiled_base(rb, p.G) : p.genomes + (size_t)rb * (size_t)p.G;   // one lane: the robot's column of its tile
         FixedMlp<LPR, NET> mlp;
         if constexpr (NET::kLayers > 0 && !NET::kSmemWeights) {
             if constexpr (LPR > 1) mlp.load(gen, g.sub);
         } else if (LPR > 1 && p.w_in_smem) {
-            double* dst_g = s_gen + (size_t)slot * p.G;
+            double* dst_g = s_gen + (size_t)slot * smem_gstride(LPR, p.G);
             for (int i = g.sub; i < p.G; i += LPR) dst_g[i] = __ldg(gen + i);
             g.sync();
             gen = dst_g;
@@ -1354,7 +1363,7 @@ __global__ void __launch_bounds__((NET::kLayers > 0 && !NET::kSmemWeights) ? kRe
             if constexpr (NET::kSmemWeights) {            // one lane per robot, compile-time shape (capi dispatches it for LPR == 1 only)
 #pragma unroll
                 for (int i = 0; i < NET::sz(0); ++i) bufA[i * NR] = R2P2_DIV(p.vr1, bufA[i * NR]);   // 25/dst (inf when dst == 0)
-                lane_mlp<NET>(p.genomes + rb, (size_t)p.P, bufA, bufB, NR, p.activation, s_tanh, v, w);
+                lane_mlp<NET>(gen, bufA, bufB, NR, p.activation, s_tanh, v, w);
                 if (v > 180.0) v = R2P2_SUB(v, 360.0);
             } else if constexpr (NET::kLayers > 0) {
                 double h[FixedMlp<LPR, NET>::kSlots];
@@ -1364,7 +1373,7 @@ __global__ void __launch_bounds__((NET::kLayers > 0 && !NET::kSmemWeights) ? kRe
                     h[s] = (i < NET::sz(0)) ? R2P2_DIV(p.vr1, bufA[i * NR]) : 0.0;                     // 25/dst (inf when dst == 0)
                 }
                 if constexpr (LPR > 1) mlp.forward(g.mask, g.sub, h, p.activation, s_tanh, v, w);
-                else mlp.forward_global(p.genomes + rb, (size_t)p.P, h, p.activation, s_tanh, v, w);
+                else mlp.forward_global(gen, h, p.activation, s_tanh, v, w);
                 if (v > 180.0) v = R2P2_SUB(v, 360.0);
                 g.sync();                                  // bufA is rewritten by the next tick's sense
             } else if (p.ctrl_kind == R2P2_CTRL_NEURO) {
@@ -1379,8 +1388,8 @@ __global__ void __launch_bounds__((NET::kLayers > 0 && !NET::kSmemWeights) ? kRe
                     for (int j = g.sub; j < nout; j += LPR) {
                         double acc = 0.0;
                         if (LPR == 1) {
-                            const double* wp = p.genomes + (size_t)(woff + j) * (size_t)p.P + rb;
-                            for (int i = 0; i < nin; ++i) acc = R2P2_FMA(hin[i * NR], __ldg(wp + (size_t)i * nout * (size_t)p.P), acc);
+                            const double* wp = gen + (size_t)(woff + j) * kTileStride;
+                            for (int i = 0; i < nin; ++i) acc = R2P2_FMA(hin[i * NR], __ldg(wp + (size_t)i * nout * kTileStride), acc);
                         } else {
                             // batches of 8: all loads first (independent of the chain), then the ordered FMA chain;
                             // out-of-range slots read a clamped (valid) address and are predicated off
@@ -1413,8 +1422,8 @@ __global__ void __launch_bounds__((NET::kLayers > 0 && !NET::kSmemWeights) ? kRe
                 const int m = n < R ? n : R;
                 double lin = 0.0, angv = 0.0;
                 if (LPR == 1) {
-                    for (int i = 0; i < m; ++i) lin = R2P2_ADD(lin, R2P2_MUL(__ldg(p.genomes + (size_t)i * p.P + rb), bufA[i * NR]));
-                    for (int i = 0; i < m; ++i) angv = R2P2_ADD(angv, R2P2_MUL(__ldg(p.genomes + (size_t)(n + i) * p.P + rb), bufA[i * NR]));
+                    for (int i = 0; i < m; ++i) lin = R2P2_ADD(lin, R2P2_MUL(__ldg(gen + (size_t)i * kTileStride), bufA[i * NR]));
+                    for (int i = 0; i < m; ++i) angv = R2P2_ADD(angv, R2P2_MUL(__ldg(gen + (size_t)(n + i) * kTileStride), bufA[i * NR]));
                 } else {
                     for (int i = 0; i < m; ++i) lin = R2P2_ADD(lin, R2P2_MUL(gen[i], bufA[i * NR]));
                     for (int i = 0; i < m; ++i) angv = R2P2_ADD(angv, R2P2_MUL(gen[n + i], bufA[i * NR]));
@@ -1423,12 +1432,12 @@ __global__ void __launch_bounds__((NET::kLayers > 0 && !NET::kSmemWeights) ? kRe
                 g.sync();
             } else if (pid) {
                 // every lane of the group evaluates the controller on the same values; lane 0 writes the goal stack
-                const bool ok = (LPR == 1) ? pid_control(p, sv, ps, rb, true, x, y, theta, speed, bufA, NR, p.genomes + rb, (size_t)p.P, s_tab, flags, v, w)
+                const bool ok = (LPR == 1) ? pid_control(p, sv, ps, rb, true, x, y, theta, speed, bufA, NR, gen, (size_t)kTileStride, s_tab, flags, v, w)
                                            : pid_control(p, sv, ps, rb, g.sub == 0, x, y, theta, speed, bufA, NR, gen, (size_t)1, s_tab, flags, v, w);
                 g.sync();                                  // bufA is rewritten by the next tick's sense; a pushed goal is visible to the group
                 if (!ok) { flags |= R2P2_F_FAULT; break; }
             } else {
-                if (LPR == 1) { v = __ldg(p.genomes + rb); w = __ldg(p.genomes + (size_t)p.P + rb); }
+                if (LPR == 1) { v = __ldg(gen); w = __ldg(gen + kTileStride); }
                 else { v = gen[0]; w = gen[1]; }
             }
             PT(2)
@@ -1680,19 +1689,22 @@ __global__ void i32_to_u8_kernel(const int32_t* __restrict__ in, uint8_t* __rest
     out[i] = (uint8_t)v;
 }
 
-// [P][G] -> [G][P], rows lo .. P-1 of `in` (lo a multiple of 32 or 0; P = the end of the range and the stride of `out`'s rows
-// is P_total)
-__global__ void transpose_genomes_kernel(const double* __restrict__ in, double* __restrict__ out, int lo, int P, int P_total, int G) {
+// One-lane mapping: the genomes in tiles of 32 robots, [ceil(P/32)][G][32] -- gene q of robot rb at
+// ((rb >> 5) * G + q) * 32 + (rb & 31).  A warp's 32 robots read gene q as one coalesced 256-byte line, and for one robot
+// consecutive genes are a compile-time 256 bytes apart: the loads of the compile-time-shaped MLP take immediate offsets
+// from one pointer per robot (with a [G][P] array every weight cost four address instructions next to its load and FMA).
+// Rows lo .. hi-1 of `in` ([P][G]); lo is a multiple of 32 or 0.
+__global__ void transpose_genomes_kernel(const double* __restrict__ in, double* __restrict__ out, int lo, int hi, int G) {
     __shared__ double tile[32][33];
     const int p0 = lo + blockIdx.x * 32, g0 = blockIdx.y * 32;
     for (int r = threadIdx.y; r < 32; r += blockDim.y) {
         const int pp = p0 + r, gg = g0 + threadIdx.x;
-        if (pp < P && gg < G) tile[r][threadIdx.x] = in[(size_t)pp * G + gg];
+        if (pp < hi && gg < G) tile[r][threadIdx.x] = in[(size_t)pp * G + gg];
     }
     __syncthreads();
     for (int r = threadIdx.y; r < 32; r += blockDim.y) {
         const int gg = g0 + r, pp = p0 + threadIdx.x;
-        if (pp < P && gg < G) out[(size_t)gg * P_total + pp] = tile[threadIdx.x][r];
+        if (pp < hi && gg < G) out[tiled_base((unsigned)pp, G) + (size_t)gg * kTileStride] = tile[threadIdx.x][r];
     }
 }
 
