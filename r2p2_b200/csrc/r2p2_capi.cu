@@ -456,7 +456,7 @@ void plan_smem(KParams& kp, int lpr, bool smem_stage) {
 int choose_block(r2p2_handle h, const KParams& kp, int lpr, bool smem_stage) {
     const bool regw = lpr >= 16 && !smem_stage && (net_matches<NetNeuro>(kp) || net_matches<NetSimple>(kp));
     if (regw) return kRegBlock;
-    static const int forced = [] { const char* e = getenv("R2P2_BLOCK"); const int v = e ? atoi(e) : 0; return (v >= 128 && v <= 512 && v % 32 == 0) ? v : 0; }();
+    static const int forced = [] { const char* e = getenv("R2P2_BLOCK"); const int v = e ? atoi(e) : 0; return (v >= 128 && v <= kMaxBlock && v % 32 == 0) ? v : 0; }();
     if (forced) return forced;
     int best = 128;
     long long best_warps = -1;
@@ -466,7 +466,7 @@ int choose_block(r2p2_handle h, const KParams& kp, int lpr, bool smem_stage) {
         plan_smem(k2, lpr, smem_stage);
         return episode_smem_bytes(block, lpr, smem_stage, k2.plane_bytes, k2.has50, k2.maxw, k2.w_in_smem, k2.G, k2.win_ww * k2.win_wb, k2.tanh_in_smem);
     };
-    for (int block = kMaxBlock; block >= 128; block >>= 1) {
+    for (int block : {kMaxBlock, 256, 128}) {
         const size_t smem = smem_of(block);
         if (smem > h->smem_optin || smem * (kMaxBlock / block) > (size_t)225 * 1024) continue;   // 16 warps per SM must fit
         const long long ctas = ((long long)(kp.rb_end - kp.rb_begin) * lpr + block - 1) / block;

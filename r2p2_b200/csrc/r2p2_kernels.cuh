@@ -46,7 +46,10 @@ __device__ unsigned long long g_robot_cycles[65536 * 12];   // per robot, per ph
 // whatever the split, and one large CTA stages the read-only tables once per SM instead of four times -- the shared
 // memory that frees goes to L1, where the genomes of the robots in flight live (measured: config E 130 -> 122 ms per 200
 // ticks, scenario-track 62 -> 57 ms).  The register-weight instances (up to 242 registers) run 128 threads.
-constexpr int kMaxBlock = 512;
+#ifndef R2P2_MAXBLOCK
+#define R2P2_MAXBLOCK 512
+#endif
+constexpr int kMaxBlock = R2P2_MAXBLOCK;   // threads per SM of the shared-memory / run-time-shaped instances (registers per thread = 65536 / this)
 constexpr int kRegBlock = 128;
 constexpr double kRad = 3.14159265358979323846 / 180.0;   // CPython math.radians multiplier
 constexpr double kDeg = 180.0 / 3.14159265358979323846;   // CPython math.degrees multiplier
@@ -1100,6 +1103,8 @@ __device__ __forceinline__ void lane_layer(const double* __restrict__ wt, const 
 #pragma unroll
     for (int j = 0; j < nout; ++j) hout[j * NR] = acc[j];
     if (!last) {
+        // (measured: a branch-free tanh evaluated for two neurons at a time, so that their chains overlap, is 5 % slower --
+        // the table rows are picked per lane and the shared-memory pipe, not the chain, is what the activations wait for)
 #pragma unroll 1
         for (int j = 0; j < nout; ++j) hout[j * NR] = activate(activation, hout[j * NR], tanhtab);
     }
@@ -1122,6 +1127,9 @@ __device__ __forceinline__ void lane_mlp(const double* __restrict__ wt, double* 
 // in the [P][G] array -- and each neuron keeps the reference's ordered chain acc = fma(h_i, w_ij, acc), i ascending.
 // (The first version exchanged activations with __shfl_sync: two SHFL per double and input were 11 % of the synthetic
 // sweep's instructions.)
+// (Measured on config E, where the genomes of the robots in flight fit neither shared memory nor L1 and every batch of
+// weight loads waits for L2 -- 9 % of the run in long-scoreboard stalls: prefetch.global.L1 of the next batch's lines, one
+// per lane and batch, made the run 20 % slower.)
 template <int LPR, class NET, int L>
 __device__ __forceinline__ void group_layer(const double* __restrict__ gs, const double* hin, double* hout, int NR, int sub, int activation, const double* tanhtab) {
     constexpr int nin = NET::sz(L), nout = NET::sz(L + 1), slots = (nout + LPR - 1) / LPR;
