@@ -346,7 +346,7 @@ void window_geometry(KParams& kp, int lpr) {
     if (lpr < 2 || lpr > 16 || !kp.g_hot || no_win || !(kp.L > -1.0 && kp.L < 30000.0)) return;
     int tl = 1;
     while (tl * 2 * kp.R <= lpr && tl < kMaxSonarTeam) tl *= 2;
-    const int own_s = sonar_nown(tl, kWsSonarOwn<2> == kWsSonarOwn<8> ? 8 : (lpr <= 2 ? 8 : 4)), own_c = (lpr >= 16 ? 1 : lpr >= 8 ? 2 : 4);
+    const int own_s = sonar_nown(tl, lpr <= 2 ? kWsSonarOwn<2> : kWsSonarOwn<8>, lpr <= 2 ? kWsTeamOwn<2> : kWsTeamOwn<8>), own_c = (lpr >= 16 ? 1 : lpr >= 8 ? 2 : 4);
     const int kB_s = (int)std::ceil(kp.L + 1e-6);
     const double climit = std::fabs(kp.max_speed * kp.delta) + std::fabs(kp.radius);
     if (!(climit < 4096.0)) return;

@@ -58,6 +58,7 @@ template <int LPR> constexpr int kWsSonarOwn = 8;
 #else
 template <int LPR> constexpr int kWsSonarOwn = (LPR <= 2 ? 8 : 4);
 #endif
+template <int LPR> constexpr int kWsTeamOwn = kWsSonarOwn<LPR>;
 template <int LPR> constexpr int kWsCollOwn = (LPR >= 16 ? 1 : LPR >= 8 ? 2 : 4);
 
 template <int LPR, class NET, bool EXTRA = false>
@@ -212,7 +213,7 @@ __global__ void __launch_bounds__((NET::kLayers > 0 && !NET::kSmemWeights) ? kRe
                 const double ang = have_ray ? R2P2_ADD(p.ray_deg[i], theta) : 0.0;
                 const SinCos sc = sincos_call(R2P2_MUL(ang, kRad), s_tab);
                 if (!sc.ok && have_ray) { flags |= R2P2_F_TRIGRANGE; fault = true; }
-                const Hit h = team_march<(LPR < kMaxSonarTeam ? LPR : kMaxSonarTeam), kWsSonarOwn<LPR>, kWsWin>(kWsWin ? svw : sv, sonar_team, plan, ox, oy, sc.c, sc.s, p.L);
+                const Hit h = team_march<(LPR < kMaxSonarTeam ? LPR : kMaxSonarTeam), kWsSonarOwn<LPR>, kWsWin, kWsTeamOwn<LPR>>(kWsWin ? svw : sv, sonar_team, plan, ox, oy, sc.c, sc.s, p.L);
                 if (h.fault && have_ray) fault = true;
                 const bool leader = have_ray && (team_j == 0);
                 double d = 0.0;

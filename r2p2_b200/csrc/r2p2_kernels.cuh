@@ -434,7 +434,9 @@ __device__ __forceinline__ Hit team_march_t(const StageView& s, const Team& tm, 
         // Position of an own sample when it is needed afterwards (the lane's first event, the knife-edge sample).  One
         // lane per ray: re-walked from the pass start with the same additions (at most NOWN - 1 of them; no registers
         // held across the pass).  Teams: kept per sample -- a re-walk of up to TL * (NOWN - 1) dependent additions would
-        // sit on the critical path of the latency-bound mappings (config B: +7 %).
+        // sit on the critical path of the latency-bound mappings (config B: +7 %).  The warp-synchronous kernel keeps them
+        // too: there the re-walk is a loop whose trip count differs from lane to lane (measured on config E, 200 ticks:
+        // 4 own samples kept 123 ms, re-walked 128 ms, 8 own samples re-walked 130 ms).
         constexpr int NKEEP = (TL > 1 || WIN) ? NOWN : 1;
         double xs[NKEEP], ys[NKEEP];
         xs[0] = x; ys[0] = y;                               // this lane's first sample of the pass
@@ -484,7 +486,11 @@ __device__ __forceinline__ Hit team_march_t(const StageView& s, const Team& tm, 
             key = ((unsigned)(k0 + me * TL) << 2) | (inter ? (unsigned)kSampleHit : kSampleSlow);
             break;                                          // this lane's later samples cannot come before its first event
         }
-        if (rem > TL * NOWN) {                              // another pass follows
+        // On to the lane's first sample of the next pass.  After the last pass the position is not read again: a lane that
+        // walks its ray alone skips the test (the compiler turned it into four selects per pass: config E -1 %, 8,192
+        // robots -3 %); teams keep it -- their TL additions would sit at the end of the in-order chain of the
+        // latency-bound mappings (config B +2 % without it).
+        if (TL == 1 || rem > TL * NOWN) {
 #pragma unroll
             for (int u = 0; u < TL; ++u) { x = R2P2_ADD(x, vx); y = R2P2_ADD(y, vy); }
         }
@@ -524,8 +530,9 @@ __device__ __forceinline__ Hit team_march_t(const StageView& s, const Team& tm, 
 // Team sizes the kernels use: sonar rays 1, 2, 4 or 8 lanes (the largest that gives every ray of the fan a team within
 // the group), the collision ray the whole group.  MAXTL = lanes per robot.
 constexpr int kMaxSonarTeam = 8;
-__host__ __device__ constexpr int sonar_nown(int tl, int maxown) { return tl >= 32 ? 1 : tl >= 16 ? 2 : tl >= 8 ? 4 : maxown; }
-template <int MAXTL, int MAXOWN = 8, bool WIN = false>
+// own samples per pass (maxown: of a lane that walks a ray alone, teamown: of teams of 2 or 4 lanes)
+__host__ __device__ constexpr int sonar_nown(int tl, int maxown, int teamown) { return tl >= 32 ? 1 : tl >= 16 ? 2 : tl >= 8 ? 4 : tl >= 2 ? teamown : maxown; }
+template <int MAXTL, int MAXOWN = 8, bool WIN = false, int TEAMOWN = MAXOWN>
 __device__ __forceinline__ Hit team_march(const StageView& s, const Team& tm, const MarchPlan& mp, double ox, double oy,
                                           double vx, double vy, double limit) {
     constexpr int O = MAXOWN;
@@ -533,8 +540,8 @@ __device__ __forceinline__ Hit team_march(const StageView& s, const Team& tm, co
         case 32: if constexpr (MAXTL >= 32) return team_march_t<32, 1, WIN>(s, tm, mp, ox, oy, vx, vy, limit);
         case 16: if constexpr (MAXTL >= 16) return team_march_t<16, 2, WIN>(s, tm, mp, ox, oy, vx, vy, limit);
         case 8: if constexpr (MAXTL >= 8) return team_march_t<8, 4, WIN>(s, tm, mp, ox, oy, vx, vy, limit);
-        case 4: if constexpr (MAXTL >= 4) return team_march_t<4, O, WIN>(s, tm, mp, ox, oy, vx, vy, limit);
-        case 2: if constexpr (MAXTL >= 2) return team_march_t<2, O, WIN>(s, tm, mp, ox, oy, vx, vy, limit);
+        case 4: if constexpr (MAXTL >= 4) return team_march_t<4, TEAMOWN, WIN>(s, tm, mp, ox, oy, vx, vy, limit);
+        case 2: if constexpr (MAXTL >= 2) return team_march_t<2, TEAMOWN, WIN>(s, tm, mp, ox, oy, vx, vy, limit);
         default: return team_march_t<1, O, WIN>(s, tm, mp, ox, oy, vx, vy, limit);
     }
 }
