@@ -9,10 +9,13 @@ import csv, gzip, io, os, re, subprocess, sys, tempfile, collections
 src_csv, key = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 and sys.argv[3].isdigit() else 60
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-tmp = tempfile.mkdtemp()
-subprocess.check_call(["cuobjdump", "-xelf", "all", os.path.join(ROOT, "r2p2_b200/csrc/libr2p2_b200.so")], cwd=tmp, stdout=subprocess.DEVNULL)
-cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
-sass = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout.splitlines()
+if os.environ.get("SASS_TXT"):        # `nvdisasm -g -c` output of the build that was profiled, kept from before later rebuilds
+    sass = open(os.environ["SASS_TXT"]).read().splitlines()
+else:
+    tmp = tempfile.mkdtemp()
+    subprocess.check_call(["cuobjdump", "-xelf", "all", os.path.join(ROOT, "r2p2_b200/csrc/libr2p2_b200.so")], cwd=tmp, stdout=subprocess.DEVNULL)
+    cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
+    sass = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout.splitlines()
 start = next(i for i, l in enumerate(sass) if l.startswith(".text.") and key in l and l.rstrip().endswith(":"))
 lines = []
 cur = ("?", 0)
@@ -44,7 +47,10 @@ src = {}
 for (f, ln) in agg:
     p = os.path.join(ROOT, "r2p2_b200/csrc", f)
     if f not in src and os.path.exists(p):
-        src[f] = open(p).read().splitlines()
+        if os.environ.get("SRC_REV"):     # the source as of the profiled build
+            src[f] = subprocess.run(["git", "show", "%s:r2p2_b200/csrc/%s" % (os.environ["SRC_REV"], f)], capture_output=True, text=True, cwd=ROOT).stdout.splitlines()
+        else:
+            src[f] = open(p).read().splitlines()
 print("total warp-inst %d samples %d" % (tot_i, tot_s))
 for (f, ln), (ie, sm) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
     text = src[f][ln - 1].strip()[:100] if f in src and ln - 1 < len(src[f]) else ""
