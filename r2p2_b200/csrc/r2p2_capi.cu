@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "r2p2_kernel_ws.cuh"
+#include "r2p2_lprtab.h"
 #include "r2p2_ga.cuh"
 
 using namespace r2p2;
@@ -494,11 +495,24 @@ int dispatch_episode(r2p2_handle h, KParams& kp, int lpr, bool smem_stage, int* 
     }
 }
 
-// Widest group whose whole population is resident at once, judged by the occupancy of the kernel instance that mapping
-// selects (the register-weight instances hold 2 CTAs per SM, the run-time-shaped ones 4).  Measured on B200:
-// P=1024 -> 32 lanes, P=2048 -> 16, P=8192 -> 8, P=65536 -> 1.
+// Lanes per robot.  From 768 robots on: the fastest mapping of the measured sweep (tools/sweep_lpr.py on a B200 ->
+// profiles/r02_lpr_sweep.json -> r2p2_lprtab.h), row by ray count, column by the population's power of two.  The rule it
+// replaces -- the widest group whose whole population is resident at once -- agrees with the sweep within 3 % except where
+// it picked 2 lanes (32,768 five-ray robots: 1 lane is 1.3x faster; 16,384 / 32,768 robots with 32 rays: 8 lanes are
+// 1.7x / 1.2x faster); it still serves small populations (always resident: a warp per robot) and mappings the table
+// names but this configuration cannot launch.
 int choose_lpr(r2p2_handle h, const KParams& kp) {
     if (h->lpr_req) return h->lpr_req;
+    if (h->P >= 768) {
+        const LprRow* row = &kLprTable[0];
+        for (const LprRow& r : kLprTable) { row = &r; if (h->R <= r.max_rays) break; }
+        int col = 0;
+        while (col < 7 && (double)h->P > 1024.0 * std::pow(2.0, col + 0.5)) ++col;       // nearest power of two (log scale)
+        const int lpr = row->best[col];
+        KParams k2 = kp;
+        int occ = 0;
+        if (dispatch_episode(h, k2, lpr, false, &occ) == R2P2_OK && occ >= 1) return lpr;
+    }
     for (int lpr = 32; lpr > 1; lpr >>= 1) {
         KParams k2 = kp;
         int occ = 0;
@@ -506,8 +520,6 @@ int choose_lpr(r2p2_handle h, const KParams& kp) {
         const long long ctas = ((long long)h->P * lpr + k2.block - 1) / k2.block;
         if (ctas <= (long long)occ * h->sm_count) return lpr;
     }
-    // more robots than fit at once.  Many rays per robot (config E: 32 rays, 262144 robots): eight lanes split the fan, the
-    // windows of the robots in flight fit shared memory (measured, 200 ticks: 8 lanes 134 ms, 4 lanes 150, 16 lanes 185)
     return h->R >= 16 ? 8 : 1;
 }
 
