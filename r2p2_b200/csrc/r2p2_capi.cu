@@ -119,6 +119,8 @@ struct r2p2_sim {
     int* d_ga_elite = nullptr;
     // scheduling / counters
     unsigned int* d_work = nullptr;
+    uint32_t* d_slice[2] = {nullptr, nullptr};   // time slicing: slices written back per batch of robots, one buffer per launch slot
+    size_t slice_cap[2] = {0, 0};
     unsigned long long* d_cnt3 = nullptr;
     uint64_t launches = 0;
 };
@@ -303,7 +305,8 @@ std::vector<OccEntry> g_occ_cache;      // per kernel instance: dynamic shared m
 std::mutex g_occ_mutex;                 // handles of different host threads share the cache
 
 template <int LPR, class KERN>
-int launch_kernel(r2p2_handle h, KERN kern, const KParams& kp, size_t smem, int* occ_out) {
+int launch_kernel(r2p2_handle h, KERN kern, const KParams& kp_in, size_t smem, int* occ_out, bool can_slice = false) {
+    KParams kp = kp_in;
     int occ = -1;
     std::lock_guard<std::mutex> lock(g_occ_mutex);
     for (const OccEntry& e : g_occ_cache)
@@ -321,6 +324,27 @@ int launch_kernel(r2p2_handle h, KERN kern, const KParams& kp, size_t smem, int*
     long long ctas = ((long long)(kp.rb_end - kp.rb_begin) + robots_per_cta - 1) / robots_per_cta;
     ctas = std::max<long long>(1, std::min<long long>(ctas, (long long)occ * h->sm_count));   // persistent: the work counter feeds the rest
     cudaStream_t st = h->slot ? h->aux_stream : h->stream;
+    // Time slicing (warp-synchronous kernel, see KParams): only when the population runs in several waves, and then fine
+    // enough that the launch ends within ~1/24 of its length of the ideal; slices of at least 25 ticks (state and window
+    // are re-read per slice).  R2P2_NO_SLICES=1: off (A/B measurements).
+    kp.n_slices = 0; kp.slice_T = 0; kp.slice_done = nullptr;
+    static const bool no_slices = [] { const char* e = getenv("R2P2_NO_SLICES"); return e && e[0] == '1'; }();
+    if (can_slice && !no_slices && !kp.tr_pose && kp.T >= 50) {
+        const long long warps = ((long long)(kp.rb_end - kp.rb_begin) * LPR + 31) / 32, cap = (long long)occ * h->sm_count * (kp.block / 32);
+        if (warps > cap) {
+            const double waves = (double)warps / (double)cap;
+            int n = std::min((int)std::ceil(24.0 / waves), kp.T / 25);
+            if (n >= 2) {
+                kp.slice_T = (kp.T + n - 1) / n;
+                kp.n_slices = (kp.T + kp.slice_T - 1) / kp.slice_T;
+                const size_t batches = ((size_t)(kp.rb_end - kp.rb_begin) + (32 / LPR) - 1) / (32 / LPR);
+                if (batches > h->slice_cap[h->slot]) { CK(dalloc(&h->d_slice[h->slot], batches)); h->slice_cap[h->slot] = batches; }
+                kp.slice_done = h->d_slice[h->slot];
+                CK(cudaMemsetAsync(kp.slice_done, 0, batches * sizeof(uint32_t), st));
+                ctas = std::min<long long>((long long)occ * h->sm_count, ctas);
+            }
+        }
+    }
     CK(cudaMemsetAsync(kp.work_counter, 0, sizeof(unsigned int), st));
     if (!h->timing_off) CK(cudaEventRecord(h->ev0, st));
     kern<<<(unsigned)ctas, kp.block, smem, st>>>(kp);
@@ -369,7 +393,7 @@ int launch_episode(r2p2_handle h, const KParams& kp, size_t smem, int* occ_out) 
     if constexpr (LPR >= 2 && LPR <= 16 && !SMEM) {
         if (ws_allowed(kp))
             return extra ? launch_kernel<LPR>(h, episode_kernel_ws<LPR, NET, true>, kp, smem, occ_out)
-                         : launch_kernel<LPR>(h, episode_kernel_ws<LPR, NET, false>, kp, smem, occ_out);
+                         : launch_kernel<LPR>(h, episode_kernel_ws<LPR, NET, false>, kp, smem, occ_out, true);
     }
     if constexpr (!NET::kSmemWeights || LPR == 1) {
         return extra ? launch_kernel<LPR>(h, episode_kernel<LPR, SMEM, NET, true>, kp, smem, occ_out)
@@ -418,7 +442,7 @@ int launch_episode_s(r2p2_handle h, KParams& kp, bool smem_stage, int* occ_out) 
         if (net_matches<NetNeuro>(kp)) return launch_episode<LPR, false, SmemNet<NetNeuro>>(h, kp, sm, occ_out);
         if (net_matches<NetSimple>(kp)) return launch_episode<LPR, false, SmemNet<NetSimple>>(h, kp, sm, occ_out);
         if constexpr (LPR >= 4) if (net_matches<NetSweep>(kp) && !(kp.goal_on || kp.skip_sense))
-            return launch_kernel<LPR>(h, episode_kernel_ws<LPR, SmemNet<NetSweep>, false>, kp, sm, occ_out);
+            return launch_kernel<LPR>(h, episode_kernel_ws<LPR, SmemNet<NetSweep>, false>, kp, sm, occ_out, true);
     }
     const size_t smem = episode_smem_bytes(kp.block, LPR, smem_stage, kp.plane_bytes, kp.has50, kp.maxw, kp.w_in_smem, kp.G, kp.win_ww * kp.win_wb, kp.tanh_in_smem);
     return smem_stage ? launch_episode<LPR, true, GenericNet>(h, kp, smem, occ_out) : launch_episode<LPR, false, GenericNet>(h, kp, smem, occ_out);
@@ -579,7 +603,7 @@ int r2p2_destroy(r2p2_handle h) {
                     s.time, s.fitness, s.flags, s.ncollide, s.ticks, s.ndraws, s.goal_tick, s.nsamp_sonar, s.nsamp_coll, h->d_noise, h->d_x0, h->d_y0, h->d_t0,
                     h->d_wall, h->d_l50, h->d_dist, h->d_crxy, h->d_sincostab, h->d_genomes, h->d_genomes_t, h->d_work, h->d_cnt3,
                     h->d_ga_pop[0], h->d_ga_pop[1], h->d_ga_fit, h->d_ga_elite, h->d_sense_dst, h->d_sense_px, h->d_cmd, h->d_levels, h->d_hot,
-                    h->d_pid_goals, h->pid_acc_ang, h->pid_acc_dist, h->pid_last_ang, h->pid_last_dist, h->pid_target, h->pid_state, h->pid_backing,
+                    h->d_slice[0], h->d_slice[1], h->d_pid_goals, h->pid_acc_ang, h->pid_acc_dist, h->pid_last_ang, h->pid_last_dist, h->pid_target, h->pid_state, h->pid_backing,
                     h->pid_ngoals, h->pid_gx, h->pid_gy};
     for (void* p : ptrs) cudaFree(p);
     free_trace(h);

@@ -124,25 +124,44 @@ __global__ void __launch_bounds__((NET::kLayers > 0 && !NET::kSmemWeights) ? kRe
     const uint32_t win_saddr = smem_u32(s_win + (size_t)slot * win_words);
     const int win_cpb = p.win_ww >> 2;                    // 16-byte chunks per band
 
+    const unsigned n_batches = (p.rb_end - p.rb_begin + (unsigned)RPW - 1u) / (unsigned)RPW;
+    const unsigned n_slices = p.n_slices > 1 ? (unsigned)p.n_slices : 1u;
     for (;;) {
-        // ---- the warp fetches its next 32/LPR robots ---------------------------------------------------
-        unsigned base = 0;
-        if (lane == 0) base = atomicAdd(p.work_counter, (unsigned)RPW) + p.rb_begin;
-        base = __shfl_sync(FULL, base, 0);
-        if (base >= p.rb_end) break;
+        // ---- the warp fetches its next work item: 32/LPR robots, all T ticks or one slice of them -----------
+        unsigned item = 0;
+        if (lane == 0) item = atomicAdd(p.work_counter, 1u);
+        item = __shfl_sync(FULL, item, 0);
+        if (item >= n_batches * n_slices) break;
+        const unsigned slice = item / n_batches, batch = item - slice * n_batches;
+        const unsigned base = batch * (unsigned)RPW + p.rb_begin;
+        if (slice > 0u) {
+            // Items are handed out in order, so the previous slice of this batch was taken earlier by a warp that is
+            // resident and running (an item only ever waits for a smaller one): the wait ends.  A bound on the polls turns
+            // a broken invariant into a launch error instead of a hang.
+            if (lane == 0) {
+                unsigned polls = 0u;
+                while (ld_acquire_u32(p.slice_done + batch) < slice) {
+                    __nanosleep(256);
+                    if (++polls > (1u << 26)) __trap();
+                }
+            }
+            __syncwarp();
+        }
         const unsigned rb_raw = base + lane / LPR;
         const bool valid = rb_raw < p.rb_end;
         const unsigned rb = valid ? rb_raw : p.rb_end - 1u;              // lanes without a robot read a valid one, commit nothing
 
-        double x = p.x[rb], y = p.y[rb], theta = p.theta[rb], speed = p.speed[rb], omega = p.omega[rb];
-        double last_x = p.last_x[rb], last_y = p.last_y[rb];
-        double dist = p.dist[rb], odom_x = p.odom_x[rb], odom_y = p.odom_y[rb];
-        const double origin_x = p.origin_x[rb], origin_y = p.origin_y[rb];
-        double tmr = p.time[rb];
-        double fitness = p.fitness[rb];
-        unsigned flags = p.flags[rb], ncollide = p.ncollide[rb], ticks = p.ticks[rb];
+        // (L2 loads: with time slicing the previous slice of this robot may have been written by another SM, and L1 is not
+        // coherent between SMs)
+        double x = __ldcg(p.x + rb), y = __ldcg(p.y + rb), theta = __ldcg(p.theta + rb), speed = __ldcg(p.speed + rb), omega = __ldcg(p.omega + rb);
+        double last_x = __ldcg(p.last_x + rb), last_y = __ldcg(p.last_y + rb);
+        double dist = __ldcg(p.dist + rb), odom_x = __ldcg(p.odom_x + rb), odom_y = __ldcg(p.odom_y + rb);
+        const double origin_x = __ldcg(p.origin_x + rb), origin_y = __ldcg(p.origin_y + rb);
+        double tmr = __ldcg(p.time + rb);
+        double fitness = __ldcg(p.fitness + rb);
+        unsigned flags = __ldcg(p.flags + rb), ncollide = __ldcg(p.ncollide + rb), ticks = __ldcg(p.ticks + rb);
         const unsigned ncollide_in = ncollide;
-        unsigned ndraws = p.noise_mode ? p.ndraws[rb] : 0u;
+        unsigned ndraws = p.noise_mode ? __ldcg(p.ndraws + rb) : 0u;
         unsigned my_ns_sonar = 0u, ns_coll = 0u;
         const double* gen = p.genomes + (size_t)rb * (size_t)p.G;
         FixedMlp<LPR, NET> mlp;
@@ -155,7 +174,7 @@ __global__ void __launch_bounds__((NET::kLayers > 0 && !NET::kSmemWeights) ? kRe
             gen = dst_g;
         }
 
-        unsigned goal_tick = (EXTRA && p.goal_on) ? p.goal_tick[rb] : 0xffffffffu;
+        unsigned goal_tick = (EXTRA && p.goal_on) ? __ldcg(p.goal_tick + rb) : 0xffffffffu;
         const bool pid = EXTRA && p.ctrl_kind == R2P2_CTRL_PID;      // Sequential_PID_Controller on the device
         PidState ps;
         ps.acc_ang = ps.acc_dist = ps.last_ang = ps.last_dist = ps.target = 0.0; ps.state = ps.backing = ps.ngoals = 0;
@@ -166,7 +185,9 @@ __global__ void __launch_bounds__((NET::kLayers > 0 && !NET::kSmemWeights) ? kRe
         svw.hx0 = 1; svw.hy0 = 1; svw.hx1 = 0; svw.hy1 = 0;   // (nothing fetched yet)
         int tdone = 0;                                    // ticks completed in this launch
         unsigned ncollide0 = ncollide;
-        for (int t = 0; t < p.T; ++t) {
+        const int t_begin = (n_slices > 1u) ? (int)slice * p.slice_T : 0;
+        const int t_end = (n_slices > 1u) ? min(p.T, t_begin + p.slice_T) : p.T;
+        for (int t = t_begin; t < t_end; ++t) {
             if (!__any_sync(FULL, alive)) break;
             bool live = alive;
             if (live) ncollide0 = ncollide;
@@ -488,12 +509,17 @@ __global__ void __launch_bounds__((NET::kLayers > 0 && !NET::kSmemWeights) ? kRe
             p.dist[rb] = dist; p.odom_x[rb] = odom_x; p.odom_y[rb] = odom_y;
             p.time[rb] = tmr; p.fitness[rb] = fitness;
             p.flags[rb] = flags; p.ncollide[rb] = ncollide; p.ticks[rb] = ticks;
-            p.nsamp_sonar[rb] += ns_sonar; p.nsamp_coll[rb] += ns_coll;
+            p.nsamp_sonar[rb] = __ldcg(p.nsamp_sonar + rb) + ns_sonar; p.nsamp_coll[rb] = __ldcg(p.nsamp_coll + rb) + ns_coll;
             if (p.noise_mode) p.ndraws[rb] = ndraws;
             if ((EXTRA && p.goal_on)) p.goal_tick[rb] = goal_tick;
             if (pid) pid_store(p, rb, ps);
         }
         __syncwarp();
+        if (n_slices > 1u) {                               // this batch's state is in L2: its next slice may start
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) st_release_u32(p.slice_done + batch, slice + 1u);
+        }
     }
 }
 

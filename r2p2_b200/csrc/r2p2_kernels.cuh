@@ -117,6 +117,12 @@ struct KParams {
     int32_t block;                     // threads per CTA of this launch (host side; the kernels read blockDim.x)
     uint32_t rb_begin, rb_end;         // robots [rb_begin, rb_end) are this launch's work (the whole population, or one chunk of a
                                        // pipelined evaluation whose later genomes are still being uploaded)
+    // Time slicing (warp-synchronous kernel, populations that run in several waves): the T ticks are cut into n_slices
+    // slices of slice_T ticks; a warp's work item is (slice, batch of 32/LPR robots), handed out slice-major, and an item
+    // waits until the previous slice of its batch has been written back (slice_done[batch] counts them).  Without it
+    // the last, partly filled wave takes as long as a full one (32,768 32-ray robots = 3.46 waves ran like 3.8).
+    int32_t n_slices, slice_T;         // n_slices <= 1: off
+    uint32_t* slice_done;              // [batches], zeroed before the launch
 };
 
 struct StageView {
@@ -184,6 +190,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t mbar, uint32_t parity) {
 __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint32_t mbar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(mbar) : "memory");
+}
+
+// release / acquire on a 32-bit flag in global memory (time slicing: a batch's next slice waits for the previous one)
+__device__ __forceinline__ unsigned ld_acquire_u32(const uint32_t* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u32(uint32_t* p, unsigned v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
 // 16-byte asynchronous copy global -> shared (LDGSTS), cached at L2 only

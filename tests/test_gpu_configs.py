@@ -121,6 +121,42 @@ def test_config_E_large_population_mapping_invariance(sweep_stage):
     assert c0["robot_steps"] == P * T
 
 
+@pytest.mark.parametrize("evolve,noise", [(False, "off"), (True, "device")])
+def test_time_slicing_of_multi_wave_populations(evolve, noise, sweep_stage):
+    """A population that runs in several waves on the warp-synchronous kernel is time-sliced (a warp's work item is one
+    slice of the ticks of one batch of robots; the next slice of a batch waits for the previous one's write-back):
+    24 000 32-ray robots x 130 ticks = 2.5 waves -> five slices of 26 ticks.  One lane per robot (another kernel, never
+    sliced) must give the same bits -- state, flags, fitness, sample counters, noise draws -- with robots that stop early
+    (evolve: a collision ends the episode) and with the device noise generator."""
+    import r2p2_b200
+    w = bench.WORKLOADS["E"]
+    rob = bench.ROBOTS[w["robot"]]
+    P, T = 24000, 130
+    x0, y0, th0 = bench.slice_poses(bench.start_poses(w, P), 0, P)
+    genomes = bench.make_genomes(w, 11, 0, P)
+    res = []
+    for lpr in (8, 1):
+        sim = r2p2_b200.BatchSim(0)
+        sim.set_stage(sweep_stage)
+        sim.set_robot(sonar_range=rob["sonar_range"], radius=rob["radius"], max_speed=rob["max_speed"], sonars=rob["sonars"])
+        sim.set_controller("neuro", hidden_layer=[16, 8])
+        sim.set_noise(noise, seed=77)
+        sim.set_mapping(lpr, -1)
+        sim.upload_genomes(genomes)
+        sim.reset(x0, y0, th0, time_budget=9000.0)
+        sim.run(T, delta=0.1, delta_ctrl=100.0, evolve=evolve)        # evolve: the timer runs out after 90 control calls
+        res.append((sim.state(), sim.fitness(), sim.counters(), sim.noise_draws()))
+        sim.close()
+    (s0, f0, c0, n0), (s1, f1, c1, n1) = res
+    for k in s0:
+        assert np.array_equal(s0[k], s1[k]), k
+    assert np.array_equal(f0, f1) and c0 == c1 and np.array_equal(n0, n1)
+    if evolve:
+        assert 0 < c0["robot_steps"] < P * T and int((s0["ticks"] < 90).sum()) > P // 20     # collisions ended episodes early
+    else:
+        assert c0["robot_steps"] == P * T
+
+
 def test_config_A_as_shipped(oracle_port, oracle_libm):
     """scenario-neuro-simple.json as shipped: track_2.png + robot-neuro.json + controller-neuro-simple.json (hidden [1], tanh,
     7 weights), single robots, 600 and 1000 ticks."""
