@@ -15,6 +15,22 @@ from .evaluator import PopulationEvaluator
 from .simulation import load_image, stage_env
 
 _default = None
+_history = None          # open file of the run's history log (evolution.py:9), or None
+_fitness_path = None     # the mailbox file the reference's controller answers through (neurocontroller.py:62-65), or None
+cur_best = 0
+
+
+def record_history(candidates, fits, history, best):
+    """What evaluate_ann appends to ``../logs/history_<time>.log`` (r2p2/evolution.py:31,45-47), for a whole list of
+    candidates in the order the reference would have evaluated them: a record for every candidate whose fitness is >=
+    the best so far.  Returns the new best."""
+    for c, f in zip(candidates, fits):
+        if f >= best:
+            string = str([float(v) for v in c]).replace(" ", "")          # the reference's candidates are lists of Python floats
+            history.write("\n\n[" + str(float(f)) + "]: " + string)
+            best = f
+    history.flush()
+    return best
 
 
 def generate_const(random, args):
@@ -47,10 +63,19 @@ def make_evaluator(scenario, ticks=600, delta=1.0 / 30.0, delta_ctrl=1000.0 / 30
                                delta_ctrl=delta_ctrl, time_budget=budget, evolve=evolve, device=device, **kw)
 
 
-def configure(scenario, **kw):
-    """Set the evaluator used by ``evaluate_ann`` / ``evaluator`` when ``args`` carries none."""
-    global _default
+def configure(scenario, history_path=None, fitness_path=None, **kw):
+    """Set the evaluator used by ``evaluate_ann`` / ``evaluator`` when ``args`` carries none.
+
+    history_path: write the reference's history log there (``'../logs/history_' + str(int(time.time())) + '.log'`` in the
+    reference, evolution.py:9); fitness_path: also leave the last candidate's fitness in the reference's mailbox file
+    (``'../res/fitness.txt'``) for tools that watch it."""
+    global _default, _history, _fitness_path, cur_best
     _default = make_evaluator(scenario, **kw)
+    if _history is not None:
+        _history.close()
+    _history = open(history_path, "a+") if history_path else None
+    _fitness_path = fitness_path
+    cur_best = 0
     return _default
 
 
@@ -59,8 +84,15 @@ def evaluator(candidates, args=None):
     ev = (args or {}).get("r2p2_evaluator", _default)
     if ev is None:
         raise RuntimeError("call r2p2_b200.evolution.configure(scenario) first, or pass args['r2p2_evaluator']")
+    global cur_best
     try:
-        return ev.evaluate(np.asarray(candidates, dtype=np.float64)).tolist()
+        fits = ev.evaluate(np.asarray(candidates, dtype=np.float64)).tolist()
+        if _history is not None and ev is _default:
+            cur_best = record_history(candidates, fits, _history, cur_best)
+        if _fitness_path and ev is _default and fits:
+            with open(_fitness_path, "w") as fp:
+                fp.write(str(fits[-1]))
+        return fits
     except Exception as e:                                   # evolution.py:49-52: any failure scores 0
         print(__file__)
         print(e)

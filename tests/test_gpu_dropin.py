@@ -86,13 +86,23 @@ def test_scenario_files_and_evolution_callback(tmp_path, oracle_port):
     sim.run(20, delta=0.1)
     assert sim.robots[0].x != 230
 
-    ev = evolution.configure(os.path.join(conf, "scenario-neuro.json"), ticks=300)
+    ev = evolution.configure(os.path.join(conf, "scenario-neuro.json"), ticks=300, history_path=str(tmp_path / "history.log"),
+                             fitness_path=str(tmp_path / "fitness.txt"))
     genomes = np.random.RandomState(3).uniform(-1, 1, (64, 156))
     fit = evolution.evaluator(genomes.tolist(), {})
     rob, kw = common.ROBOTS["robot-neuro.json"], common.oracle_robot_kwargs("robot-neuro.json")
     ref = oracle_port.run(common.load_stage("track_2.png"), ctrl="neuro", genomes=genomes, x0=rob["x"], y0=rob["y"], theta0=0.0, T=300,
                           delta=1.0 / 30.0, delta_ctrl=1000.0 / 30.0, time_budget=20000.0, evolve=True, layers=[5, 10, 7, 4, 2], **kw)
     assert fit == ref["fitness"].tolist()
+    # the reference's side files: history records for every candidate at least as good as the best so far, the mailbox file
+    recs = open(tmp_path / "history.log").read().split("\n\n")[1:]
+    best, want = 0, []
+    for g, f in zip(genomes.tolist(), fit):
+        if f >= best:
+            want.append("[" + str(f) + "]: " + str(g).replace(" ", ""))
+            best = f
+    assert recs == want and len(recs) >= 1
+    assert float(open(tmp_path / "fitness.txt").read()) == fit[-1]
     assert evolution.evaluate_ann(genomes[7].tolist(), {}) == fit[7]
     assert evolution.evaluator([[0.0] * 3], {}) == [0]            # evolution.py:49-52: a failing candidate scores 0
     ev.close()

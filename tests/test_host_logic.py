@@ -97,3 +97,16 @@ def test_ga_improves_and_is_deterministic():
     bests = runs[0][2]
     assert bests[-1] > bests[0] and all(b2 >= b1 for b1, b2 in zip(bests, bests[1:]))     # elitism: monotone
     assert runs[0][1] > 17.0 and np.all(runs[0][0] <= 2.0) and np.all(runs[0][0] >= 0.0)
+
+
+def test_history_log_records(tmp_path):
+    """evolution.evaluate_ann's history records (r2p2/evolution.py:31,45-47): '\\n\\n[fitness]: [genes without spaces]' for every
+    candidate that is at least as good as the best so far, in evaluation order."""
+    import io
+    from r2p2_b200.evolution import record_history
+    buf = io.StringIO()
+    best = record_history([[0.1, 0.2], [0.3, -0.4], [0.5, 0.6]], [1.5, 1.0, 1.5], buf, 0)
+    assert best == 1.5
+    assert buf.getvalue() == "\n\n[1.5]: [0.1,0.2]\n\n[1.5]: [0.5,0.6]"
+    best = record_history([np.array([1.0, 2.0])], [np.float64(2.25)], buf, best)       # numpy inputs print like the reference's lists
+    assert best == 2.25 and buf.getvalue().endswith("\n\n[2.25]: [1.0,2.0]")
