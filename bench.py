@@ -225,7 +225,7 @@ def cpu_port_run(w, genomes, threads, reps=1, poses=None):
     return steps / dt, out, dt
 
 
-CPU_SAMPLE = 1024        # individuals of the workload the CPU arm evaluates per step (the first ones of the population)
+CPU_SAMPLE = 4096        # individuals of the workload the CPU arm evaluates per step (the first ones of the population)
 
 
 def run_reference(args, w):
