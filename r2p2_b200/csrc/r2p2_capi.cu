@@ -458,7 +458,7 @@ int w_in_smem_for(int block, int lpr, int G) {
 // Shared-memory plan of one launch for a given CTA size: windows first, then the genomes of the robots in flight, then
 // the tanh table -- each only while 16 warps per SM (512 / block CTAs of the 128-register instances) still fit.
 void plan_smem(KParams& kp, int lpr, bool smem_stage) {
-    const size_t per_cta = (size_t)55 * 1024 * kp.block / 128;
+    const size_t per_cta = (size_t)225 * 1024 / std::max(1, kMaxBlock / kp.block);   // what one CTA may take with kMaxBlock / block CTAs per SM (one CTA for 448 or 512 threads)
     kp.w_in_smem = w_in_smem_for(kp.block, lpr, kp.G);
     window_geometry(kp, lpr);
     if (kp.w_in_smem && kp.win_ww && episode_smem_bytes(kp.block, lpr, false, kp.plane_bytes, kp.has50, kp.maxw, 1, kp.G, kp.win_ww * kp.win_wb) > per_cta)
