@@ -61,6 +61,7 @@ struct r2p2_sim {
     double vr0 = 0, vr1 = 0, radius = 0, max_speed = 0;
     double* d_crxy = nullptr;
     double* d_sincostab = nullptr;
+    double* d_sincostab_pad = nullptr;   // rows padded to kSinCosRow doubles (shared-memory copy of the episode kernels)
     // controller
     bool have_ctrl = false;
     int kind = 0, n_layers = 0, activation = 0, maxw = 1;
@@ -584,6 +585,13 @@ int r2p2_create(int device, r2p2_handle* out) {
     if (e == cudaSuccess) e = cudaMalloc(&s->d_cnt3, 3 * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMalloc(&s->d_sincostab, R2P2_SINCOSTAB_LEN * sizeof(double));
     if (e == cudaSuccess) e = cudaMemcpy(s->d_sincostab, r2p2_h_sincostab, R2P2_SINCOSTAB_LEN * sizeof(double), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_sincostab_pad, kSinCosPadLen * sizeof(double));
+    if (e == cudaSuccess) {
+        std::vector<double> pad(kSinCosPadLen, 0.0);
+        for (int r = 0; r < R2P2_SINCOSTAB_LEN / 4; ++r)
+            for (int j = 0; j < 4; ++j) pad[(size_t)r * kSinCosRow + j] = r2p2_h_sincostab[r * 4 + j];
+        e = cudaMemcpy(s->d_sincostab_pad, pad.data(), kSinCosPadLen * sizeof(double), cudaMemcpyHostToDevice);
+    }
     if (e != cudaSuccess) {
         fail(nullptr, R2P2_E_CUDA, "r2p2_create: %s", cudaGetErrorString(e));
         cudaGetLastError();
@@ -601,7 +609,7 @@ int r2p2_destroy(r2p2_handle h) {
     StateArrays& s = h->st;
     void* ptrs[] = {s.x, s.y, s.theta, s.speed, s.omega, s.last_x, s.last_y, s.dist, s.odom_x, s.odom_y, s.origin_x, s.origin_y,
                     s.time, s.fitness, s.flags, s.ncollide, s.ticks, s.ndraws, s.goal_tick, s.nsamp_sonar, s.nsamp_coll, h->d_noise, h->d_x0, h->d_y0, h->d_t0,
-                    h->d_wall, h->d_l50, h->d_dist, h->d_crxy, h->d_sincostab, h->d_genomes, h->d_genomes_t, h->d_work, h->d_cnt3,
+                    h->d_wall, h->d_l50, h->d_dist, h->d_crxy, h->d_sincostab, h->d_sincostab_pad, h->d_genomes, h->d_genomes_t, h->d_work, h->d_cnt3,
                     h->d_ga_pop[0], h->d_ga_pop[1], h->d_ga_fit, h->d_ga_elite, h->d_sense_dst, h->d_sense_px, h->d_cmd, h->d_levels, h->d_hot,
                     h->d_slice[0], h->d_slice[1], h->d_pid_goals, h->pid_acc_ang, h->pid_acc_dist, h->pid_last_ang, h->pid_last_dist, h->pid_target, h->pid_state, h->pid_backing,
                     h->pid_ngoals, h->pid_gx, h->pid_gy};
@@ -866,7 +874,7 @@ static int fill_params(r2p2_handle h, KParams& kp, int32_t T, double delta, doub
     kp.P = h->P; kp.T = T; kp.evolve = evolve ? 1 : 0;
     kp.rb_begin = 0u; kp.rb_end = (uint32_t)h->P;
     kp.delta = delta; kp.delta_ctrl = delta_ctrl;
-    kp.g_sincostab = h->d_sincostab; kp.g_crxy = h->d_crxy;
+    kp.g_sincostab = h->d_sincostab; kp.g_sincostab_pad = h->d_sincostab_pad; kp.g_crxy = h->d_crxy;
     {
         void* tt = nullptr;
         CK(cudaGetSymbolAddress(&tt, r2p2_d_tanhtab));

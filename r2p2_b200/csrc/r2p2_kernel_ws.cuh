@@ -70,7 +70,7 @@ __global__ void __launch_bounds__((NET::kLayers > 0 && !NET::kSmemWeights) ? kRe
     constexpr unsigned FULL = 0xffffffffu;
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw);
     double* s_tab = reinterpret_cast<double*>(smem_raw + 16);
-    double* s_crx = s_tab + R2P2_SINCOSTAB_LEN;
+    double* s_crx = s_tab + kSinCosPadLen;
     double* s_cry = s_crx + 360;
     const double* s_tanh = p.g_tanhtab;
     double* s_after = s_cry + 360;
@@ -85,8 +85,8 @@ __global__ void __launch_bounds__((NET::kLayers > 0 && !NET::kSmemWeights) ? kRe
     const uint32_t mb = smem_u32(mbar);
     if (threadIdx.x == 0) {
         mbar_init(mb, 1);
-        mbar_expect_tx(mb, R2P2_SINCOSTAB_LEN * 8 + 720 * 8 + (p.tanh_in_smem ? R2P2_TANH_NINT * R2P2_TANH_ROW * 8 : 0));
-        tma_load_1d(s_tab, p.g_sincostab, R2P2_SINCOSTAB_LEN * 8, mb);
+        mbar_expect_tx(mb, kSinCosPadLen * 8 + 720 * 8 + (p.tanh_in_smem ? R2P2_TANH_NINT * R2P2_TANH_ROW * 8 : 0));
+        tma_load_1d(s_tab, p.g_sincostab_pad, kSinCosPadLen * 8, mb);
         tma_load_1d(s_crx, p.g_crxy, 720 * 8, mb);
         if (p.tanh_in_smem) tma_load_1d(const_cast<double*>(s_tanh), p.g_tanhtab, R2P2_TANH_NINT * R2P2_TANH_ROW * 8, mb);
     }

@@ -51,6 +51,12 @@ __device__ unsigned long long g_robot_cycles[65536 * 12];   // per robot, per ph
 #endif
 constexpr int kMaxBlock = R2P2_MAXBLOCK;   // threads per SM of the shared-memory / run-time-shaped instances (registers per thread = 65536 / this)
 constexpr int kRegBlock = 128;
+// sin/cos table in shared memory: rows (sn, ssn, cs, ccs) padded to 5 doubles.  Lanes with different angles read
+// different rows; at glibc's 4 doubles (8 words) per row they fall on 4 bank groups -- 8-way conflicts on each of the 8
+// loads of a sincos (ncu: 57 % of the one-lane kernel's shared-load wavefronts were conflicts, the LSU pipe 66 % busy);
+// 10 words per row spread them over 16.
+constexpr int kSinCosRow = 5;
+constexpr int kSinCosPadLen = (R2P2_SINCOSTAB_LEN / 4) * kSinCosRow;      // 550 doubles = 4400 bytes (a multiple of 16)
 constexpr double kRad = 3.14159265358979323846 / 180.0;   // CPython math.radians multiplier
 constexpr double kDeg = 180.0 / 3.14159265358979323846;   // CPython math.degrees multiplier
 constexpr double kNormSlack = 1e-6;            // |norm(p_k - o) - k| bound used to skip the norm test (see march)
@@ -86,7 +92,8 @@ struct KParams {
     int32_t P, T, evolve;
     double delta, delta_ctrl;
     // tables
-    const double* g_sincostab;         // 440 doubles
+    const double* g_sincostab;         // 440 doubles (glibc's layout; kernels without a shared-memory copy)
+    const double* g_sincostab_pad;     // the same rows padded to kSinCosRow doubles: what the episode kernels stage into shared memory
     const double* g_crxy;              // 360 x offsets then 360 y offsets (cos/sin(radians(i)) * radius)
     // state (SoA, P each)
     double *x, *y, *theta, *speed, *omega, *last_x, *last_y, *dist, *odom_x, *odom_y, *origin_x, *origin_y, *time, *fitness;
@@ -796,13 +803,13 @@ struct SinCos {
     int ok;
 };
 #ifdef R2P2_EXP_SINCOS_NOINLINE
-__device__ __noinline__ SinCos sincos_call(double a, const double* tab) {
+__device__ __noinline__ SinCos sincos_call(double a, const double* tab, int rs = kSinCosRow) {
 #else
-__device__ __forceinline__ SinCos sincos_call(double a, const double* tab) {
+__device__ __forceinline__ SinCos sincos_call(double a, const double* tab, int rs = kSinCosRow) {
 #endif
     SinCos r;
     r.ok = 1;
-    r2p2_sincos(a, tab, &r.s, &r.c, &r.ok);
+    r2p2_sincos_rs(a, tab, rs, &r.s, &r.c, &r.ok);
     return r;
 }
 
@@ -940,7 +947,7 @@ __device__ __forceinline__ bool pid_control(const KParams& p, const StageView& s
 // ---------------------------------------------------------------------------------------------
 // dynamic shared memory layout (bytes):
 //   [0,16)                         mbarrier
-//   [16, 16+3520)                  sin/cos table
+//   [16, 16+4400)                  sin/cos table, rows padded to 5 doubles
 //   [.., +5760)                    crash-radius offsets (360 x, 360 y)
 //   [.., +18304)                   tanh table (tanh_in_smem only)
 //   [.., +plane_bytes)             wall plane      (SMEM_STAGE only)
@@ -956,7 +963,7 @@ __host__ __device__ inline int smem_gstride(int lpr, int G) { return G + ((lpr -
 
 __host__ __device__ inline size_t episode_smem_bytes(int block, int lpr, bool smem_stage, uint32_t plane_bytes, int has50, int maxw, int w_in_smem, int G,
                                                      int win_words = 0, int tanh_in_smem = 0) {
-    size_t n = 16 + R2P2_SINCOSTAB_LEN * 8 + 720 * 8;
+    size_t n = 16 + kSinCosPadLen * 8 + 720 * 8;
     if (tanh_in_smem) n += (size_t)R2P2_TANH_NINT * R2P2_TANH_ROW * 8;
     if (smem_stage) n += (size_t)plane_bytes * (has50 ? 2 : 1);
     n += (size_t)2 * maxw * (block / lpr) * 8;
@@ -1204,7 +1211,7 @@ __global__ void __launch_bounds__((NET::kLayers > 0 && !NET::kSmemWeights) ? kRe
     const int NR = (int)blockDim.x / LPR;                 // robots in flight per CTA
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw);
     double* s_tab = reinterpret_cast<double*>(smem_raw + 16);
-    double* s_crx = s_tab + R2P2_SINCOSTAB_LEN;
+    double* s_crx = s_tab + kSinCosPadLen;
     double* s_cry = s_crx + 360;
     unsigned char* cur = reinterpret_cast<unsigned char*>(s_cry + 360);
     const double* s_tanh = p.g_tanhtab;
@@ -1223,11 +1230,11 @@ __global__ void __launch_bounds__((NET::kLayers > 0 && !NET::kSmemWeights) ? kRe
     const uint32_t mb = smem_u32(mbar);
     if (threadIdx.x == 0) {
         mbar_init(mb, 1);
-        uint32_t total = R2P2_SINCOSTAB_LEN * 8 + 720 * 8;
+        uint32_t total = kSinCosPadLen * 8 + 720 * 8;
         if (SMEM_STAGE) total += p.plane_bytes * (p.has50 ? 2u : 1u);
         if (p.tanh_in_smem) total += R2P2_TANH_NINT * R2P2_TANH_ROW * 8;
         mbar_expect_tx(mb, total);
-        tma_load_1d(s_tab, p.g_sincostab, R2P2_SINCOSTAB_LEN * 8, mb);
+        tma_load_1d(s_tab, p.g_sincostab_pad, kSinCosPadLen * 8, mb);
         tma_load_1d(s_crx, p.g_crxy, 720 * 8, mb);
         if (p.tanh_in_smem) tma_load_1d(const_cast<double*>(s_tanh), p.g_tanhtab, R2P2_TANH_NINT * R2P2_TANH_ROW * 8, mb);
         if (SMEM_STAGE) {
@@ -1872,7 +1879,7 @@ __global__ void sense_kernel(const __grid_constant__ SenseParams sp) {
     unsigned ndraws = p.noise_mode ? p.ndraws[rb] : 0u;
     unsigned long long ns = 0;
     for (int i = 0; i < p.R && !fault; ++i) {
-        const SinCos sc = sincos_call(R2P2_MUL(R2P2_ADD(p.ray_deg[i], theta), kRad), p.g_sincostab);
+        const SinCos sc = sincos_call(R2P2_MUL(R2P2_ADD(p.ray_deg[i], theta), kRad), p.g_sincostab, 4);
         if (!sc.ok) { flags |= R2P2_F_TRIGRANGE; fault = true; break; }
         const Hit h = march(sv, ox, oy, sc.c, sc.s, p.L);
         if (h.fault) { fault = true; break; }

@@ -243,7 +243,10 @@ R2P2_HD double r2p2_cos(double x, const double* tab, int* ok) {
 // so the three ranges only select the arguments and route the two results.  Lanes of a warp that hold angles of
 // different ranges (the rays of a sonar fan; robots of a population) execute one instruction stream instead of up to
 // six; inside do_sin the Taylor branch (|x| < 0.126) is evaluated next to the table branch and selected.
-R2P2_HD void r2p2_sincos(double x, const double* tab, double* s, double* c, int* ok) {
+// rowlen: doubles between consecutive table rows (4 = glibc's layout; the kernels keep a copy with rows padded to 5 in shared
+// memory: with a stride of 8 words the rows of 32 lanes fall on 4 bank groups -- 8-way conflicts on each of the 8 loads
+// -- with 10 words on 16).
+R2P2_HD void r2p2_sincos_rs(double x, const double* tab, int rowlen, double* s, double* c, int* ok) {
     const int32_t k = r2p2_hi32(x) & 0x7fffffff;
     if (k >= 0x419921FB) {                                  // rare: unsupported range / not finite
         if (ok) *ok = 0;
@@ -276,7 +279,7 @@ R2P2_HD void r2p2_sincos(double x, const double* tab, double* s, double* c, int*
         const double xx = R2P2_MUL(xr, xr);
         const double sp = R2P2_ADD(xr, R2P2_FMA(R2P2_MUL(xr, xx), R2P2_FMA(xx, R2P2_S_SN5, R2P2_S_SN3), sdx));
         const double cp = R2P2_FMA(xr, sdx, R2P2_MUL(xx, R2P2_FMA(xx, R2P2_FMA(xx, R2P2_S_CS6, R2P2_S_CS4), R2P2_S_CS2)));
-        int ti = r2p2_lo32(u) * 4;
+        int ti = r2p2_lo32(u) * rowlen;
         if (asx < 0.126) ti = 0;                            // the table value is not used; keep the address in range
         const double sn = tab[ti], ssn = tab[ti + 1], cs = tab[ti + 2], ccs = tab[ti + 3];
         const double cor = R2P2_FMA(sp, cs, R2P2_FMA(r2p2_neg(cp), sn, R2P2_FMA(sp, ccs, ssn)));
@@ -292,7 +295,7 @@ R2P2_HD void r2p2_sincos(double x, const double* tab, double* s, double* c, int*
         const double xx = R2P2_MUL(xr, xr);
         const double sp = R2P2_FMA(R2P2_MUL(xr, xx), R2P2_FMA(xx, R2P2_S_SN5, R2P2_S_SN3), xr);
         const double cp = R2P2_MUL(xx, R2P2_FMA(xx, R2P2_FMA(xx, R2P2_S_CS6, R2P2_S_CS4), R2P2_S_CS2));
-        const int ti = r2p2_lo32(u) * 4;
+        const int ti = r2p2_lo32(u) * rowlen;
         const double sn = tab[ti], ssn = tab[ti + 1], cs = tab[ti + 2], ccs = tab[ti + 3];
         const double cor = R2P2_FMA(r2p2_neg(sp), sn, R2P2_FMA(r2p2_neg(cp), cs, R2P2_FMA(r2p2_neg(sp), ssn, ccs)));
         dc = R2P2_ADD(cs, cor);
@@ -312,6 +315,8 @@ R2P2_HD void r2p2_sincos(double x, const double* tab, double* s, double* c, int*
     *s = rs;
     *c = rc;
 }
+
+R2P2_HD void r2p2_sincos(double x, const double* tab, double* s, double* c, int* ok) { r2p2_sincos_rs(x, tab, 4, s, c, ok); }
 
 // ---------------------------------------------------------------------------------------------
 // own atan2 / exp / tanh (deterministic, <= 2 ulp; not libm-identical)
