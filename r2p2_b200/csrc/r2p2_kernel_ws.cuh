@@ -65,7 +65,8 @@ template <int LPR, class NET, bool EXTRA = false>
 __global__ void __launch_bounds__((NET::kLayers > 0 && !NET::kSmemWeights) ? kRegBlock : kMaxBlock, 1) episode_kernel_ws(const __grid_constant__ KParams p) {
     static_assert(LPR >= 2 && LPR <= 16, "warp-synchronous kernel: 2..16 lanes per robot");
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int NR = (int)blockDim.x / LPR;                 // robots in flight per CTA
+    const int NRC = (int)blockDim.x / LPR;                // robots in flight per CTA
+    const int NR = buf_stride(LPR, NRC);                  // stride of the activation buffers
     constexpr int RPW = 32 / LPR;                         // robots per warp
     constexpr unsigned FULL = 0xffffffffu;
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw);
@@ -80,7 +81,7 @@ __global__ void __launch_bounds__((NET::kLayers > 0 && !NET::kSmemWeights) ? kRe
     double* s_gen = s_bufB + (size_t)p.maxw * NR;         // [NR][G], only when p.w_in_smem
     // per-robot windows of the hot plane (see below)
     const int win_words = p.win_ww * p.win_wb;
-    uint32_t* s_win = reinterpret_cast<uint32_t*>(s_gen + (p.w_in_smem ? (size_t)NR * smem_gstride(LPR, p.G) : 0));
+    uint32_t* s_win = reinterpret_cast<uint32_t*>(s_gen + (p.w_in_smem ? (size_t)NRC * smem_gstride(LPR, p.G) : 0));
 
     const uint32_t mb = smem_u32(mbar);
     if (threadIdx.x == 0) {

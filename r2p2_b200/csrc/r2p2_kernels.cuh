@@ -952,7 +952,7 @@ __device__ __forceinline__ bool pid_control(const KParams& p, const StageView& s
 //   [.., +18304)                   tanh table (tanh_in_smem only)
 //   [.., +plane_bytes)             wall plane      (SMEM_STAGE only)
 //   [.., +plane_bytes)             level-50 plane  (SMEM_STAGE and has50 only)
-//   [.., +2*maxw*NR*8)             MLP / sonar buffers A and B, element i of robot slot r at [i*NR + r]; NR = blockDim.x / LPR
+//   [.., +2*maxw*NR*8)             MLP / sonar buffers A and B, element i of robot slot r at [i*NR + r]; NR = buf_stride(LPR, blockDim.x / LPR)
 //   [.., +NR*GS*8)                 genomes of the robots in flight (w_in_smem only), row r at [r*GS], GS = smem_gstride(LPR, G)
 //   [.., +NR*win_words*4)          per-robot windows of the hot plane (warp-synchronous kernel)
 // Row stride (doubles) of the genome copies in shared memory.  The groups of a warp read the same weight columns of
@@ -961,12 +961,19 @@ __device__ __forceinline__ bool pid_control(const KParams& p, const StageView& s
 // LPR modulo 16 spreads the 32 / LPR groups evenly over the 32 banks.
 __host__ __device__ inline int smem_gstride(int lpr, int G) { return G + ((lpr - G) % 16 + 16) % 16; }
 
+// Stride (doubles) of the activation buffers, element i of robot slot r at [i * stride + r].  With several lanes per robot
+// the lanes of a group touch DIFFERENT elements of ONE robot (ray leaders writing their distances, the 25/dst pass,
+// neurons writing their outputs): at a stride that is a multiple of 16 doubles all of them hit one bank pair (config E,
+// 64 robots per CTA: 16 wavefronts per such instruction, a fifth of the kernel's shared-memory wavefronts).  An odd stride
+// puts consecutive elements two banks apart.  One lane per robot: lanes are consecutive slots, no padding needed.
+__host__ __device__ inline int buf_stride(int lpr, int robots) { return lpr == 1 ? robots : (robots | 1); }
+
 __host__ __device__ inline size_t episode_smem_bytes(int block, int lpr, bool smem_stage, uint32_t plane_bytes, int has50, int maxw, int w_in_smem, int G,
                                                      int win_words = 0, int tanh_in_smem = 0) {
     size_t n = 16 + kSinCosPadLen * 8 + 720 * 8;
     if (tanh_in_smem) n += (size_t)R2P2_TANH_NINT * R2P2_TANH_ROW * 8;
     if (smem_stage) n += (size_t)plane_bytes * (has50 ? 2 : 1);
-    n += (size_t)2 * maxw * (block / lpr) * 8;
+    n += (size_t)2 * maxw * buf_stride(lpr, block / lpr) * 8;
     if (w_in_smem) n += (size_t)(block / lpr) * smem_gstride(lpr, G) * 8;
     if (win_words) n += (size_t)(block / lpr) * (size_t)win_words * 4;
     return n;
@@ -1208,7 +1215,8 @@ struct FixedMlp<LPR, GenericNet> {
 template <int LPR, bool SMEM_STAGE, class NET, bool EXTRA = false>
 __global__ void __launch_bounds__((NET::kLayers > 0 && !NET::kSmemWeights) ? kRegBlock : kMaxBlock, 1) episode_kernel(const __grid_constant__ KParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int NR = (int)blockDim.x / LPR;                 // robots in flight per CTA
+    const int NRC = (int)blockDim.x / LPR;                // robots in flight per CTA
+    const int NR = buf_stride(LPR, NRC);                  // stride of the activation buffers
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw);
     double* s_tab = reinterpret_cast<double*>(smem_raw + 16);
     double* s_crx = s_tab + kSinCosPadLen;
