@@ -110,3 +110,21 @@ def test_history_log_records(tmp_path):
     assert buf.getvalue() == "\n\n[1.5]: [0.1,0.2]\n\n[1.5]: [0.5,0.6]"
     best = record_history([np.array([1.0, 2.0])], [np.float64(2.25)], buf, best)       # numpy inputs print like the reference's lists
     assert best == 2.25 and buf.getvalue().endswith("\n\n[2.25]: [1.0,2.0]")
+
+
+def test_lanes_per_robot_table_matches_the_committed_sweep():
+    """r2p2_lprtab.h (what choose_lpr looks up) is generated from profiles/r02_lpr_sweep.json (tools/sweep_lpr.py on a B200):
+    the committed header must be the generator's output for the committed measurements, and every entry the fastest
+    mapping of its row."""
+    import json, re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    table = json.load(open(os.path.join(root, "profiles", "r02_lpr_sweep.json")))["table"]
+    hdr = open(os.path.join(root, "r2p2_b200", "csrc", "r2p2_lprtab.h")).read()
+    rows = re.findall(r"\{(\d+), \{([0-9, ]+)\}\}", hdr)
+    assert len(rows) == 3
+    for (rmax, best), shape in zip(rows, ("C3", "C1", "E")):
+        best = [int(b) for b in best.split(",")]
+        for col, lpr in enumerate(best):
+            row = table["%s/%d" % (shape, 1024 << col)]
+            times = {int(k): v for k, v in row.items() if k.isdigit()}
+            assert lpr == row["best"] == min(times, key=times.get), (shape, 1024 << col)
