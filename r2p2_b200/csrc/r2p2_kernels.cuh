@@ -42,7 +42,8 @@ __device__ unsigned long long g_robot_cycles[65536 * 12];   // per robot, per ph
 #ifndef R2P2_RING_T
 #define R2P2_RING_T 8           // one-lane mapping: above this many rings per converged warp every lane scans its own (measured: 4, 8, 12, 16)
 #endif
-// Threads per CTA are chosen per launch (128, 256 or 512; blockDim.x): the 128-register instances hold 16 warps per SM
+// Threads per CTA are chosen per launch (128, 256, 512, or one CTA per SM of 32 * ceil(warps / SMs) threads for a
+// population that is resident at once; blockDim.x): the 128-register instances hold 16 warps per SM
 // whatever the split, and one large CTA stages the read-only tables once per SM instead of four times -- the shared
 // memory that frees goes to L1, where the genomes of the robots in flight live (measured: config E 130 -> 122 ms per 200
 // ticks, scenario-track 62 -> 57 ms).  The register-weight instances (up to 242 registers) run 128 threads.
@@ -1164,6 +1165,8 @@ __device__ __forceinline__ void lane_mlp(const double* __restrict__ wt, double* 
 // in the [P][G] array -- and each neuron keeps the reference's ordered chain acc = fma(h_i, w_ij, acc), i ascending.
 // (The first version exchanged activations with __shfl_sync: two SHFL per double and input were 11 % of the synthetic
 // sweep's instructions.)
+// (Measured on config E: keeping only the two small layers' weights (144 of 656) in shared memory, at the price of the tanh
+// table's place there, is 3.5 % slower than reading everything through L2.)
 // (Measured on config E, where the genomes of the robots in flight fit neither shared memory nor L1 and every batch of
 // weight loads waits for L2 -- 9 % of the run in long-scoreboard stalls: prefetch.global.L1 of the next batch's lines, one
 // per lane and batch, made the run 20 % slower.)
