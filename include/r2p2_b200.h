@@ -212,10 +212,13 @@ int r2p2_set_trace(r2p2_handle h, int32_t enable, int32_t T_max);
 int r2p2_read_trace(r2p2_handle h, int32_t T, double* pose, double* dst, int32_t* hitk, int32_t* hitpx,
                     uint32_t* nsamp, uint32_t* ncoll);
 /* The collide() calls of each tick, for the collision lines of the robot log (Robot.collide, r2p2/robot.py:170-179,
- * called from __update_position, r2p2/robot.py:211-253): cinfo [T][P][4] = code, wx, wy, b.
+ * called from __update_position, r2p2/robot.py:211-253), and the controller's answer, for the controller's own log
+ * (log_step, r2p2/controllers/neurocontroller.py:97-98, inspyred.py:102-103): cinfo [T][P][6] = code, wx, wy, b, out0, out1.
  * code bit 0: wall collision at the proposed position (wx, wy) (robot.py:212); bits 1-4: map-border case 1..8 in
  * the order of robot.py:222-247 -- spot (W, b), (W, H), (W, 0), (0, b), (0, H), (0, 0), (b, H), (b, 0); bit 5: the
- * crash-radius / level-50 test fired and the robot went back to its last position, which is the spot (robot.py:249-252). */
+ * crash-radius / level-50 test fired and the robot went back to its last position, which is the spot (robot.py:249-252).
+ * (out0, out1): what control() returned in that tick, before Robot.control's speed clamp (robot.py:385-387) -- for the
+ * neuro controller (output 0 after its > 180 wrap, output 1); zeros for a tick in which control() did not get that far. */
 int r2p2_read_trace_collisions(r2p2_handle h, int32_t T, double* cinfo);
 
 /* ---- path planner's cost grid ------------------------------------------------------------------- */

@@ -170,7 +170,7 @@ class Oracle:
             out["pose"] = np.zeros((T, P, 5)); out["dst"] = np.zeros((T, P, R))
             out["hitk"] = np.full((T, P, R), -1, dtype=np.int32); out["hitpx"] = np.full((T, P, R, 2), -1, dtype=np.int32)
             out["nsamp"] = np.zeros((T, P, R), dtype=np.uint32); out["ncoll"] = np.zeros((T, P), dtype=np.uint32)
-            out["cinfo"] = np.zeros((T, P, 4))
+            out["cinfo"] = np.zeros((T, P, 6))
             ptrs = [out[k].ctypes.data for k in ("pose", "dst", "hitk", "hitpx", "nsamp", "ncoll", "cinfo")]
         rc = self.lib.orc_run(C.byref(cfg), st.ctypes.data, genomes.ctypes.data, P, int(T), int(threads), *ptrs)
         if rc != 0:

@@ -457,6 +457,7 @@ static int orc_tick(const orc_cfg* c, orc_robot* rb, const double* genome, const
         if (c->ctrl_kind != ORC_CTRL_PID) { rb->speed = 0; rb->omega = 0; }
         return 0;
     }
+    if (tr && tr->cinfo) { tr->cinfo[4] = v; tr->cinfo[5] = w; }        /* what the controller's log_step records (neurocontroller.py:94-98) */
     if (fabs(v) > c->max_speed) v = v / fabs(v) * c->max_speed;
     rb->speed = v; rb->omega = w;
     rb->theta = rb->theta + rb->omega * c->delta;
@@ -523,7 +524,7 @@ static void* orc_worker(void* arg) {
             tr.hitk = j->tr_hitk ? j->tr_hitk + row * R : NULL;
             tr.hitpx = j->tr_hitpx ? j->tr_hitpx + row * R * 2 : NULL;
             tr.nsamp = j->tr_nsamp ? j->tr_nsamp + row * R : NULL;
-            tr.cinfo = j->tr_cinfo ? j->tr_cinfo + row * 4 : NULL;
+            tr.cinfo = j->tr_cinfo ? j->tr_cinfo + row * 6 : NULL;      /* code, wx, wy, b (orc_move); controller outputs (orc_tick) */
             const uint32_t ncoll0 = rb->ncollide;
             int alive = 0;
             if (!(rb->flags & (ORC_F_FAULT | ORC_F_DONE))) {

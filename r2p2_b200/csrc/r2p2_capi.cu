@@ -967,7 +967,7 @@ static int run_range(r2p2_handle h, int32_t T, double delta, double delta_ctrl, 
             CK(cudaMemsetAsync(h->tr_hitpx, 0xff, rows * h->R * 2 * sizeof(int32_t), h->stream));
             CK(cudaMemsetAsync(h->tr_nsamp, 0, rows * h->R * sizeof(uint32_t), h->stream));
             CK(cudaMemsetAsync(h->tr_ncoll, 0, rows * sizeof(uint32_t), h->stream));
-            CK(cudaMemsetAsync(h->tr_cinfo, 0, rows * 4 * sizeof(double), h->stream));
+            CK(cudaMemsetAsync(h->tr_cinfo, 0, rows * kCinfoRow * sizeof(double), h->stream));
         }
         kp.tr_pose = h->tr_pose; kp.tr_dst = h->tr_dst; kp.tr_hitk = h->tr_hitk; kp.tr_hitpx = h->tr_hitpx;
         kp.tr_nsamp = h->tr_nsamp; kp.tr_ncoll = h->tr_ncoll; kp.tr_cinfo = h->tr_cinfo;
@@ -1199,7 +1199,7 @@ int r2p2_move(r2p2_handle h, const double* commands, double delta) {
         const size_t rows = (size_t)h->P;
         CK(cudaMemsetAsync(h->tr_pose, 0, rows * 5 * sizeof(double), h->stream));
         CK(cudaMemsetAsync(h->tr_ncoll, 0, rows * sizeof(uint32_t), h->stream));
-        CK(cudaMemsetAsync(h->tr_cinfo, 0, rows * 4 * sizeof(double), h->stream));
+        CK(cudaMemsetAsync(h->tr_cinfo, 0, rows * kCinfoRow * sizeof(double), h->stream));
         kp.tr_pose = h->tr_pose; kp.tr_dst = h->tr_dst; kp.tr_hitk = h->tr_hitk; kp.tr_hitpx = h->tr_hitpx;
         kp.tr_nsamp = h->tr_nsamp; kp.tr_ncoll = h->tr_ncoll; kp.tr_cinfo = h->tr_cinfo;
     }
@@ -1359,7 +1359,7 @@ int r2p2_set_trace(r2p2_handle h, int32_t enable, int32_t T_max) {
     const size_t rows = (size_t)T_max * h->P;
     CK(dalloc(&h->tr_pose, rows * 5)); CK(dalloc(&h->tr_dst, rows * h->R));
     CK(dalloc(&h->tr_hitk, rows * h->R)); CK(dalloc(&h->tr_hitpx, rows * h->R * 2));
-    CK(dalloc(&h->tr_nsamp, rows * h->R)); CK(dalloc(&h->tr_ncoll, rows)); CK(dalloc(&h->tr_cinfo, rows * 4));
+    CK(dalloc(&h->tr_nsamp, rows * h->R)); CK(dalloc(&h->tr_ncoll, rows)); CK(dalloc(&h->tr_cinfo, rows * kCinfoRow));
     h->trace = true; h->trace_T = T_max; h->trace_P = h->P; h->trace_R = h->R;
     return R2P2_OK;
 }
@@ -1386,7 +1386,7 @@ int r2p2_read_trace_collisions(r2p2_handle h, int32_t T, double* cinfo) {
     if (T < 0 || T > h->trace_T) return fail(h, R2P2_E_ARG, "T out of range");
     if (!cinfo) return fail(h, R2P2_E_ARG, "cinfo is NULL");
     ON_DEVICE(h);
-    CK(cudaMemcpyAsync(cinfo, h->tr_cinfo, (size_t)T * h->trace_P * 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(cinfo, h->tr_cinfo, (size_t)T * h->trace_P * kCinfoRow * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return R2P2_OK;
 }

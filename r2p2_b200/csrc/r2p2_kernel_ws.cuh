@@ -355,6 +355,10 @@ __global__ void __launch_bounds__((NET::kLayers > 0 && !NET::kSmemWeights) ? kRe
             } else {
                 v = gen[0]; w = gen[1];
             }
+            if (tracing && live && g.sub == 0) {           // the controller's return value, as its log_step records it
+                double* ci = p.tr_cinfo + trow * kCinfoRow;
+                ci[4] = v; ci[5] = w;
+            }
             if (live) {
                 if (r2p2_fabs(v) > p.max_speed) v = R2P2_MUL(R2P2_DIV(v, r2p2_fabs(v)), p.max_speed);   // robot.py:386-387
                 speed = v; omega = w;
@@ -483,7 +487,7 @@ __global__ void __launch_bounds__((NET::kLayers > 0 && !NET::kSmemWeights) ? kRe
                     double* q = p.tr_pose + trow * 5;
                     q[0] = x; q[1] = y; q[2] = theta; q[3] = speed; q[4] = omega;
                     p.tr_ncoll[trow] = ncollide - ncollide0;
-                    double* ci = p.tr_cinfo + trow * 4;
+                    double* ci = p.tr_cinfo + trow * kCinfoRow;
                     ci[0] = (double)ccode; ci[1] = ccx; ci[2] = ccy; ci[3] = cbv;
                 }
             }

@@ -52,6 +52,7 @@ __device__ unsigned long long g_robot_cycles[65536 * 12];   // per robot, per ph
 #endif
 constexpr int kMaxBlock = R2P2_MAXBLOCK;   // threads per SM of the shared-memory / run-time-shaped instances (registers per thread = 65536 / this)
 constexpr int kRegBlock = 128;
+constexpr int kCinfoRow = 6;          // doubles per tick and robot in the collision / controller trace
 // sin/cos table in shared memory: rows (sn, ssn, cs, ccs) padded to 5 doubles.  Lanes with different angles read
 // different rows; at glibc's 4 doubles (8 words) per row they fall on 4 bank groups -- 8-way conflicts on each of the 8
 // loads of a sincos (ncu: 57 % of the one-lane kernel's shared-load wavefronts were conflicts, the LSU pipe 66 % busy);
@@ -114,7 +115,8 @@ struct KParams {
     double goal_x, goal_y, goal_r;
     uint32_t* goal_tick;        //   [P] ticks completed when the predicate first held, 0xffffffff = never
     int skip_sense;             // r2p2_move: the tick starts at the controller output (command in `genomes`), no sensor sweep
-    double* tr_cinfo;           // [T][P][4]: collide() calls of the tick (code, wall spot x, y, border coordinate), see r2p2_read_trace_collisions
+    double* tr_cinfo;           // [T][P][6]: collide() calls of the tick (code, wall spot x, y, border coordinate) and the controller's
+                                //            answer before the speed clamp (what its own log records), see r2p2_read_trace_collisions
     // Sequential_PID_Controller (R2P2_CTRL_PID): per-robot controller state, SoA [P]; the goal stack [R2P2_PID_MAX_GOALS][P]
     double *pid_acc_ang, *pid_acc_dist, *pid_last_ang, *pid_last_dist, *pid_target;
     int32_t *pid_state, *pid_backing, *pid_ngoals;
@@ -1490,6 +1492,10 @@ __global__ void __launch_bounds__((NET::kLayers > 0 && !NET::kSmemWeights) ? kRe
                 else { v = gen[0]; w = gen[1]; }
             }
             PT(2)
+            if (tracing && g.sub == 0) {                   // the controller's return value, as its log_step records it
+                double* ci = p.tr_cinfo + trow * kCinfoRow;
+                ci[4] = v; ci[5] = w;
+            }
             // Robot.control clamp (robot.py:386-387)
             if (r2p2_fabs(v) > p.max_speed) v = R2P2_MUL(R2P2_DIV(v, r2p2_fabs(v)), p.max_speed);
             speed = v; omega = w;
@@ -1623,7 +1629,7 @@ __global__ void __launch_bounds__((NET::kLayers > 0 && !NET::kSmemWeights) ? kRe
                 double* q = p.tr_pose + trow * 5;
                 q[0] = x; q[1] = y; q[2] = theta; q[3] = speed; q[4] = omega;
                 p.tr_ncoll[trow] = ncollide - ncollide0;
-                double* ci = p.tr_cinfo + trow * 4;
+                double* ci = p.tr_cinfo + trow * kCinfoRow;
                 ci[0] = (double)ccode; ci[1] = ccx; ci[2] = ccy; ci[3] = cbv;
             }
         }

@@ -255,7 +255,7 @@ class BatchSim:
                "hitpx": np.empty((T, P, R, 2), dtype=np.int32), "nsamp": np.empty((T, P, R), dtype=np.uint32),
                "ncoll": np.empty((T, P), dtype=np.uint32)}
         self._ck(self._L.r2p2_read_trace(self._h, int(T), *[out[k].ctypes.data for k in ("pose", "dst", "hitk", "hitpx", "nsamp", "ncoll")]))
-        out["cinfo"] = np.empty((T, P, 4))        # collide() calls per tick (code, wall spot, border coordinate): r2p2_b200.logs
+        out["cinfo"] = np.empty((T, P, 6))        # collide() calls per tick (code, wall spot, border coordinate) + the controller's answer: r2p2_b200.logs
         self._ck(self._L.r2p2_read_trace_collisions(self._h, int(T), out["cinfo"].ctypes.data))
         return out
 

@@ -396,6 +396,32 @@ def gen_logs(E):
         json.dump(out, fp, indent=1)
 
 
+def gen_ctrl_logs(E):
+    """The controllers' own logs (log_step: neurocontroller.py:97-98 -> ../logs/neuro.log, inspyred.py:102-103 ->
+    ../logs/inspyred.log) for two episodes -> tests/golden/ctrl_logs.json.  Lines carry time.time(); everything else is kept."""
+    out = {}
+
+    def run(name, stage, robot_json, ctrl, T, genome, kind, logfile, layers=(), delta=0.1):
+        env = E.load_env(stage)
+        with contextlib.redirect_stdout(io.StringIO()):
+            r = E.make_robot(robot_json, ctrl)
+        cfg = json.load(open(os.path.join("..", "conf", robot_json)))
+        for t in range(T):
+            r.update(env, delta, True)
+        ctrl.log.flush()
+        out[name] = {"text": open(os.path.join("..", "logs", logfile)).read(), "robot_json": cfg, "stage": stage, "T": T, "kind": kind,
+                     "layers": list(layers), "delta": delta, "genome": [float(g) for g in genome], "identifier": r.identifier,
+                     "final": [float(r.x), float(r.y), float(r.orientation)]}
+        print("ctrl log", name, len(out[name]["text"]), "bytes,", out[name]["text"].count("Odom:"), "lines")
+
+    c = np.random.RandomState(7).uniform(-1, 1, 18) * 0.05
+    run("linear_omni", "track_2.png", "robot_omni.json", E.linear_controller(c), 60, c, "linear", "inspyred.log")
+    g = np.random.RandomState(21).uniform(-1, 1, 156)
+    run("neuro_track", "track_2.png", "robot-neuro.json", E.neuro_controller(g, [10, 7, 4]), 120, g, "neuro", "neuro.log", layers=[5, 10, 7, 4, 2])
+    with open(os.path.join(OUT, "ctrl_logs.json"), "w") as fp:
+        json.dump(out, fp, indent=1)
+
+
 def gen_goal(E):
     """is_at_goal of the reference's Sequential_PID_Controller (controllers/pid_controller.py:207-213) evaluated on the pose
     after every tick of two reference episodes, for several goal points -> tests/golden/goal.json."""
@@ -543,6 +569,9 @@ def main():
         if "--logs-only" in sys.argv:
             gen_logs(E)
             return
+        if "--ctrl-logs-only" in sys.argv:
+            gen_ctrl_logs(E)
+            return
         if "--noise-only" in sys.argv:
             gen_noisy_episodes(E)
             return
@@ -553,6 +582,7 @@ def main():
         gen_noisy_episodes(E)
         gen_act_episodes(E)
         gen_logs(E)
+        gen_ctrl_logs(E)
         gen_goal(E)
         gen_grids(E)
         gen_host_controllers(E)
