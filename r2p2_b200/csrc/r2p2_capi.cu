@@ -326,7 +326,7 @@ int launch_kernel(r2p2_handle h, KERN kern, const KParams& kp_in, size_t smem, i
     ctas = std::max<long long>(1, std::min<long long>(ctas, (long long)occ * h->sm_count));   // persistent: the work counter feeds the rest
     cudaStream_t st = h->slot ? h->aux_stream : h->stream;
     // Time slicing (warp-synchronous kernel, see KParams): only when the population runs in several waves, and then fine
-    // enough that the launch ends within ~1/24 of its length of the ideal; slices of at least 25 ticks (state and window
+    // enough that the launch ends within ~1/48 of its length of the ideal; slices of at least 25 ticks (state and window
     // are re-read per slice).  R2P2_NO_SLICES=1: off (A/B measurements).
     kp.n_slices = 0; kp.slice_T = 0; kp.slice_done = nullptr;
     static const bool no_slices = [] { const char* e = getenv("R2P2_NO_SLICES"); return e && e[0] == '1'; }();
@@ -334,7 +334,7 @@ int launch_kernel(r2p2_handle h, KERN kern, const KParams& kp_in, size_t smem, i
         const long long warps = ((long long)(kp.rb_end - kp.rb_begin) * LPR + 31) / 32, cap = (long long)occ * h->sm_count * (kp.block / 32);
         if (warps > cap) {
             const double waves = (double)warps / (double)cap;
-            int n = std::min((int)std::ceil(24.0 / waves), kp.T / 25);
+            int n = std::min((int)std::ceil(48.0 / waves), kp.T / 25);
             if (n >= 2) {
                 kp.slice_T = (kp.T + n - 1) / n;
                 kp.n_slices = (kp.T + kp.slice_T - 1) / kp.slice_T;
