@@ -557,7 +557,6 @@ int r2p2_version(void) { return 100; }
 const char* r2p2_last_error(r2p2_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
 int r2p2_create(int device, r2p2_handle* out) {
-    r2p2_handle h = nullptr;
     if (!out) return fail(nullptr, R2P2_E_ARG, "out is NULL");
     *out = nullptr;
     int n = 0;
@@ -571,7 +570,6 @@ int r2p2_create(int device, r2p2_handle* out) {
     if (prop.major != 10)
         return fail(nullptr, R2P2_E_NODEV, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
     r2p2_sim* s = new r2p2_sim();
-    h = s;
     s->device = device;
     s->sm_count = prop.multiProcessorCount;
     s->smem_optin = prop.sharedMemPerBlockOptin;
